@@ -1,0 +1,114 @@
+/* ocrpp.h - C ABI of the B200-native OCR post-processing library (libocrpp.so).
+ *
+ * This is the drop-in boundary for the post-processing hot path of DYJNG/PyTorchOCR
+ * (R = the reference tree). Each entry point replaces one native/numpy boundary of the
+ * reference and is what a reference-side binding (ctypes stub) would bind:
+ *
+ *   ocrpp_ctc_greedy        <- R/pytocr/postprocess/rec_postprocess.py:77-89 (+ decode :35-59)
+ *   ocrpp_db_postprocess    <- R/pytocr/postprocess/db_postprocess_fast/src/db_postprocess.cpp:319-325
+ *                              (`db_postprocess(pred, bitmap, box_thresh, unclip_ratio, src_w, src_h,
+ *                              use_padding_resize)`, pybind11 :362-370) plus the thresholding that
+ *                              precedes it, R/pytocr/postprocess/db_postprocess.py:43-46
+ *   ocrpp_pse_postprocess   <- R/pytocr/postprocess/pse_postprocess_fast/pse.pyx:66 `pse(kernels, min_area)`
+ *                              plus R/pytocr/postprocess/pse_postprocess.py:34-45 (upsample/sigmoid/threshold)
+ *                              and :65-105 (generate_box)
+ *   ocrpp_pan_postprocess   <- R/pytocr/postprocess/pan_postprocess_fast/pa.pyx:99 `pa(kernels, emb, min_area)`
+ *                              plus R/pytocr/postprocess/pan_postprocess.py:36-51 and :73-113
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, scalars. No torch / C++ types. Every function returns an int status
+ *     (OCRPP_OK == 0); ocrpp_last_error() gives the message of the calling thread's last failure.
+ *     No exceptions cross the boundary.
+ *   - batch level and stream ordered: all pointers named *_dev are DEVICE pointers on the current
+ *     CUDA device; work is enqueued on `stream` (a cudaStream_t passed as void*) and the call
+ *     returns without synchronising. Results are valid after the stream is synchronised.
+ *   - caller-owned buffers: outputs have fixed capacity plus per-item counts; scratch comes from a
+ *     caller-provided workspace whose size the matching *_workspace_bytes() call returns.
+ *   - there is NO CPU path: without a CUDA device every compute entry point fails.
+ */
+#ifndef OCRPP_H_
+#define OCRPP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCRPP_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define OCRPP_API __attribute__((visibility("default")))
+#else
+#define OCRPP_API
+#endif
+
+/* status codes */
+#define OCRPP_OK 0
+#define OCRPP_ERR_INVALID_ARGUMENT 1
+#define OCRPP_ERR_CUDA 2
+#define OCRPP_ERR_WORKSPACE_TOO_SMALL 3
+
+/* element types of input maps */
+#define OCRPP_F32 0
+#define OCRPP_F16 1
+
+/* per-image status bits written to `status_out_dev` by the detection entry points */
+#define OCRPP_IMG_RUN_OVERFLOW 1        /* more runs than `max_runs` - result of that image is invalid; retry with a larger max_runs */
+#define OCRPP_IMG_CANDIDATES_TRUNCATED 2 /* more candidates than `max_candidates`; the reference keeps cv2's first 1000, we keep ours */
+#define OCRPP_IMG_VALUE_OUT_OF_RANGE 4   /* a map value was NaN/Inf or |v| > 1024: fixed-point score accumulation not valid */
+
+OCRPP_API int ocrpp_abi_version(void);
+OCRPP_API const char* ocrpp_last_error(void);
+
+/* Number of kernel launches issued by this library since load / since the last reset
+ * (bench.py reports it as gpu_launches). */
+OCRPP_API int64_t ocrpp_launch_count(void);
+OCRPP_API void ocrpp_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * CTC greedy decode. probs element (t,b,c) is at probs_dev[t*stride_t + b*stride_b + c]
+ * (element strides; class stride is 1). For every line b:
+ *   idx_out_dev[b*T + 0..len)  kept class ids  (argmax per step, first maximum wins; blank 0
+ *                              dropped; a step equal to the previous RAW argmax dropped)
+ *   prob_out_dev[b*T + 0..len) their max-probabilities (float32)
+ *   len_out_dev[b]             number kept
+ *   conf_out_dev[b]            float32 mean of the kept probabilities, NaN when none kept
+ *   raw_idx_out_dev            optional [B*T] raw argmax per step (may be NULL)
+ * ------------------------------------------------------------------------------------------- */
+OCRPP_API int ocrpp_ctc_greedy(const void* probs_dev, int dtype, int T, int B, int C,
+                     int64_t stride_t, int64_t stride_b,
+                     int32_t* idx_out_dev, float* prob_out_dev, int32_t* len_out_dev,
+                     float* conf_out_dev, int32_t* raw_idx_out_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DB / DB++ box extraction for a batch of probability maps.
+ *   maps_dev: image n, pixel (y,x) at maps_dev[n*stride_n + y*stride_h + x] (element strides).
+ *   src_wh_dev: int32 [N,2] = (src_w, src_h) of every image (shape_list columns 1,0).
+ *   max_candidates: output capacity per image (reference constant: 1000).
+ *   max_runs: capacity of the per-image run table (foreground + background runs);
+ *             0 selects the worst case H*(W+1).
+ * outputs (device):
+ *   boxes_out_dev   int16 [N,max_candidates,4,2]  TL,TR,BR,BL, rescaled to (src_w,src_h), roundf, clamped
+ *   scores_out_dev  float [N,max_candidates]      BoxScore of every kept box (the reference wrapper
+ *                                                 discards it and reports 1.0)
+ *   counts_out_dev  int32 [N]
+ *   status_out_dev  int32 [N]                     OCRPP_IMG_* bits
+ *   boxes_f_out_dev float [N,max_candidates,4,2]  optional (NULL ok): pre-rounding rescaled corners
+ *   labels_dbg_dev  int32 [N,H,W]                 optional (NULL ok): 8-connected foreground labels,
+ *                                                 id = 1 + rank of the component's first raster pixel
+ * ------------------------------------------------------------------------------------------- */
+OCRPP_API size_t ocrpp_db_workspace_bytes(int N, int H, int W, int max_runs);
+OCRPP_API int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int H, int W,
+                         int64_t stride_n, int64_t stride_h, const int32_t* src_wh_dev,
+                         float thresh, float box_thresh, float unclip_ratio,
+                         int max_candidates, int max_runs,
+                         int16_t* boxes_out_dev, float* scores_out_dev, int32_t* counts_out_dev,
+                         int32_t* status_out_dev, float* boxes_f_out_dev, int32_t* labels_dbg_dev,
+                         void* workspace_dev, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCRPP_H_ */

@@ -1,0 +1,92 @@
+"""GPU parity: CTC greedy decode through the C-ABI vs the CPU oracle (bit-exact strings, exact
+float32 confidences)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle.ctc_oracle import CTCLabelDecodeNumpy, CTCLabelDecodeOracle
+from pytorchocr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dict_path(tmp_path_factory):
+    return synth.write_char_dict(str(tmp_path_factory.mktemp("d") / "dict6623.txt"), 6623)
+
+
+def _ops(dict_path):
+    from pytorchocr_b200.postprocess import build_post_process
+    op = build_post_process({"name": "CTCLabelDecode", "character_dict_path": dict_path,
+                             "use_space_char": False, "cuda_speedup": True}, {"use_gpu": True})
+    return op, CTCLabelDecodeOracle(dict_path, False), CTCLabelDecodeNumpy(dict_path, False)
+
+
+def _same(a, b):
+    assert len(a) == len(b)
+    for (ta, ca), (tb, cb) in zip(a, b):
+        assert ta == tb
+        if math.isnan(cb):
+            assert math.isnan(ca)
+        else:
+            assert np.float32(ca) == np.float32(cb), (ca, cb)
+
+
+@pytest.mark.parametrize("T,B,C", [(80, 64, 6623), (80, 33, 6624), (81, 5, 6624), (1, 1, 6623),
+                                   (7, 3, 37), (40, 257, 97), (130, 4, 513)])
+def test_ctc_matches_oracle(dict_path, T, B, C):
+    import torch
+    op, oracle, _ = _ops(dict_path)
+    probs, _ = synth.ctc_probs_numpy(1234 + T + B + C, T, B, C)
+    got = op(torch.from_numpy(probs).cuda())
+    want = oracle(torch.from_numpy(probs))
+    _same(got, want)
+    assert any(len(t) for t, _ in want)
+
+
+def test_ctc_matches_reference_python_loop(dict_path):
+    """small case against the line-by-line numpy/pure-Python restatement"""
+    import torch
+    op, _, npy = _ops(dict_path)
+    probs, _ = synth.ctc_probs_numpy(99, 24, 9, 6623)
+    _same(op(torch.from_numpy(probs).cuda()), npy(torch.from_numpy(probs)))
+
+
+def test_ctc_ties_blank_lines_and_numpy_input(dict_path):
+    import torch
+    op, oracle, _ = _ops(dict_path)
+    T, B, C = 16, 6, 6623
+    rng = np.random.default_rng(5)
+    p = rng.random((T, B, C)).astype(np.float32) * 0.5
+    p[:, 0, 0] = 1.0                      # all blank -> empty string, NaN confidence
+    p[:, 1, 77] = 1.0                     # one repeated class -> single char
+    p[:, 2, 5] = 2.0; p[:, 2, 6000] = 2.0  # exact ties -> FIRST maximum (5)
+    p[::2, 3, 10] = 1.0; p[1::2, 3, 0] = 1.0   # char, blank, char, blank ... -> T/2 chars
+    p[:, 4, 6622] = 3.0                   # last class (tail elements)
+    p[:, 5, 1] = 3.0; p[3, 5, 2] = 4.0    # head elements
+    got = op(torch.from_numpy(p).cuda())
+    want = oracle(torch.from_numpy(p))
+    _same(got, want)
+    assert got[0][0] == "" and math.isnan(got[0][1])
+    assert len(got[1][0]) == 1 and len(got[3][0]) == T // 2
+    # numpy input is [B,T,C] (reference :80-82 leaves numpy untransposed)
+    got_np = op(np.ascontiguousarray(p.transpose(1, 0, 2)))
+    _same(got_np, want)
+    # tuple input, strided view, label passthrough
+    big = torch.from_numpy(p).cuda()
+    view = big[:, 1:5]
+    _same(op((None, view)), oracle(torch.from_numpy(p[:, 1:5])))
+    text, lab = op(big, label=[[1, 2, 0, 2], [0, 0]])
+    assert lab[0][0] == op.character[1] + op.character[2] + op.character[2] and lab[1][0] == ""
+
+
+def test_ctc_fp16(dict_path):
+    import torch
+    op, oracle, _ = _ops(dict_path)
+    probs, _ = synth.ctc_probs_numpy(7, 80, 17, 6623)
+    h = torch.from_numpy(probs).half()
+    got = op(h.cuda())
+    want = oracle(h.float())           # oracle sees the half values upcast
+    _same(got, want)
