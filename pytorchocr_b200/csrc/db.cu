@@ -1,0 +1,958 @@
+// DB / DB++ box extraction on sm_100a.
+//
+// Replaces, for a whole batch and without leaving the device:
+//   R/pytocr/postprocess/db_postprocess.py:43-46     D2H + `pred > thresh`
+//   R/pytocr/postprocess/db_postprocess_fast/src/db_postprocess.cpp:231-317  BoxesFromBitmap
+//     (cv::findContours RETR_LIST / CHAIN_APPROX_SIMPLE, minAreaRect, BoxScore :194-229,
+//      UnClip :34-64, GetMiniBoxes :159-192, rescale/roundf/clamp :303-311)
+//
+// cv::findContours is restated in connected-component terms (oracle/db_ccl_oracle.py):
+//   candidates = outer(C) for every 8-connected foreground component C
+//              + hole(C,h) for every 4-connected background region h that does not reach the frame
+//   points(outer C) = C,  points(hole C,h) = ring = pixels of C 4-adjacent to h
+//   fill(outer C)   = C + everything C encloses + "stair" pixels of the 4-connected fillPoly boundary
+//   fill(hole C,h)  = h + islands in h + ring + stair pixels
+//
+// Data layout: the map is read ONCE at full HBM rate into a 1-bit/pixel mask (db_binarize_kernel);
+// everything after works on horizontal RUNS of equal bits (a few thousand per image, L2 resident):
+// run union-find for both polarities, per-component reductions keyed by the root run, a parent tree
+// between foreground components and holes, per-component row extents -> convex hull -> min-area
+// rectangle -> unclip -> rectangle -> rescale. Scores are accumulated in 32.32 fixed point (exact for
+// probabilities >= 2^-9, order independent => deterministic). Algorithmic bytes per image:
+// H*W*sizeof(elem), the probability map, read once by db_binarize_kernel.
+#include "common.cuh"
+#include "geometry.cuh"
+
+namespace ocrpp {
+namespace {
+
+using geom::P2i;
+
+constexpr int kOutFlag = 1;
+constexpr double kFixScale = 4294967296.0;  // 2^32
+
+struct DbParams {
+  // input
+  const void* maps;
+  long long stride_n, stride_h;
+  const int32_t* src_wh;
+  int N, H, W, Wd, R, maxc;
+  float thresh, box_thresh, unclip_ratio;
+  // per-image workspace (index with n * count)
+  uint32_t* bits;        // [H*Wd]
+  int32_t* rowptr;       // [H+1]
+  uint16_t *run_xs, *run_xe, *run_yf;  // [R]
+  int32_t* par;          // [R]
+  int32_t *area, *xmin, *xmax, *ymax, *dmin, *dmax, *smin, *smax;  // [R]
+  long long* sum;        // [R]
+  int32_t* fcnt;         // [R]
+  long long* fsum;       // [R]
+  int32_t* xcnt;         // [R]
+  long long* xsum;       // [R]
+  int32_t *cpar, *cflag, *rowoff;  // [R]
+  int32_t *ext_l, *ext_r;          // [E]
+  P2i* hull;                       // [4*E]
+  int E;
+  int32_t *nruns, *ext_alloc, *imgflags, *ncand;  // [1] per image
+  int32_t* cand;         // [maxc]
+  int32_t* res_keep;     // [maxc]
+  int16_t* res_box;      // [maxc*8]
+  float* res_boxf;       // [maxc*8]
+  float* res_score;      // [maxc]
+  // outputs
+  int16_t* boxes_out;
+  float* scores_out;
+  int32_t* counts_out;
+  int32_t* status_out;
+  float* boxes_f_out;
+  int32_t* labels_dbg;
+};
+
+__device__ __forceinline__ long long to_fixed(float v) { return __float2ll_rn(v * 4294967296.0f); }
+
+template <typename T>
+__device__ __forceinline__ float load_px(const void* maps, long long off) {
+  return load_scalar<T>(reinterpret_cast<const T*>(maps) + off);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: threshold -> bit mask. One warp per image row; 128-bit loads, nibble/byte gather by shuffles.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct PxVec;
+template <>
+struct PxVec<float> {
+  static constexpr int kElems = 4;
+  __device__ static __forceinline__ unsigned bits(const uint4& u, float th, bool& bad) {
+    const float a = __uint_as_float(u.x), b = __uint_as_float(u.y), c = __uint_as_float(u.z), d = __uint_as_float(u.w);
+    bad |= !(fabsf(a) <= 1024.f) | !(fabsf(b) <= 1024.f) | !(fabsf(c) <= 1024.f) | !(fabsf(d) <= 1024.f);
+    return (a > th ? 1u : 0u) | (b > th ? 2u : 0u) | (c > th ? 4u : 0u) | (d > th ? 8u : 0u);
+  }
+};
+template <>
+struct PxVec<__half> {
+  static constexpr int kElems = 8;
+  __device__ static __forceinline__ unsigned bits(const uint4& u, float th, bool& bad) {
+    const float f[8] = {h2f_lo(u.x), h2f_hi(u.x), h2f_lo(u.y), h2f_hi(u.y), h2f_lo(u.z), h2f_hi(u.z), h2f_lo(u.w), h2f_hi(u.w)};
+    unsigned r = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      bad |= !(fabsf(f[k]) <= 1024.f);
+      r |= (f[k] > th ? 1u : 0u) << k;
+    }
+    return r;
+  }
+};
+
+constexpr int kBinWarps = 8;
+
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(kBinWarps * 32) db_binarize_kernel(DbParams p) {
+  const int n = blockIdx.y;
+  const int y = blockIdx.x * kBinWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (y >= p.H) return;
+  const T* row = reinterpret_cast<const T*>(p.maps) + n * p.stride_n + y * p.stride_h;
+  uint32_t* out = p.bits + ((size_t)n * p.H + y) * p.Wd;
+  bool bad = false;
+  if (kVec) {
+    constexpr int EPL = PxVec<T>::kElems;      // pixels per lane per load
+    constexpr int LPW = 32 / EPL;              // lanes per 32-bit word
+    constexpr int PPI = 32 * EPL;              // pixels per warp iteration
+    const uint4* vp = reinterpret_cast<const uint4*>(row);
+    constexpr int U = 4;
+    for (int x0 = 0; x0 < p.W; x0 += PPI * U) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int x = x0 + u * PPI + lane * EPL;
+        v[u] = x < p.W ? ldg_stream_u4(vp + (x / EPL)) : make_uint4(0, 0, 0, 0);  // W % EPL == 0 on this path
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int x = x0 + u * PPI + lane * EPL;
+        unsigned b = x < p.W ? PxVec<T>::bits(v[u], p.thresh, bad) : 0u;
+        unsigned w = b << (EPL * (lane % LPW));
+#pragma unroll
+        for (int o = 1; o < LPW; o <<= 1) w |= __shfl_xor_sync(0xffffffffu, w, o);
+        const int wi = (x0 + u * PPI) / 32 + lane / LPW;
+        if ((lane % LPW) == 0 && wi < p.Wd) out[wi] = w;
+      }
+    }
+  } else {
+    for (int x0 = 0; x0 < p.W; x0 += 32) {
+      const int x = x0 + lane;
+      float v = 0.f;
+      if (x < p.W) {
+        v = load_scalar<T>(row + x);
+        bad |= !(fabsf(v) <= 1024.f);
+      }
+      const unsigned w = __ballot_sync(0xffffffffu, x < p.W && v > p.thresh);
+      if (lane == 0) out[x0 >> 5] = w;
+    }
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&p.imgflags[n], OCRPP_IMG_VALUE_OUT_OF_RANGE);
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-wide exclusive scan of one int per thread; returns the exclusive prefix, total in *total
+// ------------------------------------------------------------------------------------------------
+__device__ int block_exclusive_scan(int v, int* total) {
+  __shared__ int warp_sums[32];
+  __shared__ int s_total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();  // protect warp_sums reuse across calls
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int ws = lane < nw ? warp_sums[lane] : 0;
+    int winc = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < nw) warp_sums[lane] = winc - ws;
+    if (lane == 31) s_total = winc;
+  }
+  __syncthreads();
+  *total = s_total;
+  return warp_sums[warp] + inc - v;
+}
+
+__device__ __forceinline__ unsigned valid_mask(int k, int W) {
+  const int rem = W - k * 32;
+  return rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+}
+
+// transitions inside word k of a row: bit i set <=> pixel 32k+i differs from pixel 32k+i-1
+// (bit 0 of word 0 is never a transition). `prev` = word k-1 (ignored for k == 0).
+__device__ __forceinline__ unsigned transitions(unsigned w, unsigned prev, int k, int W) {
+  const unsigned carry = k > 0 ? (prev >> 31) : (w & 1u);
+  return (w ^ ((w << 1) | carry)) & valid_mask(k, W);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: bit mask -> run table (both polarities, raster order). One CTA per image.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRunThreads = 512;
+
+__global__ void __launch_bounds__(kRunThreads) db_runs_kernel(DbParams p) {
+  extern __shared__ int s_rowcnt[];  // [H+1]
+  const int n = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kRunThreads / 32;
+  const uint32_t* bits = p.bits + (size_t)n * p.H * p.Wd;
+  int32_t* rowptr = p.rowptr + (size_t)n * (p.H + 1);
+
+  for (int y = warp; y < p.H; y += nw) {
+    int c = 0;
+    for (int k = lane; k < p.Wd; k += 32) {
+      const unsigned w = bits[(size_t)y * p.Wd + k];
+      const unsigned pw = k > 0 ? bits[(size_t)y * p.Wd + k - 1] : 0u;
+      c += __popc(transitions(w, pw, k, p.W));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) s_rowcnt[y] = c + 1;
+  }
+  __syncthreads();
+  // exclusive scan over rows: each thread owns a contiguous chunk
+  const int chunk = (p.H + kRunThreads - 1) / kRunThreads;
+  const int y0 = threadIdx.x * chunk, y1 = min(p.H, y0 + chunk);
+  int local = 0;
+  for (int y = y0; y < y1; ++y) local += s_rowcnt[y];
+  int total;
+  int base = block_exclusive_scan(local, &total);
+  for (int y = y0; y < y1; ++y) {
+    const int c = s_rowcnt[y];
+    s_rowcnt[y] = base;
+    base += c;
+  }
+  if (threadIdx.x == 0) s_rowcnt[p.H] = total;
+  __syncthreads();
+  if (total > p.R) {
+    if (threadIdx.x == 0) {
+      atomicOr(&p.imgflags[n], OCRPP_IMG_RUN_OVERFLOW);
+      p.nruns[n] = 0;
+    }
+    for (int y = threadIdx.x; y <= p.H; y += kRunThreads) rowptr[y] = 0;
+    return;
+  }
+  for (int y = threadIdx.x; y <= p.H; y += kRunThreads) rowptr[y] = s_rowcnt[y];
+  if (threadIdx.x == 0) p.nruns[n] = total;
+
+  const size_t ro = (size_t)n * p.R;
+  for (int y = warp; y < p.H; y += nw) {
+    const int rbase = s_rowcnt[y];
+    int carry = 0;  // starts seen in earlier words of this row
+    for (int k0 = 0; k0 < p.Wd; k0 += 32) {
+      const int k = k0 + lane;
+      unsigned w = 0, S = 0;
+      if (k < p.Wd) {
+        w = bits[(size_t)y * p.Wd + k];
+        const unsigned pw = k > 0 ? bits[(size_t)y * p.Wd + k - 1] : 0u;
+        S = transitions(w, pw, k, p.W) | (k == 0 ? 1u : 0u);
+      }
+      const int cnt = __popc(S);
+      int inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      int j = carry + inc - cnt;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+      while (S) {
+        const int b = __ffs(S) - 1;
+        S &= S - 1;
+        const int x = k * 32 + b;
+        const size_t r = ro + rbase + j;
+        const int fg = (w >> b) & 1u;
+        p.run_xs[r] = (uint16_t)x;
+        p.run_yf[r] = (uint16_t)(y | (fg << 15));
+        if (j > 0) p.run_xe[r - 1] = (uint16_t)(x - 1);
+        // per-run / per-component slots
+        p.par[r] = rbase + j;
+        p.area[r] = 0;
+        p.xmin[r] = 0x7fffffff; p.xmax[r] = -1; p.ymax[r] = -1;
+        p.dmin[r] = 0x7fffffff; p.dmax[r] = -0x7fffffff;
+        p.smin[r] = 0x7fffffff; p.smax[r] = -0x7fffffff;
+        p.sum[r] = 0; p.fcnt[r] = 0; p.fsum[r] = 0; p.xcnt[r] = 0; p.xsum[r] = 0;
+        p.cpar[r] = -1; p.cflag[r] = 0; p.rowoff[r] = -1;
+        ++j;
+      }
+    }
+    if (lane == 0) p.run_xe[ro + s_rowcnt[y + 1] - 1] = (uint16_t)(p.W - 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// union-find on runs (atomicMin linking: the root of a set is its smallest run index = the run
+// holding the component's first raster pixel)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(const int32_t* par, int x) {
+  int q;
+  while ((q = __ldcg(par + x)) != x) x = q;
+  return x;
+}
+
+__device__ void uf_union(int32_t* par, int a, int b) {
+  while (true) {
+    a = uf_find(par, a);
+    b = uf_find(par, b);
+    if (a == b) return;
+    if (a > b) {
+      const int t = a;
+      a = b;
+      b = t;
+    }
+    const int old = atomicMin(par + b, a);
+    if (old == b) return;
+    b = old;
+  }
+}
+
+constexpr int kImgCtas = 8;       // CTAs per image for the run-parallel kernels
+constexpr int kRunBlk = 256;
+
+#define FOR_EACH_RUN(r, nr) for (int r = blockIdx.x * kRunBlk + threadIdx.x; r < (nr); r += kImgCtas * kRunBlk)
+
+// K3: link every run with the overlapping same-polarity runs of the row above
+// (foreground: 8-connectivity => overlap of [xs-1, xe+1]; background: 4-connectivity => [xs, xe]).
+__global__ void __launch_bounds__(kRunBlk) db_link_kernel(DbParams p) {
+  const int n = blockIdx.y;
+  const int nr = p.nruns[n];
+  const size_t ro = (size_t)n * p.R;
+  const int32_t* rowptr = p.rowptr + (size_t)n * (p.H + 1);
+  const uint16_t *xs = p.run_xs + ro, *xe = p.run_xe + ro, *yf = p.run_yf + ro;
+  int32_t* par = p.par + ro;
+  FOR_EACH_RUN(r, nr) {
+    const int y = yf[r] & 0x7fff, fg = yf[r] >> 15;
+    if (y == 0) continue;
+    const int lo = (int)xs[r] - fg, hi = (int)xe[r] + fg;
+    int a = rowptr[y - 1], b = rowptr[y];
+    // first run q in row y-1 with xe[q] >= lo
+    int l = a, h = b;
+    while (l < h) {
+      const int m = (l + h) >> 1;
+      if ((int)xe[m] < lo) l = m + 1; else h = m;
+    }
+    for (int q = l; q < b && (int)xs[q] <= hi; ++q)
+      if ((yf[q] >> 15) == fg) uf_union(par, q, r);
+  }
+}
+
+// K4a: flatten; background runs touching the frame mark their region as OUT.
+__global__ void __launch_bounds__(kRunBlk) db_flatten_kernel(DbParams p) {
+  const int n = blockIdx.y;
+  const int nr = p.nruns[n];
+  const size_t ro = (size_t)n * p.R;
+  const uint16_t *xs = p.run_xs + ro, *xe = p.run_xe + ro, *yf = p.run_yf + ro;
+  int32_t* par = p.par + ro;
+  FOR_EACH_RUN(r, nr) {
+    const int root = uf_find(par, r);
+    par[r] = root;
+    const int y = yf[r] & 0x7fff, fg = yf[r] >> 15;
+    if (!fg && (y == 0 || y == p.H - 1 || xs[r] == 0 || xe[r] == p.W - 1)) p.cflag[ro + root] = kOutFlag;
+  }
+}
+
+// K4b: per-component reductions. One warp per run: pixel sums of foreground runs and of hole runs.
+template <typename T>
+__global__ void __launch_bounds__(kRunBlk) db_stats_kernel(DbParams p) {
+  const int n = blockIdx.y;
+  const int nr = p.nruns[n];
+  const size_t ro = (size_t)n * p.R;
+  const uint16_t *xs = p.run_xs + ro, *xe = p.run_xe + ro, *yf = p.run_yf + ro;
+  const int lane = threadIdx.x & 31;
+  const int wpb = kRunBlk / 32;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < nr; r += kImgCtas * wpb) {
+    const int root = p.par[ro + r];
+    const int y = yf[r] & 0x7fff, fg = yf[r] >> 15;
+    if (!fg && (p.cflag[ro + root] & kOutFlag)) continue;
+    const int a = xs[r], b = xe[r];
+    long long s = 0;
+    const long long off = n * p.stride_n + y * p.stride_h;
+    for (int x = a + lane; x <= b; x += 32) s += to_fixed(load_px<T>(p.maps, off + x));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      const size_t c = ro + root;
+      atomicAdd(&p.area[c], b - a + 1);
+      atomicAdd((unsigned long long*)&p.sum[c], (unsigned long long)s);
+      atomicMin(&p.xmin[c], a);
+      atomicMax(&p.xmax[c], b);
+      atomicMax(&p.ymax[c], y);
+      if (fg) {
+        atomicMin(&p.dmin[c], a - y);
+        atomicMax(&p.dmax[c], b - y);
+        atomicMin(&p.smin[c], a + y);
+        atomicMax(&p.smax[c], b + y);
+      }
+    }
+  }
+}
+
+// run of row y that contains pixel x
+__device__ __forceinline__ int run_at(const int32_t* rowptr, const uint16_t* xs, int y, int x) {
+  int l = rowptr[y], h = rowptr[y + 1];  // last run with xs <= x
+  while (h - l > 1) {
+    const int m = (l + h) >> 1;
+    if ((int)xs[m] <= x) l = m; else h = m;
+  }
+  return l;
+}
+
+__device__ __forceinline__ bool is_candidate_root(const DbParams& p, size_t ro, int r) {
+  if (p.par[ro + r] != r) return false;
+  const int fg = p.run_yf[ro + r] >> 15;
+  return fg || !(p.cflag[ro + r] & kOutFlag);
+}
+
+// K5: parent links of the component tree + row-extent slot allocation, one thread per candidate root.
+__global__ void __launch_bounds__(kRunBlk) db_tree_kernel(DbParams p) {
+  const int n = blockIdx.y;
+  const int nr = p.nruns[n];
+  const size_t ro = (size_t)n * p.R;
+  const int32_t* rowptr = p.rowptr + (size_t)n * (p.H + 1);
+  const uint16_t *xs = p.run_xs + ro, *yf = p.run_yf + ro;
+  FOR_EACH_RUN(r, nr) {
+    if (!is_candidate_root(p, ro, r)) continue;
+    const int y = yf[r] & 0x7fff, fg = yf[r] >> 15;
+    int parent = -1, nrows;
+    if (fg) {
+      // region LEFT of the component's first pixel: previous run of the same row (background)
+      if (xs[r] > 0) {
+        const int h = p.par[ro + r - 1];
+        if (!(p.cflag[ro + h] & kOutFlag)) parent = h;
+      }
+      nrows = p.ymax[ro + r] - y + 1;
+    } else {
+      // pixel ABOVE the hole's first pixel is foreground and belongs to the enclosing component
+      parent = p.par[ro + run_at(rowptr, xs, y - 1, xs[r])];
+      nrows = p.ymax[ro + r] - y + 3;  // ring rows ymin-1 .. ymax+1
+    }
+    p.cpar[ro + r] = parent;
+    const int off = atomicAdd(&p.ext_alloc[n], nrows + 1);
+    if (off + nrows + 1 <= p.E) {
+      p.rowoff[ro + r] = off;
+      for (int i = 0; i < nrows; ++i) {
+        p.ext_l[(size_t)n * p.E + off + i] = 0x7fffffff;
+        p.ext_r[(size_t)n * p.E + off + i] = -1;
+      }
+    }
+  }
+}
+
+// K6: every candidate adds its own (count, sum) to all its ancestors: fill = own + descendants.
+__global__ void __launch_bounds__(kRunBlk) db_fill_kernel(DbParams p) {
+  const int n = blockIdx.y;
+  const int nr = p.nruns[n];
+  const size_t ro = (size_t)n * p.R;
+  FOR_EACH_RUN(r, nr) {
+    if (!is_candidate_root(p, ro, r)) continue;
+    const int cnt = p.area[ro + r];
+    const long long s = p.sum[ro + r];
+    int a = p.cpar[ro + r];
+    while (a >= 0) {
+      atomicAdd(&p.fcnt[ro + a], cnt);
+      atomicAdd((unsigned long long*)&p.fsum[ro + a], (unsigned long long)s);
+      a = p.cpar[ro + a];
+    }
+  }
+}
+
+__device__ __forceinline__ bool bit_at(const uint32_t* bits, int Wd, int x, int y) {
+  return (bits[(size_t)y * Wd + (x >> 5)] >> (x & 31)) & 1u;
+}
+
+// K7: row extents of every candidate's point set, stair pixels, hole rings. One thread per run.
+template <typename T>
+__global__ void __launch_bounds__(kRunBlk) db_extents_kernel(DbParams p) {
+  const int n = blockIdx.y;
+  const int nr = p.nruns[n];
+  const size_t ro = (size_t)n * p.R;
+  const int32_t* rowptr = p.rowptr + (size_t)n * (p.H + 1);
+  const uint16_t *xs = p.run_xs + ro, *xe = p.run_xe + ro, *yf = p.run_yf + ro;
+  const int32_t* par = p.par + ro;
+  const uint32_t* bits = p.bits + (size_t)n * p.H * p.Wd;
+  int32_t* ext_l = p.ext_l + (size_t)n * p.E;
+  int32_t* ext_r = p.ext_r + (size_t)n * p.E;
+  const int H = p.H, W = p.W, Wd = p.Wd;
+  const long long img = n * p.stride_n;
+
+  auto px = [&](int x, int y) { return to_fixed(load_px<T>(p.maps, img + y * p.stride_h + x)); };
+  // is pixel (x,y) a background pixel of hole region h ?
+  auto in_hole = [&](int x, int y, int h) {
+    if (x < 0 || y < 0 || x >= W || y >= H) return false;
+    if (bit_at(bits, Wd, x, y)) return false;
+    return par[run_at(rowptr, xs, y, x)] == h;
+  };
+
+  FOR_EACH_RUN(r, nr) {
+    const int y = yf[r] & 0x7fff, fg = yf[r] >> 15;
+    const int a = xs[r], b = xe[r];
+    const int root = par[r];
+    if (fg) {
+      const int off = p.rowoff[ro + root];
+      if (off >= 0) {
+        const int i = off + (y - (yf[root] & 0x7fff));
+        atomicMin(&ext_l[i], a);
+        atomicMax(&ext_r[i], b);
+      }
+      continue;
+    }
+    // ---- background run ----
+    // (a) stair pixel of the OUTER contour of the component to the left: e = (a, y)
+    if (a > 0) {
+      const int C = par[r - 1];
+      const bool updn = (y > 0 && bit_at(bits, Wd, a, y - 1)) || (y < H - 1 && bit_at(bits, Wd, a, y + 1));
+      if (updn) {
+        const int pc = p.cpar[ro + C];
+        const bool outer_region = pc < 0 ? (p.cflag[ro + root] & kOutFlag) != 0 : (root == pc);
+        if (outer_region) {
+          atomicAdd(&p.xcnt[ro + C], 1);
+          atomicAdd((unsigned long long*)&p.xsum[ro + C], (unsigned long long)px(a, y));
+        }
+      }
+    }
+    if (p.cflag[ro + root] & kOutFlag) continue;
+    // (b) hole run: ring pixels (each counted once: owner = first of up/left/right/down neighbour
+    //     that lies in the hole) and their row extents; (c) stair pixels of the hole contour.
+    const int h = root;
+    const int off = p.rowoff[ro + h];
+    const int y0 = (yf[h] & 0x7fff) - 1;
+    int cnt = 0;
+    long long s = 0;
+    auto ring = [&](int x, int yy) {
+      ++cnt;
+      s += px(x, yy);
+      if (off >= 0) {
+        atomicMin(&ext_l[off + yy - y0], x);
+        atomicMax(&ext_r[off + yy - y0], x);
+      }
+    };
+    // hole runs never touch the frame: a-1, b+1, y-1, y+1 are inside the image
+    for (int x = a; x <= b; ++x) {
+      if (bit_at(bits, Wd, x, y + 1)) ring(x, y + 1);  // its UP neighbour is in h: always the owner
+      if (bit_at(bits, Wd, x, y - 1)) {                // p = (x, y-1): down neighbour in h
+        if (!in_hole(x, y - 2, h) && !in_hole(x - 1, y - 1, h) && !in_hole(x + 1, y - 1, h)) ring(x, y - 1);
+      }
+    }
+    // p = (b+1, y): left neighbour in h; owner unless its up neighbour is in h
+    if (!in_hole(b + 1, y - 1, h)) ring(b + 1, y);
+    // p = (a-1, y): right neighbour in h; owner unless up or left neighbour is in h
+    if (!in_hole(a - 1, y - 1, h) && !in_hole(a - 2, y, h)) ring(a - 1, y);
+    // (c) o = (b, y) is the last pixel of a hole run, q = (b+1, y) is foreground; for dy in {-1,+1}:
+    //     p = (b, y+dy) foreground => contour steps diagonally p <-> q and the 4-connected boundary
+    //     also paints e = (b+1, y+dy)
+    for (int dy = -1; dy <= 1; dy += 2) {
+      if (!bit_at(bits, Wd, b, y + dy)) continue;
+      const int ex = b + 1, ey = y + dy;
+      if (dy == -1) {
+        // the same e is produced from o' = (b, y-2) with dy=+1 when that qualifies: count it there
+        if (in_hole(b, y - 2, h) && bit_at(bits, Wd, b + 1, y - 2)) continue;
+      }
+      if (bit_at(bits, Wd, ex, ey)) {
+        // foreground e already belongs to the ring when one of its other neighbours is in h
+        if (in_hole(ex + 1, ey, h) || in_hole(ex, ey + dy, h)) continue;
+      } else {
+        if (par[run_at(rowptr, xs, ey, ex)] == h) continue;  // e itself is hole background
+      }
+      ++cnt;
+      s += px(ex, ey);
+    }
+    if (cnt) {
+      atomicAdd(&p.xcnt[ro + h], cnt);
+      atomicAdd((unsigned long long*)&p.xsum[ro + h], (unsigned long long)s);
+    }
+  }
+}
+
+// K8: candidate ranking in cv2 order (reverse raster order of the first point), one CTA per image.
+__global__ void __launch_bounds__(kRunThreads) db_rank_kernel(DbParams p) {
+  const int n = blockIdx.x;
+  const int nr = p.nruns[n];
+  const size_t ro = (size_t)n * p.R;
+  const int chunk = (nr + kRunThreads - 1) / kRunThreads;
+  // thread t owns runs [nr - (t+1)*chunk, nr - t*chunk) walked downwards: reverse order
+  const int hi = nr - threadIdx.x * chunk, lo = max(0, hi - chunk);
+  int local = 0;
+  for (int r = hi - 1; r >= lo; --r) local += is_candidate_root(p, ro, r) ? 1 : 0;
+  int total;
+  int rank = block_exclusive_scan(local, &total);
+  for (int r = hi - 1; r >= lo; --r) {
+    if (!is_candidate_root(p, ro, r)) continue;
+    if (rank < p.maxc) p.cand[(size_t)n * p.maxc + rank] = r;
+    ++rank;
+  }
+  if (threadIdx.x == 0) {
+    p.ncand[n] = min(total, p.maxc);
+    if (total > p.maxc) atomicOr(&p.imgflags[n], OCRPP_IMG_CANDIDATES_TRUNCATED);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9: per-candidate geometry, one warp per candidate.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGeoWarps = 4;
+constexpr int kSmallRows = 64;              // candidates up to this many rows build their hull in smem
+constexpr int kOffCap = 320;                // capacity of the unclip polygon (points)
+
+struct WarpBest {
+  double area;
+  int idx;
+};
+
+// warp-parallel min_area_rect: lanes take hull edges, same choice as geom::min_area_rect
+__device__ void warp_min_area_rect(const P2i* h, int n, geom::Rect* r, int lane) {
+  if (n == 1) {
+    geom::min_area_rect(h, n, r);
+    return;
+  }
+  const int ne = n == 2 ? 1 : n;
+  double best = 1e300;
+  int bi = 0x7fffffff;
+  for (int i = lane; i < ne; i += 32) {
+    const geom::EdgeFit f = geom::fit_edge(h, n, i);
+    if (f.area < best) {
+      best = f.area;
+      bi = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oa = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oa < best || (oa == best && oi < bi)) {
+      best = oa;
+      bi = oi;
+    }
+  }
+  const geom::EdgeFit f = geom::fit_edge(h, n, bi);  // every lane recomputes the winner
+  geom::rect_from_fit(h, n, bi, f, r);
+}
+
+__global__ void __launch_bounds__(kGeoWarps * 32) db_geometry_kernel(DbParams p) {
+  __shared__ P2i s_pts[kGeoWarps][2 * kSmallRows];
+  __shared__ P2i s_hull[kGeoWarps][2 * kSmallRows + 2];
+  __shared__ P2i s_off[kGeoWarps][kOffCap];
+  __shared__ P2i s_offh[kGeoWarps][kOffCap + 2];
+  const int n = blockIdx.y;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * kGeoWarps + wib;
+  if (k >= p.ncand[n]) return;
+  const size_t ro = (size_t)n * p.R;
+  const size_t ko = (size_t)n * p.maxc + k;
+  const int c = p.cand[ko];
+  const int fg = p.run_yf[ro + c] >> 15;
+  const int y_first = p.run_yf[ro + c] & 0x7fff;
+  if (lane == 0) p.res_keep[ko] = 0;
+
+  // "contour has <= 2 points" <=> one pixel or a 1-px straight run (-, |, /, \) (db_postprocess.cpp:255-257)
+  if (fg) {
+    const int area = p.area[ro + c];
+    const int bw = p.xmax[ro + c] - p.xmin[ro + c] + 1, bh = p.ymax[ro + c] - y_first + 1;
+    const bool diag = (bw == bh && bw == area) &&
+                      (p.dmin[ro + c] == p.dmax[ro + c] || p.smin[ro + c] == p.smax[ro + c]);
+    if (area == 1 || (bh == 1 && area == bw) || (bw == 1 && area == bh) || diag) return;
+  }
+  const int off = p.rowoff[ro + c];
+  if (off < 0) {  // extent arena exhausted (cannot happen with E = 4R); fail loudly
+    if (lane == 0) atomicOr(&p.imgflags[n], OCRPP_IMG_RUN_OVERFLOW);
+    return;
+  }
+  const int nrows = fg ? (p.ymax[ro + c] - y_first + 1) : (p.ymax[ro + c] - y_first + 3);
+  const int y0 = fg ? y_first : y_first - 1;
+  const int32_t* ext_l = p.ext_l + (size_t)n * p.E + off;
+  const int32_t* ext_r = p.ext_r + (size_t)n * p.E + off;
+  P2i* pts;
+  P2i* hull;
+  if (nrows <= kSmallRows) {
+    pts = s_pts[wib];
+    hull = s_hull[wib];
+  } else {
+    pts = p.hull + ((size_t)n * p.E + off) * 4;
+    hull = pts + 2 * nrows;
+  }
+  for (int i = lane; i < nrows; i += 32) {
+    pts[2 * i] = P2i{ext_l[i], y0 + i};
+    pts[2 * i + 1] = P2i{ext_r[i], y0 + i};
+  }
+  __syncwarp();
+  int hn = 0;
+  if (lane == 0) hn = geom::hull_sorted(pts, 2 * nrows, hull);
+  hn = __shfl_sync(0xffffffffu, hn, 0);
+  __syncwarp();
+
+  geom::Rect rect;
+  warp_min_area_rect(hull, hn, &rect, lane);
+  // float32 RotatedRect semantics from here on (db_postprocess.cpp:159-192)
+  float cx[4], cy[4], mx[4], my[4];
+  for (int q = 0; q < 4; ++q) {
+    cx[q] = (float)rect.cx[q];
+    cy[q] = (float)rect.cy[q];
+  }
+  geom::mini_box(cx, cy, mx, my);
+  const float ssid = fmaxf((float)rect.w, (float)rect.h);
+  if (ssid < 3.f) return;
+
+  // BoxScore (db_postprocess.cpp:194-229): mean over the filled contour, double accumulation
+  const long long tot = p.sum[ro + c] + p.fsum[ro + c] + p.xsum[ro + c];
+  const int cnt = p.area[ro + c] + p.fcnt[ro + c] + p.xcnt[ro + c];
+  const float score = (float)(((double)tot / kFixScale) / (double)cnt);
+  if (score < p.box_thresh) return;
+
+  // UnClip (db_postprocess.cpp:34-64)
+  const float distance = geom::unclip_distance(mx, my, p.unclip_ratio);
+  P2i quad[4];
+  for (int q = 0; q < 4; ++q) quad[q] = P2i{(int)mx[q], (int)my[q]};
+  int m = 0;
+  if (lane == 0) {
+    m = geom::do_offset_quad(quad, (double)distance, s_off[wib], kOffCap);
+    if (m > 0) geom::sort_points_yx(s_off[wib], m);
+  }
+  m = __shfl_sync(0xffffffffu, m, 0);
+  if (m < 0) {  // polygon larger than kOffCap points: unsupported size, fail loudly
+    if (lane == 0) atomicOr(&p.imgflags[n], OCRPP_IMG_RUN_OVERFLOW);
+    return;
+  }
+  if (m == 0) return;  // empty solution -> RotatedRect((0,0),(1,1),0) -> dropped by the 1.001 test
+  int hm = 0;
+  if (lane == 0) hm = geom::hull_sorted(s_off[wib], m, s_offh[wib]);
+  hm = __shfl_sync(0xffffffffu, hm, 0);
+  __syncwarp();
+  geom::Rect rect2;
+  warp_min_area_rect(s_offh[wib], hm, &rect2, lane);
+  if ((float)rect2.h < 1.001 && (float)rect2.w < 1.001) return;
+  for (int q = 0; q < 4; ++q) {
+    cx[q] = (float)rect2.cx[q];
+    cy[q] = (float)rect2.cy[q];
+  }
+  geom::mini_box(cx, cy, mx, my);
+  const float ssid2 = fmaxf((float)rect2.w, (float)rect2.h);
+  if (ssid2 < 5.f) return;
+
+  if (lane == 0) {
+    const float sw = (float)p.src_wh[2 * n], sh = (float)p.src_wh[2 * n + 1];
+    for (int q = 0; q < 4; ++q) {
+      const float fx = geom::fmul(geom::fdiv(mx[q], (float)p.W), sw);
+      const float fy = geom::fmul(geom::fdiv(my[q], (float)p.H), sh);
+      p.res_boxf[ko * 8 + 2 * q] = fx;
+      p.res_boxf[ko * 8 + 2 * q + 1] = fy;
+      p.res_box[ko * 8 + 2 * q] = (int16_t)(int)fminf(fmaxf(geom::roundf_half_away(fx), 0.f), sw);
+      p.res_box[ko * 8 + 2 * q + 1] = (int16_t)(int)fminf(fmaxf(geom::roundf_half_away(fy), 0.f), sh);
+    }
+    p.res_score[ko] = score;
+    p.res_keep[ko] = 1;
+  }
+}
+
+// K10: ordered compaction of the kept boxes, one CTA per image.
+__global__ void __launch_bounds__(kRunThreads) db_compact_kernel(DbParams p) {
+  const int n = blockIdx.x;
+  const int nc = p.ncand[n];
+  const size_t ko = (size_t)n * p.maxc;
+  const int chunk = (nc + kRunThreads - 1) / kRunThreads;
+  const int lo = min(nc, (int)threadIdx.x * chunk), hi = min(nc, lo + chunk);
+  int local = 0;
+  for (int k = lo; k < hi; ++k) local += p.res_keep[ko + k];
+  int total;
+  int pos = block_exclusive_scan(local, &total);
+  for (int k = lo; k < hi; ++k) {
+    if (!p.res_keep[ko + k]) continue;
+    for (int q = 0; q < 8; ++q) {
+      p.boxes_out[(ko + pos) * 8 + q] = p.res_box[(ko + k) * 8 + q];
+      if (p.boxes_f_out) p.boxes_f_out[(ko + pos) * 8 + q] = p.res_boxf[(ko + k) * 8 + q];
+    }
+    p.scores_out[ko + pos] = p.res_score[ko + k];
+    ++pos;
+  }
+  if (threadIdx.x == 0) {
+    const int fl = p.imgflags[n];
+    p.counts_out[n] = (fl & OCRPP_IMG_RUN_OVERFLOW) ? 0 : total;
+    p.status_out[n] = fl;
+  }
+}
+
+// debug: canonical 8-connected foreground label map (id = 1 + rank of the first raster pixel)
+__global__ void __launch_bounds__(kRunThreads) db_labels_kernel(DbParams p) {
+  const int n = blockIdx.x;
+  const int nr = p.nruns[n];
+  const size_t ro = (size_t)n * p.R;
+  const int chunk = (nr + kRunThreads - 1) / kRunThreads;
+  const int lo = min(nr, (int)threadIdx.x * chunk), hi = min(nr, lo + chunk);
+  int local = 0;
+  for (int r = lo; r < hi; ++r) local += (p.par[ro + r] == r && (p.run_yf[ro + r] >> 15)) ? 1 : 0;
+  int total;
+  int id = block_exclusive_scan(local, &total);
+  // publish each root's id through its `dmin` slot (dead after the geometry kernel)
+  for (int r = lo; r < hi; ++r)
+    if (p.par[ro + r] == r && (p.run_yf[ro + r] >> 15)) p.dmin[ro + r] = ++id;
+  __syncthreads();
+  int32_t* lab = p.labels_dbg + (size_t)n * p.H * p.W;
+  for (int r = threadIdx.x; r < nr; r += kRunThreads) {
+    if (!(p.run_yf[ro + r] >> 15)) continue;
+    const int y = p.run_yf[ro + r] & 0x7fff;
+    const int v = p.dmin[ro + p.par[ro + r]];
+    for (int x = p.run_xs[ro + r]; x <= p.run_xe[ro + r]; ++x) lab[(size_t)y * p.W + x] = v;
+  }
+}
+
+struct Carver {
+  char* base;
+  size_t off;
+  template <typename T>
+  T* take(size_t count) {
+    off = align_up(off, 256);
+    T* ptr = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return ptr;
+  }
+};
+
+size_t carve(DbParams& p, void* ws) {
+  Carver c{(char*)ws, 0};
+  const size_t N = p.N, R = p.R, E = p.E;
+  p.bits = c.take<uint32_t>(N * p.H * p.Wd);
+  p.rowptr = c.take<int32_t>(N * (p.H + 1));
+  p.run_xs = c.take<uint16_t>(N * R);
+  p.run_xe = c.take<uint16_t>(N * R);
+  p.run_yf = c.take<uint16_t>(N * R);
+  p.par = c.take<int32_t>(N * R);
+  p.area = c.take<int32_t>(N * R);
+  p.xmin = c.take<int32_t>(N * R);
+  p.xmax = c.take<int32_t>(N * R);
+  p.ymax = c.take<int32_t>(N * R);
+  p.dmin = c.take<int32_t>(N * R);
+  p.dmax = c.take<int32_t>(N * R);
+  p.smin = c.take<int32_t>(N * R);
+  p.smax = c.take<int32_t>(N * R);
+  p.sum = c.take<long long>(N * R);
+  p.fcnt = c.take<int32_t>(N * R);
+  p.fsum = c.take<long long>(N * R);
+  p.xcnt = c.take<int32_t>(N * R);
+  p.xsum = c.take<long long>(N * R);
+  p.cpar = c.take<int32_t>(N * R);
+  p.cflag = c.take<int32_t>(N * R);
+  p.rowoff = c.take<int32_t>(N * R);
+  p.ext_l = c.take<int32_t>(N * E);
+  p.ext_r = c.take<int32_t>(N * E);
+  p.hull = c.take<P2i>(N * E * 4);
+  p.nruns = c.take<int32_t>(4 * N);  // nruns | ext_alloc | imgflags | ncand, cleared together
+  p.ext_alloc = p.nruns ? p.nruns + N : nullptr;
+  p.imgflags = p.nruns ? p.nruns + 2 * N : nullptr;
+  p.ncand = p.nruns ? p.nruns + 3 * N : nullptr;
+  p.cand = c.take<int32_t>(N * p.maxc);
+  p.res_keep = c.take<int32_t>(N * p.maxc);
+  p.res_box = c.take<int16_t>(N * p.maxc * 8);
+  p.res_boxf = c.take<float>(N * p.maxc * 8);
+  p.res_score = c.take<float>(N * p.maxc);
+  return align_up(c.off, 256);
+}
+
+int resolve_max_runs(int H, int W, int max_runs) {
+  const long long worst = (long long)H * (W + 1);
+  if (max_runs <= 0 || max_runs > worst) return (int)worst;
+  return max_runs;
+}
+
+}  // namespace
+}  // namespace ocrpp
+
+extern "C" size_t ocrpp_db_workspace_bytes(int N, int H, int W, int max_runs) {
+  using namespace ocrpp;
+  if (N <= 0 || H <= 0 || W <= 0) return 0;
+  DbParams p{};
+  p.N = N; p.H = H; p.W = W; p.Wd = (W + 31) / 32;
+  p.R = resolve_max_runs(H, W, max_runs);
+  p.E = 4 * p.R + 4;
+  p.maxc = 1000;  // max_candidates is capped at the reference constant
+  return carve(p, nullptr);
+}
+
+extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int H, int W,
+                                    int64_t stride_n, int64_t stride_h, const int32_t* src_wh_dev,
+                                    float thresh, float box_thresh, float unclip_ratio,
+                                    int max_candidates, int max_runs, int16_t* boxes_out_dev,
+                                    float* scores_out_dev, int32_t* counts_out_dev,
+                                    int32_t* status_out_dev, float* boxes_f_out_dev,
+                                    int32_t* labels_dbg_dev, void* workspace_dev,
+                                    size_t workspace_bytes, void* stream) {
+  using namespace ocrpp;
+  OCRPP_CHECK_ARG(dtype == OCRPP_F32 || dtype == OCRPP_F16, "db: dtype must be OCRPP_F32 or OCRPP_F16");
+  OCRPP_CHECK_ARG(N >= 0 && H > 0 && W > 0, "db: bad shape N=%d H=%d W=%d", N, H, W);
+  OCRPP_CHECK_ARG(H < 32768 && W < 65536, "db: H must be < 32768 and W < 65536");
+  OCRPP_CHECK_ARG(max_candidates > 0 && max_candidates <= 1000, "db: max_candidates must be in [1,1000]");
+  if (N == 0) return OCRPP_OK;
+  OCRPP_CHECK_ARG(maps_dev && src_wh_dev && boxes_out_dev && scores_out_dev && counts_out_dev && status_out_dev && workspace_dev,
+                  "db: null pointer argument");
+  DbParams p{};
+  p.maps = maps_dev; p.stride_n = stride_n; p.stride_h = stride_h; p.src_wh = src_wh_dev;
+  p.N = N; p.H = H; p.W = W; p.Wd = (W + 31) / 32;
+  p.R = resolve_max_runs(H, W, max_runs);
+  p.E = 4 * p.R + 4;
+  p.maxc = max_candidates;
+  p.thresh = thresh; p.box_thresh = box_thresh; p.unclip_ratio = unclip_ratio;
+  const size_t need = carve(p, workspace_dev);
+  if (need > workspace_bytes)
+    return set_error(OCRPP_ERR_WORKSPACE_TOO_SMALL, "db: workspace needs %zu bytes, got %zu", need, workspace_bytes);
+  p.boxes_out = boxes_out_dev; p.scores_out = scores_out_dev; p.counts_out = counts_out_dev;
+  p.status_out = status_out_dev; p.boxes_f_out = boxes_f_out_dev; p.labels_dbg = labels_dbg_dev;
+  cudaStream_t s = (cudaStream_t)stream;
+
+  OCRPP_CUDA(cudaMemsetAsync(p.nruns, 0, sizeof(int32_t) * 4 * N, s));
+  const size_t esz = dtype == OCRPP_F32 ? 4 : 2;
+  const int epl = dtype == OCRPP_F32 ? 4 : 8;
+  const bool vec = ((uintptr_t)maps_dev % 16 == 0) && (stride_n % epl == 0) && (stride_h % epl == 0) && (W % epl == 0);
+  (void)esz;
+  {
+    dim3 grid((H + kBinWarps - 1) / kBinWarps, N);
+    if (dtype == OCRPP_F32) {
+      if (vec) db_binarize_kernel<float, true><<<grid, kBinWarps * 32, 0, s>>>(p);
+      else db_binarize_kernel<float, false><<<grid, kBinWarps * 32, 0, s>>>(p);
+    } else {
+      if (vec) db_binarize_kernel<__half, true><<<grid, kBinWarps * 32, 0, s>>>(p);
+      else db_binarize_kernel<__half, false><<<grid, kBinWarps * 32, 0, s>>>(p);
+    }
+    OCRPP_LAUNCHED();
+  }
+  db_runs_kernel<<<N, kRunThreads, sizeof(int) * (H + 1), s>>>(p);
+  OCRPP_LAUNCHED();
+  dim3 rgrid(kImgCtas, N);
+  db_link_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  db_flatten_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  if (dtype == OCRPP_F32) db_stats_kernel<float><<<rgrid, kRunBlk, 0, s>>>(p);
+  else db_stats_kernel<__half><<<rgrid, kRunBlk, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  db_tree_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  db_fill_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  if (dtype == OCRPP_F32) db_extents_kernel<float><<<rgrid, kRunBlk, 0, s>>>(p);
+  else db_extents_kernel<__half><<<rgrid, kRunBlk, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  db_rank_kernel<<<N, kRunThreads, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  {
+    dim3 grid((max_candidates + kGeoWarps - 1) / kGeoWarps, N);
+    db_geometry_kernel<<<grid, kGeoWarps * 32, 0, s>>>(p);
+    OCRPP_LAUNCHED();
+  }
+  db_compact_kernel<<<N, kRunThreads, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  if (labels_dbg_dev) {
+    OCRPP_CUDA(cudaMemsetAsync(labels_dbg_dev, 0, sizeof(int32_t) * (size_t)N * H * W, s));
+    db_labels_kernel<<<N, kRunThreads, 0, s>>>(p);
+    OCRPP_LAUNCHED();
+  }
+  return OCRPP_OK;
+}

@@ -1,0 +1,181 @@
+"""DB / DB++ post-processing behind the reference's operator API, computed by libocrpp (sm_100a).
+
+Mirrors R/pytocr/postprocess/db_postprocess.py (DBPostProcess :10-74, DistillationDBPostProcess
+:197-226) on its CONFIGURED path (`cpp_speedup: True`, i.e. the semantics of
+db_postprocess_fast/src/db_postprocess.cpp:231-317): same ctor kwargs, same
+`__call__(outs_dict, shape_list, use_padding_resize=False)`, same return structure
+(list of {"points": int16 [K,4,2], "scores": [1.0]*K}; K == 0 gives points.shape == (0,)).
+The true BoxScore of every box is additionally returned as "box_scores" (float32 [K]).
+
+The probability map never leaves the device: it is consumed where the head wrote it
+(zero-copy through data_ptr()); only boxes / counts come back, through pinned buffers.
+"""
+import numpy as np
+
+from .. import _lib
+
+
+class DBPostProcess(object):
+    def __init__(self, thresh=0.3, box_thresh=0.5, max_candidates=1000, unclip_ratio=1.5,
+                 use_dilation=False, score_mode="poly", cpp_speedup=False, out_polygon=False,
+                 cuda_speedup=True, max_runs=None, **kwargs):
+        if not cuda_speedup:
+            raise _lib.OcrppError("pytorchocr_b200 implements only the CUDA path: set PostProcess.cuda_speedup: True "
+                                  "(with the flag off the reference's own DBPostProcess runs)")
+        assert score_mode in ["box", "poly"], "Score mode must be in [box, poly] but got: {}".format(score_mode)
+        # The C++ path the CUDA path replaces ignores score_mode (always scores the contour polygon),
+        # hard-codes min_size = 3 and max_candidates = 1000 and cannot emit polygons
+        # (db_postprocess.cpp:238-239,270); options outside it are SURVEY 8(f) items.
+        if use_dilation:
+            raise NotImplementedError("use_dilation is not on the configured path (SURVEY.md 8(f) rank 4)")
+        if out_polygon:
+            raise NotImplementedError("out_polygon needs cpp_speedup False in the reference; not on the CUDA path")
+        self.thresh = thresh
+        self.box_thresh = box_thresh
+        self.max_candidates = min(int(max_candidates), 1000)
+        self.unclip_ratio = unclip_ratio
+        self.min_size = 3
+        self.score_mode = score_mode
+        self.max_runs = max_runs
+        self._cache = {}
+
+    # -- device plumbing ------------------------------------------------------------------------
+    @staticmethod
+    def _to_device(pred):
+        torch = _lib.require_cuda()
+        if isinstance(pred, np.ndarray):
+            t = torch.from_numpy(np.ascontiguousarray(pred))
+            if t.dtype not in (torch.float32, torch.float16):
+                t = t.float()
+            return t.pin_memory().cuda(non_blocking=True)
+        if not isinstance(pred, torch.Tensor):
+            raise TypeError("outs_dict['maps'] must be a torch.Tensor or a numpy array")
+        t = pred.detach()
+        if not t.is_cuda:
+            t = t.pin_memory().cuda(non_blocking=True)
+        if t.dtype not in (torch.float32, torch.float16):
+            t = t.float()
+        return t
+
+    def _buffers(self, device, N, H, W, R):
+        torch = _lib.require_cuda()
+        key = (str(device), N, H, W, R)
+        buf = self._cache.get(key)
+        if buf is None:
+            self._cache.clear()
+            L = _lib.lib()
+            cap = self.max_candidates
+            ws_bytes = L.ocrpp_db_workspace_bytes(N, H, W, R)
+            nb, ns = N * cap * 8 * 2, N * cap * 4
+            # one device block and one pinned block: [boxes i16 | scores f32 | counts i32 | status i32]
+            total = nb + ns + 8 * N
+            buf = {
+                "ws": torch.empty(ws_bytes, dtype=torch.uint8, device=device),
+                "ws_bytes": ws_bytes,
+                "out_dev": torch.empty(total, dtype=torch.uint8, device=device),
+                "out_host": torch.empty(total, dtype=torch.uint8, pin_memory=True),
+                "wh_host": torch.empty((N, 2), dtype=torch.int32, pin_memory=True),
+                "wh_dev": torch.empty((N, 2), dtype=torch.int32, device=device),
+                "offs": (0, nb, nb + ns, nb + ns + 4 * N),
+            }
+            self._cache[key] = buf
+        return buf
+
+    def _default_runs(self, H, W):
+        if self.max_runs is not None:
+            return int(self.max_runs)
+        return max(4096, (H * W) // 32)
+
+    def run_device(self, pred, shape_list, boxes_f=False, labels=False):
+        """Enqueues the kernels and returns host views (boxes[N,cap,4,2] i16, scores[N,cap] f32,
+        counts[N], status[N], extras dict). Blocks until the results are on the host."""
+        torch = _lib.require_cuda()
+        t = self._to_device(pred)
+        if t.dim() != 4:
+            raise ValueError("maps must be [N,C,H,W]")
+        if t.stride(3) != 1:
+            t = t.contiguous()
+        N, _, H, W = t.shape
+        cap = self.max_candidates
+        if N == 0:
+            return (np.zeros((0, cap, 4, 2), np.int16), np.zeros((0, cap), np.float32),
+                    np.zeros((0,), np.int32), np.zeros((0,), np.int32), {})
+        shape = np.asarray(shape_list, dtype=np.float64).reshape(N, -1)
+        L = _lib.lib()
+        worst = H * (W + 1)
+        R = min(self._default_runs(H, W), worst)
+        with torch.cuda.device(t.device):
+            stream = torch.cuda.current_stream()
+            while True:
+                buf = self._buffers(t.device, N, H, W, R)
+                o_box, o_sc, o_cnt, o_st = buf["offs"]
+                buf["wh_host"][:, 0] = torch.from_numpy(shape[:, 1].astype(np.int32))  # src_w
+                buf["wh_host"][:, 1] = torch.from_numpy(shape[:, 0].astype(np.int32))  # src_h
+                buf["wh_dev"].copy_(buf["wh_host"], non_blocking=True)
+                out = buf["out_dev"]
+                base = out.data_ptr()
+                extras_dev = {}
+                bf_ptr = lab_ptr = None
+                if boxes_f:
+                    extras_dev["boxes_f"] = torch.empty((N, cap, 4, 2), dtype=torch.float32, device=t.device)
+                    bf_ptr = extras_dev["boxes_f"].data_ptr()
+                if labels:
+                    extras_dev["labels"] = torch.empty((N, H, W), dtype=torch.int32, device=t.device)
+                    lab_ptr = extras_dev["labels"].data_ptr()
+                _lib.check(L.ocrpp_db_postprocess(
+                    t.data_ptr(), _lib.F32 if t.dtype == torch.float32 else _lib.F16, N, H, W,
+                    t.stride(0), t.stride(2), buf["wh_dev"].data_ptr(),
+                    float(self.thresh), float(self.box_thresh), float(self.unclip_ratio), cap, R,
+                    base + o_box, base + o_sc, base + o_cnt, base + o_st, bf_ptr, lab_ptr,
+                    buf["ws"].data_ptr(), buf["ws_bytes"], stream.cuda_stream))
+                buf["out_host"].copy_(out, non_blocking=True)
+                stream.synchronize()
+                host = buf["out_host"].numpy()
+                status = host[o_st:o_st + 4 * N].view(np.int32)
+                if (status & _lib.IMG_VALUE_OUT_OF_RANGE).any():
+                    raise _lib.OcrppError("DB probability map holds NaN/Inf or |value| > 1024: not a probability map")
+                if (status & _lib.IMG_RUN_OVERFLOW).any():
+                    if R >= worst:
+                        raise _lib.OcrppError("DB post-process: internal capacity exceeded (image too large for the unclip buffer)")
+                    R = min(worst, R * 8)   # capacity retry (still the CUDA path), not a fallback
+                    continue
+                break
+        boxes = host[o_box:o_box + N * cap * 16].view(np.int16).reshape(N, cap, 4, 2)
+        scores = host[o_sc:o_sc + N * cap * 4].view(np.float32).reshape(N, cap)
+        counts = host[o_cnt:o_cnt + 4 * N].view(np.int32)
+        extras = {k: v.cpu().numpy() for k, v in extras_dev.items()}
+        return boxes, scores, counts, status, extras
+
+    def __call__(self, outs_dict, shape_list, use_padding_resize=False):
+        if use_padding_resize:
+            raise NotImplementedError("use_padding_resize is unused in the shipped configs (SURVEY.md 8(f) rank 4)")
+        boxes, scores, counts, _, _ = self.run_device(outs_dict["maps"], shape_list)
+        res_batch = []
+        for n in range(boxes.shape[0]):
+            k = int(counts[n])
+            if k == 0:
+                pts = np.array([], dtype=np.int16)
+            else:
+                pts = boxes[n, :k].copy()
+            res_batch.append({"points": pts, "scores": [1.0] * k, "box_scores": scores[n, :k].copy()})
+        return res_batch
+
+
+class DistillationDBPostProcess(object):
+    """R/pytocr/postprocess/db_postprocess.py:197-226."""
+
+    def __init__(self, model_name=["student"], key=None, thresh=0.3, box_thresh=0.5, max_candidates=1000,
+                 unclip_ratio=1.5, use_dilation=False, score_mode="poly", cpp_speedup=False,
+                 out_polygon=False, cuda_speedup=True, **kwargs):
+        self.model_name = model_name
+        self.key = key
+        self.post_process = DBPostProcess(thresh=thresh, box_thresh=box_thresh, max_candidates=max_candidates,
+                                          unclip_ratio=unclip_ratio, use_dilation=use_dilation,
+                                          score_mode=score_mode, cpp_speedup=cpp_speedup,
+                                          out_polygon=out_polygon, cuda_speedup=cuda_speedup)
+
+    def __call__(self, predicts, shape_list):
+        results = {}
+        for k in self.model_name:
+            results[k] = self.post_process(predicts[k], shape_list=shape_list)
+        return results

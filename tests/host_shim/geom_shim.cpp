@@ -1,0 +1,62 @@
+// TEST ONLY: compiles pytorchocr_b200/csrc/geometry.cuh with g++ (host side of OCRPP_HD) so the
+// exact code the CUDA kernels run per candidate can be checked against the oracle on a CPU box.
+#include <vector>
+
+#include "../../pytorchocr_b200/csrc/geometry.cuh"
+
+using namespace ocrpp::geom;
+
+extern "C" {
+
+// points int32 [n,2] (any order) -> corners[8] (x0,y0,...), wh[2]; returns hull size
+int shim_min_area_rect(const int* xy, int n, double* corners, double* wh) {
+  std::vector<P2i> p(n), h(n + 2);
+  for (int i = 0; i < n; ++i) p[i] = P2i{xy[2 * i], xy[2 * i + 1]};
+  sort_points_yx(p.data(), n);
+  int hn = hull_sorted(p.data(), n, h.data());
+  Rect r;
+  min_area_rect(h.data(), hn, &r);
+  for (int k = 0; k < 4; ++k) {
+    corners[2 * k] = r.cx[k];
+    corners[2 * k + 1] = r.cy[k];
+  }
+  wh[0] = r.w;
+  wh[1] = r.h;
+  return hn;
+}
+
+int shim_do_offset(const int* quad_xy, double delta, int* out_xy, int cap) {
+  P2i q[4];
+  for (int i = 0; i < 4; ++i) q[i] = P2i{quad_xy[2 * i], quad_xy[2 * i + 1]};
+  std::vector<P2i> out(cap);
+  int m = do_offset_quad(q, delta, out.data(), cap);
+  for (int i = 0; i < m; ++i) {
+    out_xy[2 * i] = out[i].x;
+    out_xy[2 * i + 1] = out[i].y;
+  }
+  return m;
+}
+
+void shim_mini_box(const float* cxy, float* oxy) {
+  float cx[4], cy[4], ox[4], oy[4];
+  for (int i = 0; i < 4; ++i) { cx[i] = cxy[2 * i]; cy[i] = cxy[2 * i + 1]; }
+  mini_box(cx, cy, ox, oy);
+  for (int i = 0; i < 4; ++i) { oxy[2 * i] = ox[i]; oxy[2 * i + 1] = oy[i]; }
+}
+
+void shim_order_clockwise(const float* cxy, float* oxy) {
+  float cx[4], cy[4], ox[4], oy[4];
+  for (int i = 0; i < 4; ++i) { cx[i] = cxy[2 * i]; cy[i] = cxy[2 * i + 1]; }
+  order_points_clockwise(cx, cy, ox, oy);
+  for (int i = 0; i < 4; ++i) { oxy[2 * i] = ox[i]; oxy[2 * i + 1] = oy[i]; }
+}
+
+float shim_unclip_distance(const float* bxy, float ratio) {
+  float bx[4], by[4];
+  for (int i = 0; i < 4; ++i) { bx[i] = bxy[2 * i]; by[i] = bxy[2 * i + 1]; }
+  return unclip_distance(bx, by, ratio);
+}
+
+float shim_roundf(float v) { return roundf_half_away(v); }
+double shim_round_half_even(double v) { return round_half_even(v); }
+}

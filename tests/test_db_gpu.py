@@ -1,0 +1,143 @@
+"""GPU parity: DB / DB++ box extraction through the C-ABI vs the cv2-based oracle
+(oracle/db_oracle.py). Labels bit-exact after canonical renumbering, scores 1e-5 relative,
+vertices 1e-3 px pre-rounding, integer boxes exact outside the rounding band."""
+import cv2
+import numpy as np
+import pytest
+from scipy import ndimage as ndi
+
+from db_compare import canonical_labels, compare_image
+from oracle.db_oracle import DBPostProcessOracle
+from pytorchocr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(thresh=0.3, box_thresh=0.5, max_candidates=1000, unclip_ratio=1.7, score_mode="poly", cpp_speedup=True)
+
+
+def _op(**kw):
+    from pytorchocr_b200.postprocess import build_post_process
+    cfg = dict(CFG, name="DBPostProcess", cuda_speedup=True)
+    cfg.update(kw)
+    return build_post_process(cfg, {"use_gpu": True})
+
+
+def _check(maps, shape_list, op=None, oracle_maps=None, max_fragile=2, **kw):
+    import torch
+    op = op or _op(**kw)
+    dev_in = torch.from_numpy(maps).cuda() if isinstance(maps, np.ndarray) else maps
+    boxes, scores, counts, status, ex = op.run_device(dev_in, shape_list, boxes_f=True, labels=True)
+    ref_in = oracle_maps if oracle_maps is not None else (maps if isinstance(maps, np.ndarray) else maps.float().cpu().numpy())
+    ocfg = dict(CFG)
+    ocfg.update(kw)
+    want = DBPostProcessOracle(**ocfg)({"maps": ref_in}, shape_list, return_details=True)
+    fragile = 0
+    for n in range(len(want)):
+        k = int(counts[n])
+        fragile += compare_image(boxes[n, :k], ex["boxes_f"][n, :k], scores[n, :k], want[n]["details"])
+        fg, _ = ndi.label(ref_in[n, 0] > ocfg["thresh"], structure=np.ones((3, 3)))
+        assert np.array_equal(canonical_labels(fg), ex["labels"][n]), "label map differs"
+    assert fragile <= max_fragile, fragile
+    return want, counts
+
+
+@pytest.mark.parametrize("H,W", [(192, 320), (97, 131), (64, 64), (256, 1280), (33, 1000)])
+def test_db_synth_small(H, W):
+    maps = synth.db_batch(3, seed=synth.BASE_SEED + H, H=H, W=W)
+    shape_list = np.array([[H, W, 1.0, 1.0], [H * 2, W * 2, 2.0, 2.0], [H // 2 + 7, W // 2 + 3, 0.5, 0.5]], np.float64)
+    want, counts = _check(maps, shape_list)
+    assert counts.sum() > 0 or H * W < 10000
+
+
+def test_db_full_size_cfg1():
+    """BASELINE.json config 1: one 1x1x736x1280 map, seed 20221001."""
+    maps = synth.db_batch(1)
+    want, counts = _check(maps, np.array([[736, 1280, 1.0, 1.0]]))
+    assert 150 <= counts[0] <= 260
+
+
+def test_db_batch_full_size():
+    maps = synth.db_batch(4, seed=synth.BASE_SEED + 17)
+    _check(maps, np.array([[736, 1280, 1.0, 1.0]] * 4), max_fragile=4)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_db_random_blob_fields(seed):
+    """Adversarial topology: many holes, islands in holes, diagonal pinches, specks."""
+    rng = np.random.default_rng(seed)
+    H, W = 120, 152
+    sig = [0.6, 1.0, 1.5, 2.5, 0.45, 2.0][seed]
+    p = cv2.GaussianBlur(rng.random((2, H, W)).astype(np.float32), (0, 0), sig)
+    p = np.stack([cv2.GaussianBlur(rng.random((H, W)).astype(np.float32), (0, 0), sig) for _ in range(2)])
+    lo, hi = np.quantile(p, 0.02), np.quantile(p, 0.98)
+    p = np.clip((p - lo) / (hi - lo), 0, 1).astype(np.float32)
+    q = float(np.quantile(p, [0.45, 0.5, 0.55, 0.6, 0.5, 0.4][seed]))
+    maps = p[:, None]
+    _check(maps, np.array([[H, W, 1.0, 1.0]] * 2), thresh=q, box_thresh=q + 0.02, max_fragile=6)
+
+
+def test_db_nested_rings_and_edges():
+    H, W = 96, 128
+    m = np.full((H, W), 0.02, np.float32)
+    m[8:88, 8:120] = 0.9       # big block
+    m[16:80, 16:112] = 0.05    # hole
+    m[24:72, 24:104] = 0.8     # island in the hole
+    m[32:64, 32:96] = 0.1      # hole in the island
+    m[40:56, 40:88] = 0.95     # island in that hole
+    m[0:5, 0:9] = 0.9          # touches the corner
+    m[90:96, 50:70] = 0.9      # touches the bottom edge
+    m[2, 100] = 0.9            # single pixel
+    m[60:70, 124] = 0.9        # vertical 1-px run
+    for i in range(6):
+        m[85 + i if 85 + i < H else H - 1, 2 + i] = 0.9   # diagonal 1-px run
+    maps = m[None, None]
+    _check(maps, np.array([[H, W, 1.0, 1.0]]), box_thresh=0.3)
+
+
+def test_db_empty_and_full():
+    H, W = 64, 96
+    z = np.zeros((2, 1, H, W), np.float32)
+    z[1] = 1.0
+    want, counts = _check(z, np.array([[H, W, 1.0, 1.0]] * 2))
+    assert counts[0] == 0
+    op = _op()
+    import torch
+    res = op({"maps": torch.from_numpy(z).cuda()}, np.array([[H, W, 1.0, 1.0]] * 2))
+    assert res[0]["points"].shape == (0,) and res[0]["scores"] == []
+    assert res[1]["points"].dtype == np.int16
+
+
+def test_db_input_kinds_and_fp16():
+    import torch
+    H, W = 160, 256
+    maps = synth.db_batch(2, seed=5, H=H, W=W)
+    sl = np.array([[H, W, 1.0, 1.0]] * 2)
+    op = _op()
+    ref = DBPostProcessOracle(**CFG)({"maps": maps}, sl)
+    def same(res):
+        for r, w in zip(res, ref):
+            a = sorted(map(tuple, r["points"].reshape(-1, 8).tolist()))
+            b = sorted(map(tuple, w["points"].reshape(-1, 8).tolist()))
+            assert a == b
+            assert r["scores"] == w["scores"]
+    same(op({"maps": maps}, sl))                                   # numpy (TRT path, infer_det_trt.py:148-151)
+    same(op({"maps": torch.from_numpy(maps)}, sl))                 # CPU tensor
+    multi = torch.zeros((2, 3, H, W + 8), dtype=torch.float32, device="cuda")
+    multi[:, 0, :, :W] = torch.from_numpy(maps[:, 0]).cuda()
+    same(op({"maps": multi[:, :, :, :W]}, sl))                     # strided view, channel 0 of 3
+    half = torch.from_numpy(maps).half()
+    _check(half.cuda(), sl, oracle_maps=half.float().numpy())      # fp16 map, oracle sees upcast values
+
+
+def test_db_run_capacity_retry_and_bad_values():
+    import torch
+    from pytorchocr_b200 import _lib
+    H, W = 64, 64
+    rng = np.random.default_rng(0)
+    noise = (rng.random((1, 1, H, W)) > 0.5).astype(np.float32)   # ~H*W/2 runs >> default capacity floor
+    op = _op(max_runs=64)
+    want, counts = _check(noise, np.array([[H, W, 1.0, 1.0]]), op=op, max_fragile=50)
+    bad = noise.copy()
+    bad[0, 0, 3, 3] = np.nan
+    with pytest.raises(_lib.OcrppError):
+        _op()({"maps": torch.from_numpy(bad).cuda()}, np.array([[H, W, 1.0, 1.0]]))

@@ -1,0 +1,137 @@
+"""CPU check of the per-candidate geometry code the CUDA kernels execute
+(pytorchocr_b200/csrc/geometry.cuh compiled for the host by tests/host_shim) against the oracle
+and against cv2 / the reference's Clipper."""
+import ctypes as C
+import os
+import subprocess
+
+import cv2
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import db_oracle, geometry_oracle as G
+from oracle.pse_oracle import order_points_clockwise
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("shim") / "libgeomshim.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                           os.path.join(ROOT, "tests", "host_shim", "geom_shim.cpp"), "-o", out])
+    L = C.CDLL(out)
+    L.shim_min_area_rect.restype = C.c_int
+    L.shim_do_offset.restype = C.c_int
+    L.shim_do_offset.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int]
+    L.shim_unclip_distance.restype = C.c_float
+    L.shim_unclip_distance.argtypes = [C.c_void_p, C.c_float]
+    L.shim_roundf.restype = C.c_float
+    L.shim_roundf.argtypes = [C.c_float]
+    L.shim_round_half_even.restype = C.c_double
+    L.shim_round_half_even.argtypes = [C.c_double]
+    return L
+
+
+def _sorted_pts(p):
+    p = np.asarray(p, np.float64).reshape(-1, 2)
+    return p[np.lexsort((p[:, 1], p[:, 0]))]
+
+
+def _set_dist(a, b):
+    """symmetric max over points of the distance to the nearest point of the other set"""
+    a = np.asarray(a, np.float64).reshape(-1, 2)
+    b = np.asarray(b, np.float64).reshape(-1, 2)
+    d = np.abs(a[:, None, :] - b[None, :, :]).max(-1)
+    return max(d.min(1).max(), d.min(0).max())
+
+
+def _rect(shim, pts):
+    pts = np.ascontiguousarray(pts, np.int32)
+    corners = np.zeros(8, np.float64)
+    wh = np.zeros(2, np.float64)
+    hn = shim.shim_min_area_rect(pts.ctypes.data_as(C.c_void_p), len(pts), corners.ctypes.data_as(C.c_void_p),
+                                 wh.ctypes.data_as(C.c_void_p))
+    return corners.reshape(4, 2), wh, hn
+
+
+def _raster_blob(rng, ragged):
+    c = rng.uniform(60, 300, 2)
+    box = cv2.boxPoints(((float(c[0]), float(c[1])), (float(rng.uniform(6, 90)), float(rng.uniform(3, 25))),
+                         float(rng.uniform(-90, 90))))
+    box -= box.min(0) - 3
+    m = np.zeros((int(box[:, 1].max()) + 6, int(box[:, 0].max()) + 6), np.uint8)
+    cv2.fillPoly(m, [np.round(box).astype(np.int32)], 1)
+    if ragged:
+        m &= (rng.random(m.shape) > 0.05).astype(np.uint8)
+    ys, xs = np.nonzero(m)
+    return np.stack([xs, ys], 1)
+
+
+def test_min_area_rect_vs_cv2_and_oracle(shim):
+    rng = np.random.default_rng(3)
+    worst = 0.0
+    for i in range(800):
+        pts = _raster_blob(rng, i % 2 == 0)
+        if len(pts) < 3:
+            continue
+        got, wh, hn = _rect(shim, pts)
+        ref = cv2.boxPoints(cv2.minAreaRect(pts.astype(np.int32)))
+        err = _set_dist(ref, got)
+        worst = max(worst, err)
+        assert err < 1e-3, (i, err)
+        o_c, (ow, oh) = G.min_area_rect(pts)
+        assert _set_dist(o_c, got) < 1e-9
+        assert hn == len(G.convex_hull(pts))
+    assert worst < 1e-3
+
+
+def test_min_area_rect_degenerate(shim):
+    got, wh, hn = _rect(shim, [[5, 7]])
+    assert hn == 1 and wh.tolist() == [0.0, 0.0] and np.all(got == [5, 7])
+    got, wh, hn = _rect(shim, [[1, 1], [4, 4], [2, 2], [3, 3]])
+    assert hn == 2 and abs(wh[0] - 3 * 2 ** 0.5) < 1e-12 and wh[1] == 0.0
+    got, wh, hn = _rect(shim, [[x, y] for x in range(2, 11) for y in range(3, 7)])
+    assert hn == 4 and sorted(wh.tolist()) == [3.0, 8.0]
+    assert np.array_equal(_sorted_pts(got), _sorted_pts([[2, 3], [10, 3], [10, 6], [2, 6]]))  # exact integers
+
+
+def test_do_offset_vs_oracle_and_clipper(shim):
+    rng = np.random.default_rng(5)
+    for i in range(1500):
+        c = rng.uniform(50, 1200, 2)
+        box = cv2.boxPoints(((float(c[0]), float(c[1])), (float(rng.uniform(2, 400)), float(rng.uniform(1, 60))),
+                             float(rng.uniform(-90, 90))))
+        mini, _ = db_oracle.get_mini_boxes(cv2.minAreaRect(box))
+        d_ref = db_oracle.get_contour_area(mini, 1.7)
+        d_got = shim.shim_unclip_distance(np.ascontiguousarray(mini, np.float32).ctypes.data_as(C.c_void_p), 1.7)
+        assert np.float32(d_got) == np.float32(d_ref)
+        quad = np.array([(int(mini[k][0]), int(mini[k][1])) for k in range(4)], np.int32)
+        out = np.zeros((512, 2), np.int32)
+        m = shim.shim_do_offset(quad.ctypes.data_as(C.c_void_p), float(d_ref), out.ctypes.data_as(C.c_void_p), 512)
+        want = G.do_offset(quad.tolist(), float(d_ref))
+        assert m == len(want)
+        assert out[:m].tolist() == [list(p) for p in want]
+    # degenerate: duplicate corners -> rejected
+    quad = np.array([[3, 3], [3, 3], [9, 3], [9, 3]], np.int32)
+    out = np.zeros((64, 2), np.int32)
+    assert shim.shim_do_offset(quad.ctypes.data_as(C.c_void_p), 2.0, out.ctypes.data_as(C.c_void_p), 64) == 0
+    # capacity overflow is reported
+    quad = np.array([[0, 0], [900, 0], [900, 700], [0, 700]], np.int32)
+    assert shim.shim_do_offset(quad.ctypes.data_as(C.c_void_p), 300.0, out.ctypes.data_as(C.c_void_p), 8) == -1
+
+
+def test_box_orderings_and_rounding(shim):
+    rng = np.random.default_rng(9)
+    for _ in range(500):
+        rect = ((float(rng.uniform(20, 500)), float(rng.uniform(20, 500))),
+                (float(rng.uniform(3, 100)), float(rng.uniform(3, 40))), float(rng.uniform(-90, 90)))
+        pts = cv2.boxPoints(rect)
+        o = np.zeros((4, 2), np.float32)
+        shim.shim_mini_box(np.ascontiguousarray(pts).ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p))
+        want, _ = db_oracle.get_mini_boxes(rect)
+        assert np.array_equal(o, want)
+        shim.shim_order_clockwise(np.ascontiguousarray(pts).ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(o, order_points_clockwise(pts))
+    for v in (0.5, 1.5, 2.5, -0.5, -1.5, 0.49999997, 3.4999998, 1e6 + 0.5):
+        assert shim.shim_roundf(v) == db_oracle.roundf(np.float32(v))
+        assert shim.shim_round_half_even(v) == np.round(v)
