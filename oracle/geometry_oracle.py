@@ -161,6 +161,25 @@ def min_area_rect(points):
         return np.array([hull[0]] * 4, np.float64), (0.0, 0.0)
     H = np.array(hull, np.float64)
     best = None
+
+    def folded(d):
+        qx, qy = int(round(d[0])), int(round(d[1]))
+        for _ in range(3):
+            if qx > 0 and qy >= 0:
+                break
+            qx, qy = qy, -qx
+        return qx, qy
+
+    def better(a, b):
+        """a, b = (area, qx, qy, index). Smaller area; exact tie -> larger edge angle modulo 90 degrees
+        (cv::minAreaRect keeps the LAST minimum of a quarter-turn caliper sweep); then smaller index."""
+        if abs(a[0] - b[0]) > 1e-12 * max(a[0], b[0]):
+            return a[0] < b[0]
+        l, r = a[2] * b[1], b[2] * a[1]
+        if l != r:
+            return l > r
+        return a[3] < b[3]
+
     for i in range(n):
         p, q = H[i], H[(i + 1) % n]
         d = q - p
@@ -171,8 +190,10 @@ def min_area_rect(points):
         t = (H - p) @ v
         smin, smax, tmin, tmax = s.min(), s.max(), t.min(), t.max()
         area = (smax - smin) * (tmax - tmin)
-        if best is None or area < best[0]:
-            best = (area, p, u, v, smin, smax, tmin, tmax)
+        qx, qy = folded(d)
+        key = (area, qx, qy, i)
+        if best is None or better(key, best[0]):
+            best = (key, p, u, v, smin, smax, tmin, tmax)
         if n == 2:
             break
     _, p, u, v, smin, smax, tmin, tmax = best

@@ -526,10 +526,13 @@ __global__ void __launch_bounds__(kRunBlk) db_extents_kernel(DbParams p) {
     // (b) hole run: ring pixels (each counted once: owner = first of up/left/right/down neighbour
     //     that lies in the hole) and their row extents; (c) stair pixels of the hole contour.
     const int h = root;
+    const int C = p.cpar[ro + h];  // enclosing foreground component: the ring consists of ITS pixels only
     const int off = p.rowoff[ro + h];
     const int y0 = (yf[h] & 0x7fff) - 1;
     int cnt = 0;
     long long s = 0;
+    // foreground pixel of the enclosing component (islands inside the hole are not ring pixels)
+    auto in_C = [&](int x, int yy) { return bit_at(bits, Wd, x, yy) && par[run_at(rowptr, xs, yy, x)] == C; };
     auto ring = [&](int x, int yy) {
       ++cnt;
       s += px(x, yy);
@@ -540,20 +543,20 @@ __global__ void __launch_bounds__(kRunBlk) db_extents_kernel(DbParams p) {
     };
     // hole runs never touch the frame: a-1, b+1, y-1, y+1 are inside the image
     for (int x = a; x <= b; ++x) {
-      if (bit_at(bits, Wd, x, y + 1)) ring(x, y + 1);  // its UP neighbour is in h: always the owner
-      if (bit_at(bits, Wd, x, y - 1)) {                // p = (x, y-1): down neighbour in h
+      if (in_C(x, y + 1)) ring(x, y + 1);  // its UP neighbour is in h: always the owner
+      if (in_C(x, y - 1)) {                // p = (x, y-1): down neighbour in h
         if (!in_hole(x, y - 2, h) && !in_hole(x - 1, y - 1, h) && !in_hole(x + 1, y - 1, h)) ring(x, y - 1);
       }
     }
     // p = (b+1, y): left neighbour in h; owner unless its up neighbour is in h
-    if (!in_hole(b + 1, y - 1, h)) ring(b + 1, y);
+    if (in_C(b + 1, y) && !in_hole(b + 1, y - 1, h)) ring(b + 1, y);
     // p = (a-1, y): right neighbour in h; owner unless up or left neighbour is in h
-    if (!in_hole(a - 1, y - 1, h) && !in_hole(a - 2, y, h)) ring(a - 1, y);
+    if (in_C(a - 1, y) && !in_hole(a - 1, y - 1, h) && !in_hole(a - 2, y, h)) ring(a - 1, y);
     // (c) o = (b, y) is the last pixel of a hole run, q = (b+1, y) is foreground; for dy in {-1,+1}:
-    //     p = (b, y+dy) foreground => contour steps diagonally p <-> q and the 4-connected boundary
-    //     also paints e = (b+1, y+dy)
+    //     p = (b, y+dy) in C => the hole contour steps diagonally p <-> q and the 4-connected
+    //     boundary also paints e = (b+1, y+dy)
     for (int dy = -1; dy <= 1; dy += 2) {
-      if (!bit_at(bits, Wd, b, y + dy)) continue;
+      if (!in_C(b, y + dy)) continue;
       const int ex = b + 1, ey = y + dy;
       if (dy == -1) {
         // the same e is produced from o' = (b, y-2) with dy=+1 when that qualifies: count it there
@@ -617,21 +620,29 @@ __device__ void warp_min_area_rect(const P2i* h, int n, geom::Rect* r, int lane)
     return;
   }
   const int ne = n == 2 ? 1 : n;
-  double best = 1e300;
+  geom::EdgeFit bf;
+  bf.area = 1e300;
+  bf.qx = 1;
+  bf.qy = 0;
   int bi = 0x7fffffff;
   for (int i = lane; i < ne; i += 32) {
     const geom::EdgeFit f = geom::fit_edge(h, n, i);
-    if (f.area < best) {
-      best = f.area;
+    if (geom::fit_better(f, i, bf, bi)) {
+      bf = f;
       bi = i;
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    const double oa = __shfl_xor_sync(0xffffffffu, best, o);
+    geom::EdgeFit of;
+    of.area = __shfl_xor_sync(0xffffffffu, bf.area, o);
+    of.qx = __shfl_xor_sync(0xffffffffu, bf.qx, o);
+    of.qy = __shfl_xor_sync(0xffffffffu, bf.qy, o);
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (oa < best || (oa == best && oi < bi)) {
-      best = oa;
+    if (oi != 0x7fffffff && (bi == 0x7fffffff || geom::fit_better(of, oi, bf, bi))) {
+      bf.area = of.area;
+      bf.qx = of.qx;
+      bf.qy = of.qy;
       bi = oi;
     }
   }

@@ -115,8 +115,22 @@ OCRPP_HD int hull_sorted(const P2i* pts, int n, P2i* out) {
 struct EdgeFit {
   long long smin, smax, tmin, tmax;
   long long len2;
+  long long qx, qy;  // edge direction folded by quarter turns into qx > 0, qy >= 0
   double area;
 };
+
+// Which of two edge-aligned rectangles wins. Smaller area; on an exact tie the edge whose
+// direction has the larger angle modulo 90 degrees (cv::minAreaRect's rotating calipers sweep a
+// quarter turn starting axis-aligned and keep the LAST minimum, so e.g. a diagonal rectangle beats
+// an equal-area axis-aligned one); then the smaller edge index.
+OCRPP_HD bool fit_better(const EdgeFit& a, int ia, const EdgeFit& b, int ib) {
+  const double m = a.area > b.area ? a.area : b.area;
+  const double d = a.area - b.area;
+  if ((d < 0 ? -d : d) > 1e-12 * m) return a.area < b.area;
+  const long long l = a.qy * b.qx, r = b.qy * a.qx;
+  if (l != r) return l > r;
+  return ia < ib;
+}
 
 OCRPP_HD EdgeFit fit_edge(const P2i* h, int n, int i) {
   const P2i p = h[i], q = h[(i + 1 == n) ? 0 : i + 1];
@@ -134,6 +148,14 @@ OCRPP_HD EdgeFit fit_edge(const P2i* h, int n, int i) {
   }
   f.len2 = dx * dx + dy * dy;
   f.area = (double)(f.smax - f.smin) * (double)(f.tmax - f.tmin) / (double)f.len2;
+  long long qx = dx, qy = dy;
+  for (int t = 0; t < 3 && !(qx > 0 && qy >= 0); ++t) {  // rotate by -90 degrees: (x,y) -> (y,-x)
+    const long long tx = qy;
+    qy = -qx;
+    qx = tx;
+  }
+  f.qx = qx;
+  f.qy = qy;
   return f;
 }
 
@@ -155,7 +177,7 @@ OCRPP_HD void rect_from_fit(const P2i* h, int n, int i, const EdgeFit& f, Rect* 
 }
 
 // Sequential reference formulation (the device path parallelises the edge loop over a warp and
-// must pick the same edge: smallest area, then smallest edge index).
+// must pick the same edge, see fit_better).
 OCRPP_HD void min_area_rect(const P2i* h, int n, Rect* r) {
   if (n == 1) {
     for (int k = 0; k < 4; ++k) {
@@ -170,7 +192,7 @@ OCRPP_HD void min_area_rect(const P2i* h, int n, Rect* r) {
   const int ne = n == 2 ? 1 : n;
   for (int i = 1; i < ne; ++i) {
     EdgeFit f = fit_edge(h, n, i);
-    if (f.area < bf.area) {
+    if (fit_better(f, i, bf, best)) {
       bf = f;
       best = i;
     }

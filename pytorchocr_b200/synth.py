@@ -26,6 +26,8 @@ def _place_rects(rng, H, W, n, hh_rng=(5, 10), hw_rng=(15, 37), max_angle=20.0, 
         hw = int(rng.integers(hw_rng[0], hw_rng[1] + 1))
         ang = float(rng.uniform(-max_angle, max_angle))
         r = math.hypot(hw, hh) + margin + 2
+        if W - r <= r or H - r <= r:
+            continue
         cx = float(rng.uniform(r, W - r))
         cy = float(rng.uniform(r, H - r))
         box = cv2.boxPoints(((cx, cy), (2.0 * (hw + margin), 2.0 * (hh + margin)), ang))
