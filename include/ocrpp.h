@@ -67,6 +67,17 @@ OCRPP_API const char* ocrpp_last_error(void);
 OCRPP_API int64_t ocrpp_launch_count(void);
 OCRPP_API void ocrpp_reset_launch_count(void);
 
+/* Per-kernel device timing for bench.py's roofline. While enabled, every detection entry point
+ * brackets each of its kernels with cudaEventRecord on the caller's stream (events only, no
+ * synchronisation). After the stream is synchronised, ocrpp_profile_read() returns, for phase i,
+ * the SUM of that phase's durations in milliseconds over all calls since the last
+ * ocrpp_profile_reset() (at most 64 calls are kept) and the number of calls in *calls_out.
+ * Returns the number of phases written. Phase 0 is always the kernel that streams the input maps. */
+OCRPP_API void ocrpp_profile_enable(int on);
+OCRPP_API void ocrpp_profile_reset(void);
+OCRPP_API int ocrpp_profile_read(float* ms_out, int cap, int* calls_out);
+OCRPP_API const char* ocrpp_profile_phase_name(int phase);
+
 /* ---------------------------------------------------------------------------------------------
  * CTC greedy decode. probs element (t,b,c) is at probs_dev[t*stride_t + b*stride_b + c]
  * (element strides; class stride is 1). For every line b:

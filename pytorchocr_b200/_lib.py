@@ -23,6 +23,10 @@ SIGNATURES = {
     "ocrpp_last_error": (C.c_char_p, []),
     "ocrpp_launch_count": (C.c_int64, []),
     "ocrpp_reset_launch_count": (None, []),
+    "ocrpp_profile_enable": (None, [C.c_int]),
+    "ocrpp_profile_reset": (None, []),
+    "ocrpp_profile_read": (C.c_int, [C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),
+    "ocrpp_profile_phase_name": (C.c_char_p, [C.c_int]),
     "ocrpp_ctc_greedy": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ocrpp_db_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -74,3 +78,12 @@ def require_cuda():
     if not torch.cuda.is_available():
         raise OcrppError("pytorchocr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
     return torch
+
+
+def profile_read():
+    """-> (calls, [(phase_name, total_ms), ...]) since the last ocrpp_profile_reset()."""
+    L = lib()
+    ms = (C.c_float * 16)()
+    calls = C.c_int(0)
+    n = L.ocrpp_profile_read(ms, 16, C.byref(calls))
+    return calls.value, [(L.ocrpp_profile_phase_name(i).decode(), float(ms[i])) for i in range(n)]

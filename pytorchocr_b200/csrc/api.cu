@@ -18,9 +18,62 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+// ---- profiling ring --------------------------------------------------------------------------
+namespace {
+bool g_prof_on = false;
+int g_prof_calls = 0;
+int g_prof_phases = 0;
+const char* g_prof_names[kProfMaxPhases] = {nullptr};
+cudaEvent_t g_prof_ev[kProfMaxCalls][kProfMaxPhases + 1];
+bool g_prof_ev_ready = false;
+}  // namespace
+
+bool profile_on() { return g_prof_on; }
+
+int profile_begin(cudaStream_t s) {
+  if (!g_prof_on || g_prof_calls >= kProfMaxCalls) return -1;
+  if (!g_prof_ev_ready) {
+    for (int c = 0; c < kProfMaxCalls; ++c)
+      for (int p = 0; p <= kProfMaxPhases; ++p) cudaEventCreate(&g_prof_ev[c][p]);
+    g_prof_ev_ready = true;
+  }
+  const int slot = g_prof_calls++;
+  cudaEventRecord(g_prof_ev[slot][0], s);
+  return slot;
+}
+
+void profile_mark(int slot, int phase, const char* name, cudaStream_t s) {
+  if (slot < 0 || phase >= kProfMaxPhases) return;
+  cudaEventRecord(g_prof_ev[slot][phase + 1], s);
+  g_prof_names[phase] = name;
+  if (phase + 1 > g_prof_phases) g_prof_phases = phase + 1;
+}
+
 }  // namespace ocrpp
 
 extern "C" {
+
+void ocrpp_profile_enable(int on) { ocrpp::g_prof_on = on != 0; }
+void ocrpp_profile_reset(void) { ocrpp::g_prof_calls = 0; }
+int ocrpp_profile_read(float* ms_out, int cap, int* calls_out) {
+  using namespace ocrpp;
+  const int np = g_prof_phases < cap ? g_prof_phases : cap;
+  for (int p = 0; p < np; ++p) {
+    float sum = 0.f;
+    for (int c = 0; c < g_prof_calls; ++c) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, g_prof_ev[c][p], g_prof_ev[c][p + 1]) == cudaSuccess) sum += ms;
+    }
+    ms_out[p] = sum;
+  }
+  if (calls_out) *calls_out = g_prof_calls;
+  return np;
+}
+const char* ocrpp_profile_phase_name(int phase) {
+  using namespace ocrpp;
+  return (phase >= 0 && phase < g_prof_phases && g_prof_names[phase]) ? g_prof_names[phase] : "";
+}
+
 
 int ocrpp_abi_version(void) { return OCRPP_ABI_VERSION; }
 const char* ocrpp_last_error(void) { return ocrpp::last_error_buf(); }

@@ -59,6 +59,26 @@ __device__ __forceinline__ float load_scalar<float>(const float* p) { return __l
 template <>
 __device__ __forceinline__ float load_scalar<__half>(const __half* p) { return __half2float(__ldg(p)); }
 
+// ---- per-kernel event timing (ocrpp_profile_*) ---------------------------------------------------
+constexpr int kProfMaxPhases = 16;
+constexpr int kProfMaxCalls = 64;
+bool profile_on();
+// starts a profiled call; returns a slot (>= 0) or -1 when profiling is off / the ring is full
+int profile_begin(cudaStream_t s);
+// records the end of phase `phase` (named `name`) of call `slot`
+void profile_mark(int slot, int phase, const char* name, cudaStream_t s);
+
+struct ProfileScope {
+  int slot;
+  int phase = 0;
+  cudaStream_t s;
+  explicit ProfileScope(cudaStream_t st) : slot(profile_begin(st)), s(st) {}
+  void mark(const char* name) {
+    if (slot >= 0) profile_mark(slot, phase, name, s);
+    ++phase;
+  }
+};
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace ocrpp

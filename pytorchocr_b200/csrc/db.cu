@@ -53,7 +53,8 @@ struct DbParams {
   int32_t *ext_l, *ext_r;          // [E]
   P2i* hull;                       // [4*E]
   int E;
-  int32_t *nruns, *ext_alloc, *imgflags, *ncand;  // [1] per image
+  int32_t *nruns, *ext_alloc, *imgflags, *ncand, *nbig;  // [1] per image
+  int32_t* big;          // [maxc] candidates deferred to the generic geometry kernel
   int32_t* cand;         // [maxc]
   int32_t* res_keep;     // [maxc]
   int16_t* res_box;      // [maxc*8]
@@ -602,7 +603,8 @@ __global__ void __launch_bounds__(kRunThreads) db_rank_kernel(DbParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K9: per-candidate geometry, one warp per candidate.
+// K9b: generic per-candidate geometry, one warp per candidate: handles the (rare) candidates the
+// fast kernel below defers (more than kSmallRows rows, or an unclip polygon above its capacity).
 // ------------------------------------------------------------------------------------------------
 constexpr int kGeoWarps = 4;
 constexpr int kSmallRows = 64;              // candidates up to this many rows build their hull in smem
@@ -650,16 +652,17 @@ __device__ void warp_min_area_rect(const P2i* h, int n, geom::Rect* r, int lane)
   geom::rect_from_fit(h, n, bi, f, r);
 }
 
-__global__ void __launch_bounds__(kGeoWarps * 32) db_geometry_kernel(DbParams p) {
+__global__ void __launch_bounds__(kGeoWarps * 32) db_geometry_big_kernel(DbParams p) {
   __shared__ P2i s_pts[kGeoWarps][2 * kSmallRows];
   __shared__ P2i s_hull[kGeoWarps][2 * kSmallRows + 2];
   __shared__ P2i s_off[kGeoWarps][kOffCap];
   __shared__ P2i s_offh[kGeoWarps][kOffCap + 2];
   const int n = blockIdx.y;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k = blockIdx.x * kGeoWarps + wib;
-  if (k >= p.ncand[n]) return;
   const size_t ro = (size_t)n * p.R;
+  const int nbig = min(p.nbig[n], p.maxc);
+  for (int bi = blockIdx.x * kGeoWarps + wib; bi < nbig; bi += gridDim.x * kGeoWarps) {
+  const int k = p.big[(size_t)n * p.maxc + bi];
   const size_t ko = (size_t)n * p.maxc + k;
   const int c = p.cand[ko];
   const int fg = p.run_yf[ro + c] >> 15;
@@ -672,12 +675,12 @@ __global__ void __launch_bounds__(kGeoWarps * 32) db_geometry_kernel(DbParams p)
     const int bw = p.xmax[ro + c] - p.xmin[ro + c] + 1, bh = p.ymax[ro + c] - y_first + 1;
     const bool diag = (bw == bh && bw == area) &&
                       (p.dmin[ro + c] == p.dmax[ro + c] || p.smin[ro + c] == p.smax[ro + c]);
-    if (area == 1 || (bh == 1 && area == bw) || (bw == 1 && area == bh) || diag) return;
+    if (area == 1 || (bh == 1 && area == bw) || (bw == 1 && area == bh) || diag) continue;
   }
   const int off = p.rowoff[ro + c];
   if (off < 0) {  // extent arena exhausted (cannot happen with E = 4R); fail loudly
     if (lane == 0) atomicOr(&p.imgflags[n], OCRPP_IMG_RUN_OVERFLOW);
-    return;
+    continue;
   }
   const int nrows = fg ? (p.ymax[ro + c] - y_first + 1) : (p.ymax[ro + c] - y_first + 3);
   const int y0 = fg ? y_first : y_first - 1;
@@ -712,13 +715,13 @@ __global__ void __launch_bounds__(kGeoWarps * 32) db_geometry_kernel(DbParams p)
   }
   geom::mini_box(cx, cy, mx, my);
   const float ssid = fmaxf((float)rect.w, (float)rect.h);
-  if (ssid < 3.f) return;
+  if (ssid < 3.f) continue;
 
   // BoxScore (db_postprocess.cpp:194-229): mean over the filled contour, double accumulation
   const long long tot = p.sum[ro + c] + p.fsum[ro + c] + p.xsum[ro + c];
   const int cnt = p.area[ro + c] + p.fcnt[ro + c] + p.xcnt[ro + c];
   const float score = (float)(((double)tot / kFixScale) / (double)cnt);
-  if (score < p.box_thresh) return;
+  if (score < p.box_thresh) continue;
 
   // UnClip (db_postprocess.cpp:34-64)
   const float distance = geom::unclip_distance(mx, my, p.unclip_ratio);
@@ -732,26 +735,292 @@ __global__ void __launch_bounds__(kGeoWarps * 32) db_geometry_kernel(DbParams p)
   m = __shfl_sync(0xffffffffu, m, 0);
   if (m < 0) {  // polygon larger than kOffCap points: unsupported size, fail loudly
     if (lane == 0) atomicOr(&p.imgflags[n], OCRPP_IMG_RUN_OVERFLOW);
-    return;
+    continue;
   }
-  if (m == 0) return;  // empty solution -> RotatedRect((0,0),(1,1),0) -> dropped by the 1.001 test
+  if (m == 0) continue;  // empty solution -> RotatedRect((0,0),(1,1),0) -> dropped by the 1.001 test
   int hm = 0;
   if (lane == 0) hm = geom::hull_sorted(s_off[wib], m, s_offh[wib]);
   hm = __shfl_sync(0xffffffffu, hm, 0);
   __syncwarp();
   geom::Rect rect2;
   warp_min_area_rect(s_offh[wib], hm, &rect2, lane);
-  if ((float)rect2.h < 1.001 && (float)rect2.w < 1.001) return;
+  if ((float)rect2.h < 1.001 && (float)rect2.w < 1.001) continue;
   for (int q = 0; q < 4; ++q) {
     cx[q] = (float)rect2.cx[q];
     cy[q] = (float)rect2.cy[q];
   }
   geom::mini_box(cx, cy, mx, my);
   const float ssid2 = fmaxf((float)rect2.w, (float)rect2.h);
-  if (ssid2 < 5.f) return;
+  if (ssid2 < 5.f) continue;
 
   if (lane == 0) {
     const float sw = (float)p.src_wh[2 * n], sh = (float)p.src_wh[2 * n + 1];
+    for (int q = 0; q < 4; ++q) {
+      const float fx = geom::fmul(geom::fdiv(mx[q], (float)p.W), sw);
+      const float fy = geom::fmul(geom::fdiv(my[q], (float)p.H), sh);
+      p.res_boxf[ko * 8 + 2 * q] = fx;
+      p.res_boxf[ko * 8 + 2 * q + 1] = fy;
+      p.res_box[ko * 8 + 2 * q] = (int16_t)(int)fminf(fmaxf(geom::roundf_half_away(fx), 0.f), sw);
+      p.res_box[ko * 8 + 2 * q + 1] = (int16_t)(int)fminf(fmaxf(geom::roundf_half_away(fy), 0.f), sh);
+    }
+    p.res_score[ko] = score;
+    p.res_keep[ko] = 1;
+  }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9: per-candidate geometry, FOUR candidates per warp (groups of 8 lanes), 32-bit integer
+// projections, points packed as short2 in shared memory. Candidates that do not fit its fixed
+// buffers are appended to the per-image `big` list and handled by db_geometry_big_kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGrp = 8;                       // lanes per candidate
+constexpr int kGeoThreads = 128;              // 16 candidates per CTA
+constexpr int kFastRows = 64;                 // max rows of a candidate's point set
+constexpr int kFastOff = 96;                  // max points of its unclip polygon
+
+__device__ __forceinline__ int pk(int x, int y) { return (x & 0xffff) | (y << 16); }
+__device__ __forceinline__ int pkx(int v) { return (int)(short)(v & 0xffff); }
+__device__ __forceinline__ int pky(int v) { return v >> 16; }
+
+__device__ __forceinline__ int cross32(int o, int a, int b) {
+  return (pkx(a) - pkx(o)) * (pky(b) - pky(o)) - (pky(a) - pky(o)) * (pkx(b) - pkx(o));
+}
+
+// monotone chain over packed points sorted by (y, x); same result as geom::hull_sorted
+__device__ int hull_sorted32(const int* pts, int n, int* out) {
+  if (n <= 1) {
+    if (n == 1) out[0] = pts[0];
+    return n;
+  }
+  int k = 0;
+  for (int i = 0; i < n; ++i) {
+    const int q = pts[i];
+    if (i > 0 && q == pts[i - 1]) continue;
+    while (k >= 2 && cross32(out[k - 2], out[k - 1], q) <= 0) --k;
+    out[k++] = q;
+  }
+  if (k == 1) return 1;
+  const int lo = k + 1;
+  for (int i = n - 2; i >= 0; --i) {
+    const int q = pts[i];
+    if (q == pts[i + 1]) continue;
+    while (k >= lo && cross32(out[k - 2], out[k - 1], q) <= 0) --k;
+    out[k++] = q;
+  }
+  return k - 1;
+}
+
+struct Fit32 {
+  int smin, smax, tmin, tmax, len2, qx, qy, idx;
+  double area;
+};
+
+__device__ __forceinline__ bool fit32_better(const Fit32& a, const Fit32& b) {
+  if (b.idx == 0x7fffffff) return a.idx != 0x7fffffff;
+  if (a.idx == 0x7fffffff) return false;
+  const double m = fmax(a.area, b.area);
+  if (fabs(a.area - b.area) > 1e-12 * m) return a.area < b.area;
+  const long long l = (long long)a.qy * b.qx, r = (long long)b.qy * a.qx;
+  if (l != r) return l > r;
+  return a.idx < b.idx;
+}
+
+// group-parallel min-area rectangle over packed hull points in shared memory; identical choice
+// to geom::min_area_rect (exact integer projections, fit_better ordering)
+__device__ void group_min_area_rect(const int* h, int n, geom::Rect* r, int gl, unsigned gmask) {
+  if (n == 1) {
+    for (int q = 0; q < 4; ++q) {
+      r->cx[q] = pkx(h[0]);
+      r->cy[q] = pky(h[0]);
+    }
+    r->w = r->h = 0.0;
+    return;
+  }
+  const int ne = n == 2 ? 1 : n;
+  Fit32 best;
+  best.idx = 0x7fffffff;
+  best.area = 1e300;
+  best.qx = 1;
+  best.qy = 0;
+  best.smin = best.smax = best.tmin = best.tmax = 0;
+  best.len2 = 1;
+  for (int i = gl; i < ne; i += kGrp) {
+    const int p0 = h[i], p1 = h[i + 1 == n ? 0 : i + 1];
+    const int px = pkx(p0), py = pky(p0);
+    const int dx = pkx(p1) - px, dy = pky(p1) - py;
+    Fit32 f;
+    f.smin = f.tmin = 0x7fffffff;
+    f.smax = f.tmax = -0x7fffffff;
+    for (int j = 0; j < n; ++j) {
+      const int v = h[j];
+      const int vx = pkx(v) - px, vy = pky(v) - py;
+      const int sv = vx * dx + vy * dy, tv = vy * dx - vx * dy;
+      f.smin = min(f.smin, sv);
+      f.smax = max(f.smax, sv);
+      f.tmin = min(f.tmin, tv);
+      f.tmax = max(f.tmax, tv);
+    }
+    f.len2 = dx * dx + dy * dy;
+    f.area = (double)((long long)(f.smax - f.smin) * (long long)(f.tmax - f.tmin)) / (double)f.len2;
+    int qx = dx, qy = dy;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      if (!(qx > 0 && qy >= 0)) {
+        const int tx = qy;
+        qy = -qx;
+        qx = tx;
+      }
+    }
+    f.qx = qx;
+    f.qy = qy;
+    f.idx = i;
+    if (fit32_better(f, best)) best = f;
+  }
+#pragma unroll
+  for (int o = kGrp / 2; o > 0; o >>= 1) {
+    Fit32 of;
+    of.smin = __shfl_xor_sync(gmask, best.smin, o);
+    of.smax = __shfl_xor_sync(gmask, best.smax, o);
+    of.tmin = __shfl_xor_sync(gmask, best.tmin, o);
+    of.tmax = __shfl_xor_sync(gmask, best.tmax, o);
+    of.len2 = __shfl_xor_sync(gmask, best.len2, o);
+    of.qx = __shfl_xor_sync(gmask, best.qx, o);
+    of.qy = __shfl_xor_sync(gmask, best.qy, o);
+    of.idx = __shfl_xor_sync(gmask, best.idx, o);
+    of.area = __shfl_xor_sync(gmask, best.area, o);
+    if (fit32_better(of, best)) best = of;
+  }
+  // rect_from_fit (geometry.cuh) on the winning edge
+  const int i = best.idx;
+  const int p0 = h[i], p1 = h[i + 1 == n ? 0 : i + 1];
+  const double dx = (double)(pkx(p1) - pkx(p0)), dy = (double)(pky(p1) - pky(p0));
+  const double il2 = 1.0 / (double)best.len2;
+  const double s0 = (double)best.smin * il2, s1 = (double)best.smax * il2;
+  const double t0 = (double)best.tmin * il2, t1 = (double)best.tmax * il2;
+  const double ss[4] = {s0, s1, s1, s0}, tt[4] = {t0, t0, t1, t1};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    r->cx[q] = (double)pkx(p0) + dx * ss[q] - dy * tt[q];
+    r->cy[q] = (double)pky(p0) + dy * ss[q] + dx * tt[q];
+  }
+  const double len = sqrt((double)best.len2);
+  r->w = (double)(best.smax - best.smin) / len;
+  r->h = (double)(best.tmax - best.tmin) / len;
+}
+
+__global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
+  constexpr int kGroups = kGeoThreads / kGrp;
+  __shared__ int s_a[kGroups][2 * kFastRows];        // point set (row extents) / sorted unclip polygon
+  __shared__ int s_b[kGroups][2 * kFastRows + 2];    // hull
+  __shared__ P2i s_off[kGroups][kFastOff];           // raw unclip polygon
+  const int n = blockIdx.y;
+  const int g = threadIdx.x / kGrp, gl = threadIdx.x % kGrp;
+  const unsigned gmask = ((1u << kGrp) - 1u) << ((threadIdx.x & 31) / kGrp * kGrp);
+  const int k = blockIdx.x * kGroups + g;
+  if (k >= p.ncand[n]) return;
+  const size_t ro = (size_t)n * p.R;
+  const size_t ko = (size_t)n * p.maxc + k;
+  const int c = p.cand[ko];
+  const int yf = p.run_yf[ro + c];
+  const int fg = yf >> 15, y_first = yf & 0x7fff;
+  const int ymax = p.ymax[ro + c];
+  if (gl == 0) p.res_keep[ko] = 0;
+  const int area = p.area[ro + c];
+  if (fg) {  // "contour has <= 2 points" (db_postprocess.cpp:255-257)
+    const int bw = p.xmax[ro + c] - p.xmin[ro + c] + 1, bh = ymax - y_first + 1;
+    const bool diag = (bw == bh && bw == area) &&
+                      (p.dmin[ro + c] == p.dmax[ro + c] || p.smin[ro + c] == p.smax[ro + c]);
+    if (area == 1 || (bh == 1 && area == bw) || (bw == 1 && area == bh) || diag) return;
+  }
+  const int nrows = fg ? (ymax - y_first + 1) : (ymax - y_first + 3);
+  const int off = p.rowoff[ro + c];
+  auto defer = [&]() {
+    if (gl == 0) {
+      const int slot = atomicAdd(&p.nbig[n], 1);
+      if (slot < p.maxc) p.big[(size_t)n * p.maxc + slot] = k;
+    }
+  };
+  if (nrows > kFastRows || off < 0 || p.W >= 16384 || p.H >= 16384) {
+    defer();
+    return;
+  }
+  // BoxScore first: a low score drops the candidate whatever its rectangle is
+  const long long tot = p.sum[ro + c] + p.fsum[ro + c] + p.xsum[ro + c];
+  const int cnt = area + p.fcnt[ro + c] + p.xcnt[ro + c];
+  const float score = (float)(((double)tot / kFixScale) / (double)cnt);
+  if (score < p.box_thresh) return;
+
+  const int y0 = fg ? y_first : y_first - 1;
+  const int32_t* ext_l = p.ext_l + (size_t)n * p.E + off;
+  const int32_t* ext_r = p.ext_r + (size_t)n * p.E + off;
+  int* A = s_a[g];
+  int* B = s_b[g];
+  for (int i = gl; i < nrows; i += kGrp) {
+    A[2 * i] = pk(ext_l[i], y0 + i);
+    A[2 * i + 1] = pk(ext_r[i], y0 + i);
+  }
+  __syncwarp(gmask);
+  int hn = 0;
+  if (gl == 0) hn = hull_sorted32(A, 2 * nrows, B);
+  hn = __shfl_sync(gmask, hn, 0, kGrp);
+  __syncwarp(gmask);
+  geom::Rect rect;
+  group_min_area_rect(B, hn, &rect, gl, gmask);
+  float cx[4], cy[4], mx[4], my[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    cx[q] = (float)rect.cx[q];
+    cy[q] = (float)rect.cy[q];
+  }
+  geom::mini_box(cx, cy, mx, my);
+  if (fmaxf((float)rect.w, (float)rect.h) < 3.f) return;
+
+  // UnClip (db_postprocess.cpp:34-64)
+  const float distance = geom::unclip_distance(mx, my, p.unclip_ratio);
+  int m = 0;
+  if (gl == 0) {
+    P2i quad[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) quad[q] = P2i{(int)mx[q], (int)my[q]};
+    m = geom::do_offset_quad(quad, (double)distance, s_off[g], kFastOff);
+  }
+  m = __shfl_sync(gmask, m, 0, kGrp);
+  if (m < 0) {
+    defer();
+    return;
+  }
+  if (m == 0) return;  // empty solution -> RotatedRect((0,0),(1,1),0) -> dropped by the 1.001 test
+  __syncwarp(gmask);
+  // rank sort by (y, x, index) into A: every lane ranks its own points against all of them
+  for (int i = gl; i < m; i += kGrp) {
+    const P2i q = s_off[g][i];
+    int rank = 0;
+    for (int j = 0; j < m; ++j) {
+      const P2i o = s_off[g][j];
+      rank += (o.y < q.y || (o.y == q.y && (o.x < q.x || (o.x == q.x && j < i)))) ? 1 : 0;
+    }
+    A[rank] = pk(q.x, q.y);
+  }
+  __syncwarp(gmask);
+  int hm = 0;
+  if (gl == 0) hm = hull_sorted32(A, m, B);
+  hm = __shfl_sync(gmask, hm, 0, kGrp);
+  __syncwarp(gmask);
+  geom::Rect rect2;
+  group_min_area_rect(B, hm, &rect2, gl, gmask);
+  if ((float)rect2.h < 1.001 && (float)rect2.w < 1.001) return;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    cx[q] = (float)rect2.cx[q];
+    cy[q] = (float)rect2.cy[q];
+  }
+  geom::mini_box(cx, cy, mx, my);
+  if (fmaxf((float)rect2.w, (float)rect2.h) < 5.f) return;
+
+  if (gl == 0) {
+    const float sw = (float)p.src_wh[2 * n], sh = (float)p.src_wh[2 * n + 1];
+#pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float fx = geom::fmul(geom::fdiv(mx[q], (float)p.W), sw);
       const float fy = geom::fmul(geom::fdiv(my[q], (float)p.H), sh);
@@ -856,10 +1125,12 @@ size_t carve(DbParams& p, void* ws) {
   p.ext_l = c.take<int32_t>(N * E);
   p.ext_r = c.take<int32_t>(N * E);
   p.hull = c.take<P2i>(N * E * 4);
-  p.nruns = c.take<int32_t>(4 * N);  // nruns | ext_alloc | imgflags | ncand, cleared together
+  p.nruns = c.take<int32_t>(5 * N);  // nruns | ext_alloc | imgflags | ncand | nbig, cleared together
   p.ext_alloc = p.nruns ? p.nruns + N : nullptr;
   p.imgflags = p.nruns ? p.nruns + 2 * N : nullptr;
   p.ncand = p.nruns ? p.nruns + 3 * N : nullptr;
+  p.nbig = p.nruns ? p.nruns + 4 * N : nullptr;
+  p.big = c.take<int32_t>(N * p.maxc);
   p.cand = c.take<int32_t>(N * p.maxc);
   p.res_keep = c.take<int32_t>(N * p.maxc);
   p.res_box = c.take<int16_t>(N * p.maxc * 8);
@@ -918,7 +1189,8 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
   p.status_out = status_out_dev; p.boxes_f_out = boxes_f_out_dev; p.labels_dbg = labels_dbg_dev;
   cudaStream_t s = (cudaStream_t)stream;
 
-  OCRPP_CUDA(cudaMemsetAsync(p.nruns, 0, sizeof(int32_t) * 4 * N, s));
+  OCRPP_CUDA(cudaMemsetAsync(p.nruns, 0, sizeof(int32_t) * 5 * N, s));
+  ProfileScope prof(s);
   const size_t esz = dtype == OCRPP_F32 ? 4 : 2;
   const int epl = dtype == OCRPP_F32 ? 4 : 8;
   const bool vec = ((uintptr_t)maps_dev % 16 == 0) && (stride_n % epl == 0) && (stride_h % epl == 0) && (W % epl == 0);
@@ -933,33 +1205,48 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
       else db_binarize_kernel<__half, false><<<grid, kBinWarps * 32, 0, s>>>(p);
     }
     OCRPP_LAUNCHED();
+    prof.mark("db_binarize");
   }
   db_runs_kernel<<<N, kRunThreads, sizeof(int) * (H + 1), s>>>(p);
   OCRPP_LAUNCHED();
+  prof.mark("db_runs");
   dim3 rgrid(kImgCtas, N);
   db_link_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
   OCRPP_LAUNCHED();
+  prof.mark("db_link");
   db_flatten_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
   OCRPP_LAUNCHED();
+  prof.mark("db_flatten");
   if (dtype == OCRPP_F32) db_stats_kernel<float><<<rgrid, kRunBlk, 0, s>>>(p);
   else db_stats_kernel<__half><<<rgrid, kRunBlk, 0, s>>>(p);
   OCRPP_LAUNCHED();
+  prof.mark("db_stats");
   db_tree_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
   OCRPP_LAUNCHED();
+  prof.mark("db_tree");
   db_fill_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
   OCRPP_LAUNCHED();
+  prof.mark("db_fill");
   if (dtype == OCRPP_F32) db_extents_kernel<float><<<rgrid, kRunBlk, 0, s>>>(p);
   else db_extents_kernel<__half><<<rgrid, kRunBlk, 0, s>>>(p);
   OCRPP_LAUNCHED();
+  prof.mark("db_extents");
   db_rank_kernel<<<N, kRunThreads, 0, s>>>(p);
   OCRPP_LAUNCHED();
+  prof.mark("db_rank");
   {
-    dim3 grid((max_candidates + kGeoWarps - 1) / kGeoWarps, N);
-    db_geometry_kernel<<<grid, kGeoWarps * 32, 0, s>>>(p);
+    constexpr int kGroups = kGeoThreads / kGrp;
+    dim3 grid((max_candidates + kGroups - 1) / kGroups, N);
+    db_geometry_kernel<<<grid, kGeoThreads, 0, s>>>(p);
     OCRPP_LAUNCHED();
+    prof.mark("db_geometry");
+    db_geometry_big_kernel<<<dim3(2, N), kGeoWarps * 32, 0, s>>>(p);
+    OCRPP_LAUNCHED();
+    prof.mark("db_geometry_big");
   }
   db_compact_kernel<<<N, kRunThreads, 0, s>>>(p);
   OCRPP_LAUNCHED();
+  prof.mark("db_compact");
   if (labels_dbg_dev) {
     OCRPP_CUDA(cudaMemsetAsync(labels_dbg_dev, 0, sizeof(int32_t) * (size_t)N * H * W, s));
     db_labels_kernel<<<N, kRunThreads, 0, s>>>(p);
