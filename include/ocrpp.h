@@ -119,6 +119,61 @@ OCRPP_API int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int H
                          int32_t* status_out_dev, float* boxes_f_out_dev, int32_t* labels_dbg_dev,
                          void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * PSENet progressive scale expansion + box generation for a batch of head outputs.
+ *   maps_dev: logits; image n, channel k, pixel (y,x) at
+ *             maps_dev[n*stride_n + k*stride_c + y*stride_h + x] (element strides), k < K <= 8,
+ *             channel 0 = text, channel K-1 = smallest kernel, spatial size h x w.
+ *   upsample_in:  nearest up-sampling applied BEFORE the expansion (the reference's
+ *             F.interpolate(scale_factor=4//scale), pse_postprocess.py:34-36); processing
+ *             resolution = (h*upsample_in) x (w*upsample_in). 1 = maps already at processing res.
+ *   upsample_out: nearest up-sampling of the label/score maps AFTER the expansion
+ *             (cv2.resize(INTER_NEAREST), pse_postprocess.py:58-62); boxes are in that resolution
+ *             before the division by the ratios.
+ *   shape_dev: float64 [N,4] = shape_list rows (src_h, src_w, ratio_h, ratio_w).
+ *   min_area_seed: seed components with fewer pixels are dropped (pse.pyx:21-23; the operator
+ *             passes min_area / scale^2); min_area_box / box_thresh: generate_box filters
+ *             (pse_postprocess.py:75,80) on the up-sampled label.
+ *   max_boxes: output capacity per image (the reference has no limit; OCRPP_IMG_CANDIDATES_TRUNCATED
+ *             is set when it is exceeded). max_runs: capacity of the per-image run tables
+ *             (0 = worst case). arena_elems: capacity (uint32 elements) of the batch-wide queue
+ *             arena (0 = worst case 4*N*H*W); OCRPP_IMG_RUN_OVERFLOW reports either overflow.
+ * outputs (device): boxes int16 [N,max_boxes,4,2] in label order, corners ordered by
+ *   order_points_clockwise (utility.py:21-29), np.round + clip; scores float [N,max_boxes] =
+ *   mean sigmoid(text logit) per label; counts/status int32 [N]; boxes_f optional float
+ *   [N,max_boxes,4,2] pre-rounding; labels_dbg optional int32 [N,H,W] (processing resolution) = the
+ *   label map pse() returns, ids of cv2.connectedComponents(connectivity=4).
+ * ------------------------------------------------------------------------------------------- */
+OCRPP_API size_t ocrpp_pse_workspace_bytes(int N, int K, int h, int w, int upsample_in, int max_boxes,
+                                 int max_runs, int64_t arena_elems);
+OCRPP_API int ocrpp_pse_postprocess(const void* maps_dev, int dtype, int N, int K, int h, int w,
+                          int64_t stride_n, int64_t stride_c, int64_t stride_h,
+                          int upsample_in, int upsample_out, const double* shape_dev,
+                          float thresh, float box_thresh, float min_area_seed, float min_area_box,
+                          int max_boxes, int max_runs, int64_t arena_elems,
+                          int16_t* boxes_out_dev, float* scores_out_dev, int32_t* counts_out_dev,
+                          int32_t* status_out_dev, float* boxes_f_out_dev, int32_t* labels_dbg_dev,
+                          void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * PAN / PAN++ pixel aggregation + box generation. maps_dev has 6 channels: 0 text logit,
+ * 1 kernel logit, 2..5 the 4-d embedding (pan_postprocess.py:40-47). Kernel components smaller
+ * than min_kernel_area are dropped (pa.pyx:33-37; the operator passes min_kernel_area / scale^2);
+ * kernels whose area ratio to another kernel of the same text component exceeds 1024 are
+ * "flagged" and only claim pixels whose embedding lies within distance 3 of the kernel's mean
+ * embedding (pa.pyx:42-54,86-87). Everything else as ocrpp_pse_postprocess.
+ * ------------------------------------------------------------------------------------------- */
+OCRPP_API size_t ocrpp_pan_workspace_bytes(int N, int h, int w, int upsample_in, int max_boxes,
+                                 int max_runs, int64_t arena_elems);
+OCRPP_API int ocrpp_pan_postprocess(const void* maps_dev, int dtype, int N, int h, int w,
+                          int64_t stride_n, int64_t stride_c, int64_t stride_h,
+                          int upsample_in, int upsample_out, const double* shape_dev,
+                          float thresh, float box_thresh, float min_kernel_area, float min_area_box,
+                          int max_boxes, int max_runs, int64_t arena_elems,
+                          int16_t* boxes_out_dev, float* scores_out_dev, int32_t* counts_out_dev,
+                          int32_t* status_out_dev, float* boxes_f_out_dev, int32_t* labels_dbg_dev,
+                          void* workspace_dev, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,8 +52,9 @@ def pa(kernels, emb, min_area=0):
 
 class PANPostProcessOracle(object):
     def __init__(self, thresh=0.5, box_thresh=0.85, min_area=16, min_kernel_area=2.6, scale=4,
-                 out_polygon=False, **kwargs):
+                 out_polygon=False, maps_at_processing_res=False, **kwargs):
         assert not out_polygon
+        self.maps_at_processing_res = maps_at_processing_res
         self.thresh, self.box_thresh, self.min_area = thresh, box_thresh, min_area
         self.min_kernel_area = min_kernel_area / float(scale ** 2)
         self.scale = scale
@@ -63,9 +64,12 @@ class PANPostProcessOracle(object):
         if hasattr(pred, "detach"):
             pred = pred.detach().cpu().numpy()
         pred = np.asarray(pred, dtype=np.float32)
-        self.img_h, self.img_w = pred.shape[2] * 4, pred.shape[3] * 4
-        if self.scale != 4:
-            pred = upsample_nearest(pred, 4 // self.scale)
+        if self.maps_at_processing_res:
+            self.img_h, self.img_w = pred.shape[2] * self.scale, pred.shape[3] * self.scale
+        else:
+            self.img_h, self.img_w = pred.shape[2] * 4, pred.shape[3] * 4
+            if self.scale != 4:
+                pred = upsample_nearest(pred, 4 // self.scale)
         score = sigmoid_f32(pred[:, 0])
         kernels = pred[:, :2] > self.thresh
         text = kernels[:, 0:1]
@@ -78,6 +82,7 @@ class PANPostProcessOracle(object):
         res = []
         for b in range(score.shape[0]):
             label, flag, _ = pa(kernels[b], emb[b], self.min_kernel_area)
+            label_proc = label
             sc = score[b]
             if self.scale != 1:
                 label = upsample_nearest(label, self.img_h // label.shape[0])
@@ -87,6 +92,7 @@ class PANPostProcessOracle(object):
             if return_details:
                 d["details"] = out[2]
                 d["label"] = label
+                d["label_proc"] = label_proc
                 d["flag"] = flag
             res.append(d)
         return res

@@ -89,18 +89,25 @@ def generate_box(score, label, shape, min_area, box_thresh, return_details=False
 class PSEPostProcessOracle(object):
     """pse_postprocess.py:10-105."""
 
-    def __init__(self, thresh=0.5, box_thresh=0.85, min_area=16, scale=4, out_polygon=False, **kwargs):
+    def __init__(self, thresh=0.5, box_thresh=0.85, min_area=16, scale=4, out_polygon=False,
+                 maps_at_processing_res=False, **kwargs):
         assert not out_polygon, "out_polygon is SURVEY 8(f) rank 4 (not on the configured path)"
         self.thresh, self.box_thresh, self.min_area, self.scale = thresh, box_thresh, min_area, scale
+        # True: the maps are the tensor AFTER the reference's F.interpolate (:34-36), i.e. the
+        # up-sampling step is skipped (bench configs 3/4 enter the path in that state)
+        self.maps_at_processing_res = maps_at_processing_res
 
     def prepare(self, pred):
         """:31-45 -> score f32 [N,H,W], kernels u8 [N,K,H,W] at processing resolution."""
         if hasattr(pred, "detach"):
             pred = pred.detach().cpu().numpy()
         pred = np.asarray(pred, dtype=np.float32)
-        self.img_h, self.img_w = pred.shape[2] * 4, pred.shape[3] * 4
-        if self.scale != 4:
-            pred = upsample_nearest(pred, 4 // self.scale)
+        if self.maps_at_processing_res:
+            self.img_h, self.img_w = pred.shape[2] * self.scale, pred.shape[3] * self.scale
+        else:
+            self.img_h, self.img_w = pred.shape[2] * 4, pred.shape[3] * 4
+            if self.scale != 4:
+                pred = upsample_nearest(pred, 4 // self.scale)
         score = sigmoid_f32(pred[:, 0])
         kernels = (pred > self.thresh)
         kernels = (kernels & kernels[:, 0:1]).astype(np.uint8)
@@ -113,7 +120,7 @@ class PSEPostProcessOracle(object):
         score, kernels = self.prepare(outs_dict["maps"])
         res = []
         for b in range(score.shape[0]):
-            label = self.labels(kernels[b])
+            label = label_proc = self.labels(kernels[b])
             sc = score[b]
             if self.scale != 1:
                 label = upsample_nearest(label, self.img_h // label.shape[0])
@@ -123,5 +130,6 @@ class PSEPostProcessOracle(object):
             if return_details:
                 d["details"] = out[2]
                 d["label"] = label
+                d["label_proc"] = label_proc
             res.append(d)
         return res

@@ -1,6 +1,8 @@
 // Library-level entry points of libocrpp.so: version, error reporting, launch accounting.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace ocrpp {
 
 std::atomic<long long> g_launch_count{0};
@@ -16,6 +18,14 @@ int set_error(int code, const char* fmt, ...) {
   vsnprintf(last_error_buf(), 512, fmt, ap);
   va_end(ap);
   return code;
+}
+
+bool debug_sync() {
+  static const bool on = [] {
+    const char* e = getenv("OCRPP_DEBUG_SYNC");
+    return e && e[0] == '1';
+  }();
+  return on;
 }
 
 // ---- profiling ring --------------------------------------------------------------------------

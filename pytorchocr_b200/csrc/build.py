@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, "libocrpp.so")
-SOURCES = ["api.cu", "ctc.cu", "db.cu", "pse.cu"]
+SOURCES = ["api.cu", "ctc.cu", "db.cu", "expand.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
               "--expt-relaxed-constexpr", "-Xptxas", "-warn-spills"]
@@ -33,7 +33,8 @@ def build(force=False, verbose=False):
         if all(os.path.getmtime(p) <= t for p in _deps()):
             return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", OUT]
+    extra = ["-DOCRPP_CHECKS"] if os.environ.get("OCRPP_CHECKS") == "1" else []  # device-side bounds checks (debug)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", OUT]
     print("[build]", " ".join(cmd), flush=True)
     subprocess.check_call(cmd)
     return OUT

@@ -33,11 +33,14 @@ extern std::atomic<long long> g_launch_count;
                                 cudaGetErrorString(_e), __FILE__, __LINE__);                \
   } while (0)
 
-// counts the launch and checks the launch status
+// counts the launch and checks the launch status; with OCRPP_DEBUG_SYNC=1 in the environment every
+// launch is followed by a device synchronisation so that a faulting kernel is reported by name/line
+bool debug_sync();
 #define OCRPP_LAUNCHED()                                         \
   do {                                                           \
     ::ocrpp::g_launch_count.fetch_add(1, std::memory_order_relaxed); \
     OCRPP_CUDA(cudaGetLastError());                              \
+    if (::ocrpp::debug_sync()) OCRPP_CUDA(cudaDeviceSynchronize()); \
   } while (0)
 
 // 128-bit streaming load that does not allocate in L1 (data is touched once)

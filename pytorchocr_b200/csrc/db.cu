@@ -21,6 +21,8 @@
 // probabilities >= 2^-9, order independent => deterministic). Algorithmic bytes per image:
 // H*W*sizeof(elem), the probability map, read once by db_binarize_kernel.
 #include "common.cuh"
+#include "dev_common.cuh"
+#include "dev_geom.cuh"
 #include "geometry.cuh"
 
 namespace ocrpp {
@@ -156,50 +158,6 @@ __global__ void __launch_bounds__(kBinWarps * 32) db_binarize_kernel(DbParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
-// block-wide exclusive scan of one int per thread; returns the exclusive prefix, total in *total
-// ------------------------------------------------------------------------------------------------
-__device__ int block_exclusive_scan(int v, int* total) {
-  __shared__ int warp_sums[32];
-  __shared__ int s_total;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  int inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  __syncthreads();  // protect warp_sums reuse across calls
-  if (lane == 31) warp_sums[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    int ws = lane < nw ? warp_sums[lane] : 0;
-    int winc = ws;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, winc, o);
-      if (lane >= o) winc += t;
-    }
-    if (lane < nw) warp_sums[lane] = winc - ws;
-    if (lane == 31) s_total = winc;
-  }
-  __syncthreads();
-  *total = s_total;
-  return warp_sums[warp] + inc - v;
-}
-
-__device__ __forceinline__ unsigned valid_mask(int k, int W) {
-  const int rem = W - k * 32;
-  return rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
-}
-
-// transitions inside word k of a row: bit i set <=> pixel 32k+i differs from pixel 32k+i-1
-// (bit 0 of word 0 is never a transition). `prev` = word k-1 (ignored for k == 0).
-__device__ __forceinline__ unsigned transitions(unsigned w, unsigned prev, int k, int W) {
-  const unsigned carry = k > 0 ? (prev >> 31) : (w & 1u);
-  return (w ^ ((w << 1) | carry)) & valid_mask(k, W);
-}
-
-// ------------------------------------------------------------------------------------------------
 // K2: bit mask -> run table (both polarities, raster order). One CTA per image.
 // ------------------------------------------------------------------------------------------------
 constexpr int kRunThreads = 512;
@@ -290,32 +248,6 @@ __global__ void __launch_bounds__(kRunThreads) db_runs_kernel(DbParams p) {
       }
     }
     if (lane == 0) p.run_xe[ro + s_rowcnt[y + 1] - 1] = (uint16_t)(p.W - 1);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// union-find on runs (atomicMin linking: the root of a set is its smallest run index = the run
-// holding the component's first raster pixel)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int uf_find(const int32_t* par, int x) {
-  int q;
-  while ((q = __ldcg(par + x)) != x) x = q;
-  return x;
-}
-
-__device__ void uf_union(int32_t* par, int a, int b) {
-  while (true) {
-    a = uf_find(par, a);
-    b = uf_find(par, b);
-    if (a == b) return;
-    if (a > b) {
-      const int t = a;
-      a = b;
-      b = t;
-    }
-    const int old = atomicMin(par + b, a);
-    if (old == b) return;
-    b = old;
   }
 }
 
@@ -610,47 +542,6 @@ constexpr int kGeoWarps = 4;
 constexpr int kSmallRows = 64;              // candidates up to this many rows build their hull in smem
 constexpr int kOffCap = 320;                // capacity of the unclip polygon (points)
 
-struct WarpBest {
-  double area;
-  int idx;
-};
-
-// warp-parallel min_area_rect: lanes take hull edges, same choice as geom::min_area_rect
-__device__ void warp_min_area_rect(const P2i* h, int n, geom::Rect* r, int lane) {
-  if (n == 1) {
-    geom::min_area_rect(h, n, r);
-    return;
-  }
-  const int ne = n == 2 ? 1 : n;
-  geom::EdgeFit bf;
-  bf.area = 1e300;
-  bf.qx = 1;
-  bf.qy = 0;
-  int bi = 0x7fffffff;
-  for (int i = lane; i < ne; i += 32) {
-    const geom::EdgeFit f = geom::fit_edge(h, n, i);
-    if (geom::fit_better(f, i, bf, bi)) {
-      bf = f;
-      bi = i;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    geom::EdgeFit of;
-    of.area = __shfl_xor_sync(0xffffffffu, bf.area, o);
-    of.qx = __shfl_xor_sync(0xffffffffu, bf.qx, o);
-    of.qy = __shfl_xor_sync(0xffffffffu, bf.qy, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (oi != 0x7fffffff && (bi == 0x7fffffff || geom::fit_better(of, oi, bf, bi))) {
-      bf.area = of.area;
-      bf.qx = of.qx;
-      bf.qy = of.qy;
-      bi = oi;
-    }
-  }
-  const geom::EdgeFit f = geom::fit_edge(h, n, bi);  // every lane recomputes the winner
-  geom::rect_from_fit(h, n, bi, f, r);
-}
 
 __global__ void __launch_bounds__(kGeoWarps * 32) db_geometry_big_kernel(DbParams p) {
   __shared__ P2i s_pts[kGeoWarps][2 * kSmallRows];
@@ -774,140 +665,10 @@ __global__ void __launch_bounds__(kGeoWarps * 32) db_geometry_big_kernel(DbParam
 // projections, points packed as short2 in shared memory. Candidates that do not fit its fixed
 // buffers are appended to the per-image `big` list and handled by db_geometry_big_kernel.
 // ------------------------------------------------------------------------------------------------
-constexpr int kGrp = 8;                       // lanes per candidate
 constexpr int kGeoThreads = 128;              // 16 candidates per CTA
 constexpr int kFastRows = 64;                 // max rows of a candidate's point set
 constexpr int kFastOff = 96;                  // max points of its unclip polygon
 
-__device__ __forceinline__ int pk(int x, int y) { return (x & 0xffff) | (y << 16); }
-__device__ __forceinline__ int pkx(int v) { return (int)(short)(v & 0xffff); }
-__device__ __forceinline__ int pky(int v) { return v >> 16; }
-
-__device__ __forceinline__ int cross32(int o, int a, int b) {
-  return (pkx(a) - pkx(o)) * (pky(b) - pky(o)) - (pky(a) - pky(o)) * (pkx(b) - pkx(o));
-}
-
-// monotone chain over packed points sorted by (y, x); same result as geom::hull_sorted
-__device__ int hull_sorted32(const int* pts, int n, int* out) {
-  if (n <= 1) {
-    if (n == 1) out[0] = pts[0];
-    return n;
-  }
-  int k = 0;
-  for (int i = 0; i < n; ++i) {
-    const int q = pts[i];
-    if (i > 0 && q == pts[i - 1]) continue;
-    while (k >= 2 && cross32(out[k - 2], out[k - 1], q) <= 0) --k;
-    out[k++] = q;
-  }
-  if (k == 1) return 1;
-  const int lo = k + 1;
-  for (int i = n - 2; i >= 0; --i) {
-    const int q = pts[i];
-    if (q == pts[i + 1]) continue;
-    while (k >= lo && cross32(out[k - 2], out[k - 1], q) <= 0) --k;
-    out[k++] = q;
-  }
-  return k - 1;
-}
-
-struct Fit32 {
-  int smin, smax, tmin, tmax, len2, qx, qy, idx;
-  double area;
-};
-
-__device__ __forceinline__ bool fit32_better(const Fit32& a, const Fit32& b) {
-  if (b.idx == 0x7fffffff) return a.idx != 0x7fffffff;
-  if (a.idx == 0x7fffffff) return false;
-  const double m = fmax(a.area, b.area);
-  if (fabs(a.area - b.area) > 1e-12 * m) return a.area < b.area;
-  const long long l = (long long)a.qy * b.qx, r = (long long)b.qy * a.qx;
-  if (l != r) return l > r;
-  return a.idx < b.idx;
-}
-
-// group-parallel min-area rectangle over packed hull points in shared memory; identical choice
-// to geom::min_area_rect (exact integer projections, fit_better ordering)
-__device__ void group_min_area_rect(const int* h, int n, geom::Rect* r, int gl, unsigned gmask) {
-  if (n == 1) {
-    for (int q = 0; q < 4; ++q) {
-      r->cx[q] = pkx(h[0]);
-      r->cy[q] = pky(h[0]);
-    }
-    r->w = r->h = 0.0;
-    return;
-  }
-  const int ne = n == 2 ? 1 : n;
-  Fit32 best;
-  best.idx = 0x7fffffff;
-  best.area = 1e300;
-  best.qx = 1;
-  best.qy = 0;
-  best.smin = best.smax = best.tmin = best.tmax = 0;
-  best.len2 = 1;
-  for (int i = gl; i < ne; i += kGrp) {
-    const int p0 = h[i], p1 = h[i + 1 == n ? 0 : i + 1];
-    const int px = pkx(p0), py = pky(p0);
-    const int dx = pkx(p1) - px, dy = pky(p1) - py;
-    Fit32 f;
-    f.smin = f.tmin = 0x7fffffff;
-    f.smax = f.tmax = -0x7fffffff;
-    for (int j = 0; j < n; ++j) {
-      const int v = h[j];
-      const int vx = pkx(v) - px, vy = pky(v) - py;
-      const int sv = vx * dx + vy * dy, tv = vy * dx - vx * dy;
-      f.smin = min(f.smin, sv);
-      f.smax = max(f.smax, sv);
-      f.tmin = min(f.tmin, tv);
-      f.tmax = max(f.tmax, tv);
-    }
-    f.len2 = dx * dx + dy * dy;
-    f.area = (double)((long long)(f.smax - f.smin) * (long long)(f.tmax - f.tmin)) / (double)f.len2;
-    int qx = dx, qy = dy;
-#pragma unroll
-    for (int t = 0; t < 3; ++t) {
-      if (!(qx > 0 && qy >= 0)) {
-        const int tx = qy;
-        qy = -qx;
-        qx = tx;
-      }
-    }
-    f.qx = qx;
-    f.qy = qy;
-    f.idx = i;
-    if (fit32_better(f, best)) best = f;
-  }
-#pragma unroll
-  for (int o = kGrp / 2; o > 0; o >>= 1) {
-    Fit32 of;
-    of.smin = __shfl_xor_sync(gmask, best.smin, o);
-    of.smax = __shfl_xor_sync(gmask, best.smax, o);
-    of.tmin = __shfl_xor_sync(gmask, best.tmin, o);
-    of.tmax = __shfl_xor_sync(gmask, best.tmax, o);
-    of.len2 = __shfl_xor_sync(gmask, best.len2, o);
-    of.qx = __shfl_xor_sync(gmask, best.qx, o);
-    of.qy = __shfl_xor_sync(gmask, best.qy, o);
-    of.idx = __shfl_xor_sync(gmask, best.idx, o);
-    of.area = __shfl_xor_sync(gmask, best.area, o);
-    if (fit32_better(of, best)) best = of;
-  }
-  // rect_from_fit (geometry.cuh) on the winning edge
-  const int i = best.idx;
-  const int p0 = h[i], p1 = h[i + 1 == n ? 0 : i + 1];
-  const double dx = (double)(pkx(p1) - pkx(p0)), dy = (double)(pky(p1) - pky(p0));
-  const double il2 = 1.0 / (double)best.len2;
-  const double s0 = (double)best.smin * il2, s1 = (double)best.smax * il2;
-  const double t0 = (double)best.tmin * il2, t1 = (double)best.tmax * il2;
-  const double ss[4] = {s0, s1, s1, s0}, tt[4] = {t0, t0, t1, t1};
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    r->cx[q] = (double)pkx(p0) + dx * ss[q] - dy * tt[q];
-    r->cy[q] = (double)pky(p0) + dy * ss[q] + dx * tt[q];
-  }
-  const double len = sqrt((double)best.len2);
-  r->w = (double)(best.smax - best.smin) / len;
-  r->h = (double)(best.tmax - best.tmin) / len;
-}
 
 __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
   constexpr int kGroups = kGeoThreads / kGrp;
@@ -1084,18 +845,6 @@ __global__ void __launch_bounds__(kRunThreads) db_labels_kernel(DbParams p) {
     for (int x = p.run_xs[ro + r]; x <= p.run_xe[ro + r]; ++x) lab[(size_t)y * p.W + x] = v;
   }
 }
-
-struct Carver {
-  char* base;
-  size_t off;
-  template <typename T>
-  T* take(size_t count) {
-    off = align_up(off, 256);
-    T* ptr = base ? reinterpret_cast<T*>(base + off) : nullptr;
-    off += count * sizeof(T);
-    return ptr;
-  }
-};
 
 size_t carve(DbParams& p, void* ws) {
   Carver c{(char*)ws, 0};

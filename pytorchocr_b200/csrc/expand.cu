@@ -1,0 +1,1066 @@
+// PSENet progressive scale expansion and PAN / PAN++ pixel aggregation on sm_100a.
+//
+// Replaces, for a whole batch and without leaving the device:
+//   R/pytocr/postprocess/pse_postprocess.py:28-53     upsample / sigmoid / threshold / text masking / D2H
+//   R/pytocr/postprocess/pse_postprocess_fast/pse.pyx:13-69   cv2 CCL + FIFO multi-level expansion
+//   R/pytocr/postprocess/pse_postprocess.py:55-105    label/score upsample + generate_box
+//   R/pytocr/postprocess/pan_postprocess.py:30-113 and pan_postprocess_fast/pa.pyx:14-104 (same shape,
+//     two masks, area-ratio flags, mean embeddings, one expansion level gated by embedding distance)
+//
+// The reference's expansion is defined by a sequential FIFO queue: a contested pixel belongs to
+// whichever neighbour is popped first. That order is reproduced exactly (DESIGN.md "expansion"):
+//   * pops are processed in blocks of up to kExThreads queue entries; every entry r proposes
+//     key = 4*r + direction to its free neighbours with atomicMin, the smallest key owns the pixel,
+//     and the owners append their pixels to the next wave with an ordered (scan) compaction, which
+//     is exactly the order in which the sequential queue would have pushed them;
+//   * entries that claimed nothing go, in pop order, to the next level's queue (pse.pyx:47,58-60);
+//   * queue order only matters between pixels of ONE 4-connected component of the text mask (all
+//     kernels are multiplied by it), so every text component is an independent work item handled by
+//     one CTA; entries that can never claim again (no free text neighbour) are dropped, which does
+//     not change the relative order of the others.
+// Labels (ids of cv2.connectedComponents(connectivity=4)) = 1 + rank of the seed component's first
+// raster pixel; inside the pipeline a label is carried as (root run index + 1) of the seed mask.
+//
+// Data layout per image at processing resolution H x W (H = h*upsample_in):
+//   kb  u8  [H*W]   bit k = kernel k after text masking (PSE: k < K; PAN: bit0 text, bit1 kernel)
+//   st  u32 [H*W]   state of text pixels: kUnset | proposal key (< 2^31) | kLabelBit + label
+//   1-bit masks of text and seed kernel -> run tables -> run union-find (4-connectivity)
+// Algorithmic bytes per image: C*h*w*sizeof(elem), the head output, read once by ex_binarize_kernel
+// (plus channel 0 again at text pixels for the score mean, and embeddings at gated pixels only).
+#include "common.cuh"
+#include "dev_common.cuh"
+#include "dev_geom.cuh"
+#include "geometry.cuh"
+
+namespace ocrpp {
+namespace {
+
+constexpr uint32_t kUnset = 0xffffffffu;
+constexpr uint32_t kLabelBit = 0x80000000u;
+constexpr double kFix = 4294967296.0;  // 2^32
+
+__device__ __forceinline__ bool is_labelled(uint32_t v) { return (v & kLabelBit) && v != kUnset; }
+
+enum { kModePse = 0, kModePan = 1 };
+
+struct ExParams {
+  const void* maps;
+  long long stride_n, stride_c, stride_h;
+  const double* shape;  // [N,4] src_h, src_w, ratio_h, ratio_w
+  int N, C, K, h, w, fin, fout, H, W, Wd, R, E, maxc, mode, seed_bit;
+  float thresh, box_thresh, min_area_seed, min_area_box;
+  long long arena_cap;
+  // per-image maps
+  uint8_t* kb;      // [N][H*W]
+  uint32_t* st;     // [N][H*W]
+  uint32_t* bits;   // [N][2][H*Wd]
+  int32_t* rowptr;  // [N][2][H+1]
+  uint16_t *run_xs, *run_xe, *run_y;  // [N][2][R]
+  int32_t* par;     // [N][2][R]
+  // text-root slots [N][R]
+  int32_t *t_area, *t_xmin, *t_xmax, *t_ymax, *t_seen, *t_amin, *t_amax;
+  // seed-root slots [N][R]
+  int32_t *s_area, *s_cc, *s_cid, *s_alive, *s_flag;
+  double* s_emb;    // [N][R][4] embedding sums of flagged kernels
+  int32_t *l_area, *l_ymin, *l_ymax, *l_rowoff;
+  long long* l_sum;
+  int32_t *ext_l, *ext_r;  // [N][E]
+  P2i* hull;               // [N][8*E]
+  int32_t *nruns;          // [N][2]
+  int32_t *ext_alloc, *imgflags, *ncand;  // [N]
+  int32_t* cand;           // [N][maxc]
+  int32_t* res_keep;
+  int16_t* res_box;
+  float* res_boxf;
+  float* res_score;
+  // batch-global
+  int2* work;              // [N*R] (image, text root)
+  int32_t* g_nwork;        // [1]
+  int32_t* g_next;         // [1]
+  unsigned long long* g_arena_used;  // [1]
+  uint32_t* arena;         // [arena_cap]
+  // outputs
+  int16_t* boxes_out;
+  float* scores_out;
+  int32_t* counts_out;
+  int32_t* status_out;
+  float* boxes_f_out;
+  int32_t* labels_dbg;
+};
+
+template <typename T>
+__device__ __forceinline__ float ex_load(const ExParams& p, int n, int c, int y, int x) {
+  // value of channel c at PROCESSING-resolution pixel (y,x): nearest upsample by fin
+  // (F.interpolate(mode="nearest", scale_factor=fin) == src[y / fin][x / fin])
+  const long long off = n * p.stride_n + c * p.stride_c + (long long)(y / p.fin) * p.stride_h + (x / p.fin);
+  return load_scalar<T>(reinterpret_cast<const T*>(p.maps) + off);
+}
+
+// ------------------------------------------------------------------------------------------------
+// E1: threshold + text masking -> kb bytes and the two 1-bit masks. One warp per row, 4 pixels per
+// lane per iteration; 128-bit loads per channel when the input is at processing resolution.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBinWarps = 8;
+constexpr int kMaxK = 8;
+
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(kBinWarps * 32) ex_binarize_kernel(ExParams p) {
+  const int n = blockIdx.y;
+  const int y = blockIdx.x * kBinWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (y >= p.H) return;
+  uint8_t* kb = p.kb + ((size_t)n * p.H + y) * p.W;
+  uint32_t* tb = p.bits + ((size_t)(n * 2 + 0) * p.H + y) * p.Wd;
+  uint32_t* sb = p.bits + ((size_t)(n * 2 + 1) * p.H + y) * p.Wd;
+  const int K = p.K;
+  for (int x0 = 0; x0 < p.W; x0 += 128) {
+    const int x = x0 + lane * 4;
+    unsigned b[4] = {0u, 0u, 0u, 0u};
+    if (x < p.W) {
+      if (kVec) {  // fin == 1, float rows 16-byte aligned, W % 4 == 0
+        const float* base = reinterpret_cast<const float*>(p.maps) + n * p.stride_n + (long long)y * p.stride_h + x;
+        uint4 v[kMaxK];
+#pragma unroll
+        for (int k = 0; k < kMaxK; ++k)
+          if (k < K) v[k] = ldg_stream_u4(base + k * p.stride_c);
+#pragma unroll
+        for (int k = 0; k < kMaxK; ++k)
+          if (k < K) {
+            b[0] |= (__uint_as_float(v[k].x) > p.thresh ? 1u : 0u) << k;
+            b[1] |= (__uint_as_float(v[k].y) > p.thresh ? 1u : 0u) << k;
+            b[2] |= (__uint_as_float(v[k].z) > p.thresh ? 1u : 0u) << k;
+            b[3] |= (__uint_as_float(v[k].w) > p.thresh ? 1u : 0u) << k;
+          }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (x + i < p.W)
+            for (int k = 0; k < K; ++k) b[i] |= (ex_load<T>(p, n, k, y, x + i) > p.thresh ? 1u : 0u) << k;
+      }
+    }
+    unsigned tn = 0, sn = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (!(b[i] & 1u)) b[i] = 0u;  // every kernel is multiplied by the text mask (pse_postprocess.py:41-42)
+      tn |= (b[i] & 1u) << i;
+      sn |= ((b[i] >> p.seed_bit) & 1u) << i;
+    }
+    if (x < p.W) {
+      if (kVec) {
+        *reinterpret_cast<uint32_t*>(kb + x) = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (x + i < p.W) kb[x + i] = (uint8_t)b[i];
+      }
+    }
+    unsigned tw = tn << (4 * (lane & 7)), sw = sn << (4 * (lane & 7));
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      tw |= __shfl_xor_sync(0xffffffffu, tw, o);
+      sw |= __shfl_xor_sync(0xffffffffu, sw, o);
+    }
+    const int wi = (x0 >> 5) + (lane >> 3);
+    if ((lane & 7) == 0 && wi < p.Wd) {
+      tb[wi] = tw;
+      sb[wi] = sw;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// E2: 1-bit mask -> table of foreground runs in raster order. One CTA per (image, mask).
+// ------------------------------------------------------------------------------------------------
+constexpr int kRunThreads = 512;
+
+__device__ __forceinline__ unsigned run_starts(unsigned w, unsigned prev) { return w & ~((w << 1) | (prev >> 31)); }
+__device__ __forceinline__ unsigned run_ends(unsigned w, unsigned next) { return w & ~((w >> 1) | (next << 31)); }
+
+__global__ void __launch_bounds__(kRunThreads) ex_runs_kernel(ExParams p) {
+  extern __shared__ int s_rowcnt[];  // [H+1]
+  const int n = blockIdx.x, m = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kRunThreads / 32;
+  const uint32_t* bits = p.bits + (size_t)(n * 2 + m) * p.H * p.Wd;
+  int32_t* rowptr = p.rowptr + (size_t)(n * 2 + m) * (p.H + 1);
+  const size_t ro = (size_t)(n * 2 + m) * p.R;
+  const size_t so = (size_t)n * p.R;
+
+  for (int y = warp; y < p.H; y += nw) {
+    int c = 0;
+    for (int k = lane; k < p.Wd; k += 32) {
+      const unsigned w = bits[(size_t)y * p.Wd + k];
+      const unsigned pw = k > 0 ? bits[(size_t)y * p.Wd + k - 1] : 0u;
+      c += __popc(run_starts(w, pw));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) s_rowcnt[y] = c;
+  }
+  __syncthreads();
+  const int chunk = (p.H + kRunThreads - 1) / kRunThreads;
+  const int y0 = threadIdx.x * chunk, y1 = min(p.H, y0 + chunk);
+  int local = 0;
+  for (int y = y0; y < y1; ++y) local += s_rowcnt[y];
+  int total;
+  int base = block_exclusive_scan(local, &total);
+  for (int y = y0; y < y1; ++y) {
+    const int c = s_rowcnt[y];
+    s_rowcnt[y] = base;
+    base += c;
+  }
+  if (threadIdx.x == 0) s_rowcnt[p.H] = total;
+  __syncthreads();
+  if (total > p.R) {
+    if (threadIdx.x == 0) {
+      atomicOr(&p.imgflags[n], OCRPP_IMG_RUN_OVERFLOW);
+      p.nruns[n * 2 + m] = 0;
+    }
+    for (int y = threadIdx.x; y <= p.H; y += kRunThreads) rowptr[y] = 0;
+    return;
+  }
+  for (int y = threadIdx.x; y <= p.H; y += kRunThreads) rowptr[y] = s_rowcnt[y];
+  if (threadIdx.x == 0) p.nruns[n * 2 + m] = total;
+
+  for (int y = warp; y < p.H; y += nw) {
+    const int rbase = s_rowcnt[y];
+    int carry_s = 0, carry_e = 0;
+    for (int k0 = 0; k0 < p.Wd; k0 += 32) {
+      const int k = k0 + lane;
+      unsigned S = 0, Eb = 0;
+      if (k < p.Wd) {
+        const unsigned w = bits[(size_t)y * p.Wd + k];
+        const unsigned pw = k > 0 ? bits[(size_t)y * p.Wd + k - 1] : 0u;
+        const unsigned nx = k + 1 < p.Wd ? bits[(size_t)y * p.Wd + k + 1] : 0u;
+        S = run_starts(w, pw);
+        Eb = run_ends(w, nx);
+      }
+      const int cs = __popc(S), ce = __popc(Eb);
+      int is = cs, ie = ce;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ts = __shfl_up_sync(0xffffffffu, is, o), te = __shfl_up_sync(0xffffffffu, ie, o);
+        if (lane >= o) {
+          is += ts;
+          ie += te;
+        }
+      }
+      int js = carry_s + is - cs, je = carry_e + ie - ce;
+      carry_s += __shfl_sync(0xffffffffu, is, 31);
+      carry_e += __shfl_sync(0xffffffffu, ie, 31);
+      while (S) {
+        const int bpos = __ffs(S) - 1;
+        S &= S - 1;
+        const size_t r = ro + rbase + js;
+        p.run_xs[r] = (uint16_t)(k * 32 + bpos);
+        p.run_y[r] = (uint16_t)y;
+        p.par[r] = rbase + js;
+        const size_t q = so + rbase + js;
+        if (m == 0) {
+          p.t_area[q] = 0; p.t_xmin[q] = 0x7fffffff; p.t_xmax[q] = -1; p.t_ymax[q] = -1;
+          p.t_seen[q] = 0; p.t_amin[q] = 0x7fffffff; p.t_amax[q] = 0;
+        } else {
+          p.s_area[q] = 0; p.s_cc[q] = -1; p.s_cid[q] = 0; p.s_alive[q] = 0; p.s_flag[q] = 0;
+          p.l_area[q] = 0; p.l_ymin[q] = 0x7fffffff; p.l_ymax[q] = -1; p.l_rowoff[q] = -1; p.l_sum[q] = 0;
+          if (p.mode == kModePan) {
+            p.s_emb[q * 4 + 0] = 0.0; p.s_emb[q * 4 + 1] = 0.0; p.s_emb[q * 4 + 2] = 0.0; p.s_emb[q * 4 + 3] = 0.0;
+          }
+        }
+        ++js;
+      }
+      while (Eb) {
+        const int bpos = __ffs(Eb) - 1;
+        Eb &= Eb - 1;
+        p.run_xe[ro + rbase + je] = (uint16_t)(k * 32 + bpos);
+        ++je;
+      }
+    }
+  }
+}
+
+constexpr int kImgCtas = 8;
+constexpr int kRunBlk = 256;
+#define EX_FOR_EACH_RUN(r, nr) for (int r = blockIdx.x * kRunBlk + threadIdx.x; r < (nr); r += kImgCtas * kRunBlk)
+
+// E3: 4-connectivity: link every run with the runs of the row above that overlap [xs, xe].
+__global__ void __launch_bounds__(kRunBlk) ex_link_kernel(ExParams p) {
+  const int n = blockIdx.y, m = blockIdx.z;
+  const int nr = p.nruns[n * 2 + m];
+  const size_t ro = (size_t)(n * 2 + m) * p.R;
+  const int32_t* rowptr = p.rowptr + (size_t)(n * 2 + m) * (p.H + 1);
+  const uint16_t *xs = p.run_xs + ro, *xe = p.run_xe + ro, *ry = p.run_y + ro;
+  int32_t* par = p.par + ro;
+  EX_FOR_EACH_RUN(r, nr) {
+    const int y = ry[r];
+    if (y == 0) continue;
+    const int lo = xs[r], hi = xe[r];
+    int l = rowptr[y - 1], h = rowptr[y];
+    const int b = h;
+    while (l < h) {
+      const int mid = (l + h) >> 1;
+      if ((int)xe[mid] < lo) l = mid + 1; else h = mid;
+    }
+    for (int q = l; q < b && (int)xs[q] <= hi; ++q) uf_union(par, q, r);
+  }
+}
+
+// E4: flatten + per-root reductions (text: area and bounding box; seed: area).
+__global__ void __launch_bounds__(kRunBlk) ex_flatten_kernel(ExParams p) {
+  const int n = blockIdx.y, m = blockIdx.z;
+  const int nr = p.nruns[n * 2 + m];
+  const size_t ro = (size_t)(n * 2 + m) * p.R, so = (size_t)n * p.R;
+  const uint16_t *xs = p.run_xs + ro, *xe = p.run_xe + ro, *ry = p.run_y + ro;
+  int32_t* par = p.par + ro;
+  EX_FOR_EACH_RUN(r, nr) {
+    const int root = uf_find(par, r);
+    par[r] = root;
+    const int len = (int)xe[r] - (int)xs[r] + 1;
+    if (m == 0) {
+      atomicAdd(&p.t_area[so + root], len);
+      atomicMin(&p.t_xmin[so + root], (int)xs[r]);
+      atomicMax(&p.t_xmax[so + root], (int)xe[r]);
+      atomicMax(&p.t_ymax[so + root], (int)ry[r]);
+    } else {
+      atomicAdd(&p.s_area[so + root], len);
+    }
+  }
+}
+
+// run of `mask m` in row y that contains pixel x (the pixel is known to be set in that mask)
+__device__ __forceinline__ int ex_run_at(const int32_t* rowptr, const uint16_t* xs, int y, int x) {
+  int l = rowptr[y], h = rowptr[y + 1];
+  while (h - l > 1) {
+    const int mid = (l + h) >> 1;
+    if ((int)xs[mid] <= x) l = mid; else h = mid;
+  }
+  return l;
+}
+
+// E5: seed components: cv2 label ids, min-area filter (pse.pyx:21-23, pa.pyx:33-37), enclosing text
+// component, work items, and (PAN) the per-text-component extreme kernel areas. One CTA per image.
+__global__ void __launch_bounds__(kRunThreads) ex_seed_kernel(ExParams p) {
+  const int n = blockIdx.x;
+  const int nr = p.nruns[n * 2 + 1];
+  const size_t to = (size_t)(n * 2 + 0) * p.R, ro = (size_t)(n * 2 + 1) * p.R, so = (size_t)n * p.R;
+  const int32_t* t_rowptr = p.rowptr + (size_t)(n * 2 + 0) * (p.H + 1);
+  const int chunk = (nr + kRunThreads - 1) / kRunThreads;
+  const int lo = min(nr, (int)threadIdx.x * chunk), hi = min(nr, lo + chunk);
+  int local = 0;
+  for (int r = lo; r < hi; ++r) local += p.par[ro + r] == r ? 1 : 0;
+  int total;
+  int id = block_exclusive_scan(local, &total);
+  for (int r = lo; r < hi; ++r) {
+    if (p.par[ro + r] != r) continue;
+    p.s_cid[so + r] = ++id;
+    const int area = p.s_area[so + r];
+    if ((float)area < p.min_area_seed) continue;
+    const int y = p.run_y[ro + r], x = p.run_xs[ro + r];
+    const int cc = p.par[to + ex_run_at(t_rowptr, p.run_xs + to, y, x)];
+    p.s_cc[so + r] = cc;
+    p.s_alive[so + r] = 1;
+    if (atomicExch(&p.t_seen[so + cc], 1) == 0) {
+      const int slot = atomicAdd(p.g_nwork, 1);
+      p.work[slot] = make_int2(n, cc);
+    }
+    if (p.mode == kModePan) {
+      atomicMin(&p.t_amin[so + cc], area);
+      atomicMax(&p.t_amax[so + cc], area);
+    }
+  }
+}
+
+// E6 (PAN): area-ratio flags (pa.pyx:42-54; float32 rate vs 1024 == exact integer compare for areas
+// < 2^20) and embedding sums of flagged kernels over their ORIGINAL pixels.
+template <typename T>
+__global__ void __launch_bounds__(kRunBlk) ex_pan_flag_kernel(ExParams p) {
+  const int n = blockIdx.y;
+  const int nr = p.nruns[n * 2 + 1];
+  const size_t ro = (size_t)(n * 2 + 1) * p.R, so = (size_t)n * p.R;
+  EX_FOR_EACH_RUN(r, nr) {
+    const int root = p.par[ro + r];
+    if (!p.s_alive[so + root]) continue;
+    const long long a = p.s_area[so + root];
+    const int cc = p.s_cc[so + root];
+    const long long amin = p.t_amin[so + cc], amax = p.t_amax[so + cc];
+    const bool flag = (a * 1024 < amax) || (a > amin * 1024);
+    if (!flag) continue;
+    if (r == root) p.s_flag[so + root] = 1;
+    const int y = p.run_y[ro + r];
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int x = p.run_xs[ro + r]; x <= (int)p.run_xe[ro + r]; ++x)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[c] += (double)ex_load<T>(p, n, 2 + c, y, x);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) atomicAdd(&p.s_emb[(so + root) * 4 + c], s[c]);
+  }
+}
+
+// E7: paint the state map: every text pixel -> kUnset (m == 0; also components without a seed: the
+// bounding-box scan of a neighbouring component reads them), then the surviving seed pixels ->
+// their label (m == 1). One warp per run.
+__global__ void __launch_bounds__(kRunBlk) ex_paint_kernel(ExParams p, int m) {
+  const int n = blockIdx.y;
+  const int nr = p.nruns[n * 2 + m];
+  const size_t ro = (size_t)(n * 2 + m) * p.R, so = (size_t)n * p.R;
+  uint32_t* st = p.st + (size_t)n * p.H * p.W;
+  const int lane = threadIdx.x & 31, wpb = kRunBlk / 32;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < nr; r += kImgCtas * wpb) {
+    const int root = p.par[ro + r];
+    uint32_t v;
+    if (m == 0) {
+      v = kUnset;
+    } else {
+      if (!p.s_alive[so + root]) continue;
+      v = kLabelBit | (uint32_t)(root + 1);
+    }
+    const size_t row = (size_t)p.run_y[ro + r] * p.W;
+    for (int x = p.run_xs[ro + r] + lane; x <= (int)p.run_xe[ro + r]; x += 32) st[row + x] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// E8: the expansion. Persistent CTAs pull text components from the work list.
+// ------------------------------------------------------------------------------------------------
+constexpr int kExThreads = 256;
+constexpr int kStrip = 8;
+
+__device__ __forceinline__ uint32_t pack_yx(int y, int x) { return ((uint32_t)y << 16) | (uint32_t)x; }
+
+template <typename T>
+__global__ void __launch_bounds__(kExThreads) ex_expand_kernel(ExParams p) {
+  __shared__ int s_item;
+  __shared__ long long s_base;
+  const int tid = threadIdx.x;
+  const int H = p.H, W = p.W;
+  const int dy4[4] = {-1, 1, 0, 0}, dx4[4] = {0, 0, -1, 1};  // pse.pyx:29-30: up, down, left, right
+  while (true) {
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(p.g_next, 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= *p.g_nwork) return;
+    const int n = p.work[item].x, a = p.work[item].y;
+    const size_t to = (size_t)(n * 2 + 0) * p.R, so = (size_t)n * p.R;
+    const int x0 = p.t_xmin[so + a], x1 = p.t_xmax[so + a];
+    const int y0 = p.run_y[to + a], y1 = p.t_ymax[so + a];
+    const int area = p.t_area[so + a];
+#ifdef OCRPP_CHECKS
+    if (tid == 0 && (n < 0 || n >= p.N || a < 0 || a >= p.R || x0 < 0 || x1 >= W || x0 > x1 || y0 < 0 || y1 >= H || y0 > y1 || area <= 0 || area > H * W))
+      printf("expand: bad item %d n=%d a=%d x=[%d,%d] y=[%d,%d] area=%d nwork=%d\n", item, n, a, x0, x1, y0, y1, area, *p.g_nwork);
+#endif
+    if (tid == 0) {
+      const unsigned long long b = atomicAdd(p.g_arena_used, 4ull * (unsigned long long)area);
+      if ((long long)(b + 4ull * area) <= p.arena_cap) s_base = (long long)b;
+      else {
+        s_base = -1;
+        atomicOr(&p.imgflags[n], OCRPP_IMG_RUN_OVERFLOW);
+      }
+    }
+    __syncthreads();
+    if (s_base < 0) continue;
+    uint32_t* Qc = p.arena + s_base;
+    uint32_t* Qn = Qc + area;
+    uint32_t* X = Qn + area;
+    uint32_t* Y = X + area;
+    const uint8_t* kb = p.kb + (size_t)n * H * W;
+    uint32_t* st = p.st + (size_t)n * H * W;
+
+    // ---- initial queue: surviving seed pixels of this text component in raster order (pse.pyx:33-37),
+    //      minus the ones that have no free text neighbour (they can never claim anything)
+    int nq = 0;
+    {
+      const int spr = (x1 - x0 + kStrip) / kStrip;
+      const int total = spr * (y1 - y0 + 1);
+      for (int s0 = 0; s0 < total; s0 += kExThreads) {
+        const int s = s0 + tid;
+        unsigned mask = 0;
+        int y = 0, xb = 0;
+        if (s < total) {
+          y = y0 + s / spr;
+          xb = x0 + (s % spr) * kStrip;
+#pragma unroll
+          for (int i = 0; i < kStrip; ++i) {
+            const int x = xb + i;
+            if (x > x1) break;
+            const size_t q = (size_t)y * W + x;
+            if (!(kb[q] & 1u)) continue;
+            const uint32_t v = __ldcg(st + q);
+            if (!is_labelled(v)) continue;
+#ifdef OCRPP_CHECKS
+            if ((v & 0x7fffffffu) - 1 >= (unsigned)p.R) { printf("expand: bad label %x at (%d,%d) n=%d\n", v, y, x, n); continue; }
+#endif
+            if (p.s_cc[so + (v & 0x7fffffffu) - 1] != a) continue;
+            bool alive = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int ty = y + dy4[j], tx = x + dx4[j];
+              if (ty < 0 || ty >= H || tx < 0 || tx >= W) continue;
+              const size_t t = (size_t)ty * W + tx;
+              if ((kb[t] & 1u) && __ldcg(st + t) == kUnset) alive = true;
+            }
+            if (alive) mask |= 1u << i;
+          }
+        }
+        int tot;
+        int pos = nq + block_exclusive_scan(__popc(mask), &tot);
+        while (mask) {
+          const int i = __ffs(mask) - 1;
+          mask &= mask - 1;
+#ifdef OCRPP_CHECKS
+          if (pos >= area) { printf("expand: init queue overflow pos=%d area=%d\n", pos, area); break; }
+#endif
+          Qc[pos++] = pack_yx(y, xb + i);
+        }
+        nq += tot;
+      }
+      __syncthreads();  // queue entries visible to every thread of the CTA
+    }
+
+    // ---- levels (PSE: K-2 .. 0, level K-1 is a no-op that only re-queues every seed in order,
+    //      SURVEY H2; PAN: the text mask only, pa.pyx:72)
+    for (int level = (p.mode == kModePse ? p.K - 2 : 0); level >= 0 && nq > 0; --level) {
+      const uint32_t* wave = Qc;
+      int nw = nq, nqn = 0;
+      uint32_t* nxt = X;
+      while (nw > 0) {
+        int nn = 0;
+        for (int c0 = 0; c0 < nw; c0 += kExThreads) {
+          const int r = c0 + tid;
+          const bool active = r < nw;
+          int qy = 0, qx = 0;
+          uint32_t lab = 0, q = 0;
+          if (active) {
+            q = wave[r];
+            qy = q >> 16;
+            qx = q & 0xffffu;
+#ifdef OCRPP_CHECKS
+            if (qy >= H || qx >= W) { printf("expand: bad wave entry %x r=%d nw=%d level=%d\n", q, r, nw, level); }
+#endif
+            lab = __ldcg(st + (size_t)qy * W + qx);
+#ifdef OCRPP_CHECKS
+            if (!is_labelled(lab)) printf("expand: unlabelled wave entry (%d,%d) st=%x r=%d nw=%d level=%d wave0=%d item=%d bbox x[%d,%d] y[%d,%d]\n", qy, qx, lab, r, nw, level, (int)(wave == Qc), item, x0, x1, y0, y1);
+#endif
+            // phase 1: propose key 4r+j to every free neighbour that is inside kernel `level`
+            bool gated = false;
+            float mean[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p.mode == kModePan) {
+              const size_t sr = so + (lab & 0x7fffffffu) - 1;
+              if (p.s_flag[sr]) {
+                gated = true;
+                const double ar = (double)p.s_area[sr];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) mean[c] = (float)(p.s_emb[sr * 4 + c] / ar);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int ty = qy + dy4[j], tx = qx + dx4[j];
+              if (ty < 0 || ty >= H || tx < 0 || tx >= W) continue;
+              const size_t t = (size_t)ty * W + tx;
+              if (!((kb[t] >> level) & 1u)) continue;
+              if (is_labelled(__ldcg(st + t))) continue;
+              if (gated) {  // pa.pyx:86-87: ||emb[:,t] - mean_emb[label]||_2 > 3 blocks the claim
+                float ss = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const float d = __fsub_rn(ex_load<T>(p, n, 2 + c, ty, tx), mean[c]);
+                  ss = __fadd_rn(ss, __fmul_rn(d, d));
+                }
+                if (__fsqrt_rn(ss) > 3.f) continue;
+              }
+              atomicMin(st + t, (uint32_t)(r * 4 + j));
+            }
+          }
+          __syncthreads();
+          // phase 2: owners collect their pixels; alive = some text neighbour is still free
+          unsigned win = 0;
+          bool alive = false;
+          if (active) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int ty = qy + dy4[j], tx = qx + dx4[j];
+              if (ty < 0 || ty >= H || tx < 0 || tx >= W) continue;
+              const size_t t = (size_t)ty * W + tx;
+              if (!(kb[t] & 1u)) continue;
+              const uint32_t v = __ldcg(st + t);
+              if (v == kUnset) alive = true;
+              else if (v == (uint32_t)(r * 4 + j)) win |= 1u << j;
+            }
+          }
+          const bool requeue = active && win == 0 && alive;  // is_edge (pse.pyx:47,58-60)
+          int tot;
+          const int ex = block_exclusive_scan(__popc(win) | (requeue ? 0x10000 : 0), &tot);
+          if (active) {
+            int pos = nn + (ex & 0xffff);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (win & (1u << j)) {
+                const int ty = qy + dy4[j], tx = qx + dx4[j];
+#ifdef OCRPP_CHECKS
+                if (pos >= area) { printf("expand: wave overflow pos=%d area=%d\n", pos, area); break; }
+#endif
+                nxt[pos++] = pack_yx(ty, tx);
+                st[(size_t)ty * W + tx] = lab;
+              }
+#ifdef OCRPP_CHECKS
+            if (requeue && nqn + (ex >> 16) >= area) printf("expand: requeue overflow %d area=%d\n", nqn + (ex >> 16), area);
+#endif
+            if (requeue) Qn[nqn + (ex >> 16)] = q;
+          }
+          nn += tot & 0xffff;
+          nqn += tot >> 16;
+          __syncthreads();  // labels visible to the next block of pops
+        }
+        wave = nxt;
+        nw = nn;
+        nxt = (nxt == X) ? Y : X;
+      }
+      uint32_t* tmp = Qc;
+      Qc = Qn;
+      Qn = tmp;
+      nq = nqn;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// E9: per-label reductions over the final label map, one warp per text run.
+//   PASS 1: area, sum of sigmoid(text logit) in 32.32 fixed point, first/last row
+//   PASS 2: row extents (the hull of a label only needs its leftmost/rightmost pixel per row)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int PASS>
+__global__ void __launch_bounds__(kRunBlk) ex_stats_kernel(ExParams p) {
+  const int n = blockIdx.y;
+  const int nr = p.nruns[n * 2 + 0];
+  const size_t ro = (size_t)(n * 2 + 0) * p.R, so = (size_t)n * p.R;
+  const uint32_t* st = p.st + (size_t)n * p.H * p.W;
+  const int lane = threadIdx.x & 31, wpb = kRunBlk / 32;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < nr; r += kImgCtas * wpb) {
+    if (!p.t_seen[so + p.par[ro + r]]) continue;
+    const int y = p.run_y[ro + r], a = p.run_xs[ro + r], b = p.run_xe[ro + r];
+    for (int xb = a; xb <= b; xb += 32) {
+      const int x = xb + lane;
+      uint32_t lab = 0;
+      unsigned long long fx = 0;
+      if (x <= b) {
+        const uint32_t v = st[(size_t)y * p.W + x];
+        if (is_labelled(v)) {
+          lab = v & 0x7fffffffu;
+          if (PASS == 1) {
+            const float logit = ex_load<T>(p, n, 0, y, x);
+            const float sc = 1.f / (1.f + expf(-logit));  // F.sigmoid (pse_postprocess.py:38)
+            fx = (unsigned long long)__float2ll_rn(sc * 4294967296.0f);
+          }
+        }
+      }
+      unsigned todo = __ballot_sync(0xffffffffu, lab != 0);
+      while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const uint32_t L = __shfl_sync(0xffffffffu, lab, leader);
+        const unsigned mk = __ballot_sync(0xffffffffu, lab == L);
+        if (lab == L) {
+          const size_t q = so + L - 1;
+          if (PASS == 1) {
+            const unsigned lo = __reduce_add_sync(mk, (unsigned)(fx & 0xffffu));
+            const unsigned hi = __reduce_add_sync(mk, (unsigned)(fx >> 16));
+            if (lane == leader) {
+              atomicAdd(&p.l_area[q], __popc(mk));
+              atomicAdd((unsigned long long*)&p.l_sum[q], ((unsigned long long)hi << 16) + lo);
+              atomicMin(&p.l_ymin[q], y);
+              atomicMax(&p.l_ymax[q], y);
+            }
+          } else {
+            const int xmin = __reduce_min_sync(mk, x), xmax = __reduce_max_sync(mk, x);
+            const int off = p.l_rowoff[q];
+            if (lane == leader && off >= 0) {
+              const size_t e = (size_t)n * p.E + off + (y - p.l_ymin[q]);
+              atomicMin(&p.ext_l[e], xmin);
+              atomicMax(&p.ext_r[e], xmax);
+            }
+          }
+        }
+        todo &= ~mk;
+      }
+    }
+  }
+}
+
+// E10: candidates = surviving labels in label order (generate_box iterates i = 1..max(label),
+// pse_postprocess.py:70); row-extent slots. One CTA per image.
+__global__ void __launch_bounds__(kRunThreads) ex_cand_kernel(ExParams p) {
+  const int n = blockIdx.x;
+  const int nr = p.nruns[n * 2 + 1];
+  const size_t ro = (size_t)(n * 2 + 1) * p.R, so = (size_t)n * p.R;
+  const int chunk = (nr + kRunThreads - 1) / kRunThreads;
+  const int lo = min(nr, (int)threadIdx.x * chunk), hi = min(nr, lo + chunk);
+  auto is_cand = [&](int r) { return p.par[ro + r] == r && p.s_alive[so + r] && p.l_area[so + r] > 0; };
+  int local = 0;
+  for (int r = lo; r < hi; ++r) local += is_cand(r) ? 1 : 0;
+  int total;
+  int rank = block_exclusive_scan(local, &total);
+  for (int r = lo; r < hi; ++r) {
+    if (!is_cand(r)) continue;
+    if (rank < p.maxc) {
+      p.cand[(size_t)n * p.maxc + rank] = r;
+      const int nrows = p.l_ymax[so + r] - p.l_ymin[so + r] + 1;
+      const int off = atomicAdd(&p.ext_alloc[n], nrows + 1);
+      if (off + nrows + 1 <= p.E) {
+        p.l_rowoff[so + r] = off;
+        for (int i = 0; i < nrows; ++i) {
+          p.ext_l[(size_t)n * p.E + off + i] = 0x7fffffff;
+          p.ext_r[(size_t)n * p.E + off + i] = -1;
+        }
+      } else {
+        atomicOr(&p.imgflags[n], OCRPP_IMG_RUN_OVERFLOW);
+      }
+    }
+    ++rank;
+  }
+  if (threadIdx.x == 0) {
+    p.ncand[n] = min(total, p.maxc);
+    if (total > p.maxc) atomicOr(&p.imgflags[n], OCRPP_IMG_CANDIDATES_TRUNCATED);
+  }
+}
+
+// E11: generate_box (pse_postprocess.py:65-105 / pan_postprocess.py:73-113), one warp per label.
+constexpr int kGeoWarps = 4;
+constexpr int kSmallRows = 64;
+
+__global__ void __launch_bounds__(kGeoWarps * 32) ex_geometry_kernel(ExParams p) {
+  __shared__ P2i s_pts[kGeoWarps][4 * kSmallRows];
+  __shared__ P2i s_hull[kGeoWarps][4 * kSmallRows + 2];
+  const int n = blockIdx.y;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t so = (size_t)n * p.R;
+  const int nc = p.ncand[n];
+  const int f = p.fout;
+  for (int k = blockIdx.x * kGeoWarps + wib; k < nc; k += gridDim.x * kGeoWarps) {
+    const size_t ko = (size_t)n * p.maxc + k;
+    const int c = p.cand[ko];
+    if (lane == 0) p.res_keep[ko] = 0;
+    const long long area = (long long)p.l_area[so + c] * f * f;  // label upsampled by fout (:58-62)
+    if ((double)area < (double)p.min_area_box) continue;         // points.shape[0] < min_area (:75)
+    // np.mean(score[ind]) (:79): float32 pairwise sum in the reference, exact fixed point here
+    const float score = (float)(((double)p.l_sum[so + c] / kFix) / (double)p.l_area[so + c]);
+    if (score < p.box_thresh) continue;                           // :80
+    const int off = p.l_rowoff[so + c];
+    if (off < 0) continue;  // extent arena exhausted: flagged in ex_cand_kernel
+    const int ymin = p.l_ymin[so + c], nrows = p.l_ymax[so + c] - ymin + 1;
+    const int32_t* ext_l = p.ext_l + (size_t)n * p.E + off;
+    const int32_t* ext_r = p.ext_r + (size_t)n * p.E + off;
+    const int ppr = f == 1 ? 2 : 4;  // points per row: pixel-block corners of the upsampled label
+    P2i *pts, *hull;
+    if (nrows <= kSmallRows) {
+      pts = s_pts[wib];
+      hull = s_hull[wib];
+    } else {
+      pts = p.hull + ((size_t)n * p.E + off) * 8;
+      hull = pts + 4 * nrows;
+    }
+    for (int i = lane; i < nrows; i += 32) {
+      const int xl = ext_l[i] * f, xr = ext_r[i] * f + f - 1, yy = (ymin + i) * f;
+      if (f == 1) {
+        pts[2 * i] = P2i{xl, yy};
+        pts[2 * i + 1] = P2i{xr, yy};
+      } else {
+        pts[4 * i] = P2i{xl, yy};
+        pts[4 * i + 1] = P2i{xr, yy};
+        pts[4 * i + 2] = P2i{xl, yy + f - 1};
+        pts[4 * i + 3] = P2i{xr, yy + f - 1};
+      }
+    }
+    __syncwarp();
+    int hn = 0;
+    if (lane == 0) hn = geom::hull_sorted(pts, ppr * nrows, hull);
+    hn = __shfl_sync(0xffffffffu, hn, 0);
+    __syncwarp();
+    geom::Rect rect;
+    warp_min_area_rect(hull, hn, &rect, lane);  // cv2.minAreaRect + boxPoints (:85-86)
+    if (lane == 0) {
+      double bx[4], by[4];
+      geom::cv_box_order(rect, bx, by);  // corner order of cv2.boxPoints
+      float cx[4], cy[4], ox[4], oy[4];
+      for (int q = 0; q < 4; ++q) {
+        cx[q] = (float)bx[q];
+        cy[q] = (float)by[q];
+      }
+      geom::order_points_clockwise(cx, cy, ox, oy);  // utility.py:21-29
+      const double src_h = p.shape[4 * n + 0], src_w = p.shape[4 * n + 1];
+      const double ratio_h = p.shape[4 * n + 2], ratio_w = p.shape[4 * n + 3];
+      for (int q = 0; q < 4; ++q) {  // :100-102 (float64 division under numpy 2, np.round = half to even)
+        const double fx = (double)ox[q] / ratio_w, fy = (double)oy[q] / ratio_h;
+        p.res_boxf[ko * 8 + 2 * q] = (float)fx;
+        p.res_boxf[ko * 8 + 2 * q + 1] = (float)fy;
+        p.res_box[ko * 8 + 2 * q] = (int16_t)(int)fmin(fmax(geom::round_half_even(fx), 0.0), src_w);
+        p.res_box[ko * 8 + 2 * q + 1] = (int16_t)(int)fmin(fmax(geom::round_half_even(fy), 0.0), src_h);
+      }
+      p.res_score[ko] = score;
+      p.res_keep[ko] = 1;
+    }
+  }
+}
+
+// E12: ordered compaction of the kept boxes, one CTA per image.
+__global__ void __launch_bounds__(kRunThreads) ex_compact_kernel(ExParams p) {
+  const int n = blockIdx.x;
+  const int nc = p.ncand[n];
+  const size_t ko = (size_t)n * p.maxc;
+  const int chunk = (nc + kRunThreads - 1) / kRunThreads;
+  const int lo = min(nc, (int)threadIdx.x * chunk), hi = min(nc, lo + chunk);
+  int local = 0;
+  for (int k = lo; k < hi; ++k) local += p.res_keep[ko + k];
+  int total;
+  int pos = block_exclusive_scan(local, &total);
+  for (int k = lo; k < hi; ++k) {
+    if (!p.res_keep[ko + k]) continue;
+    for (int q = 0; q < 8; ++q) {
+      p.boxes_out[(ko + pos) * 8 + q] = p.res_box[(ko + k) * 8 + q];
+      if (p.boxes_f_out) p.boxes_f_out[(ko + pos) * 8 + q] = p.res_boxf[(ko + k) * 8 + q];
+    }
+    p.scores_out[ko + pos] = p.res_score[ko + k];
+    ++pos;
+  }
+  if (threadIdx.x == 0) {
+    const int fl = p.imgflags[n];
+    p.counts_out[n] = (fl & OCRPP_IMG_RUN_OVERFLOW) ? 0 : total;
+    p.status_out[n] = fl;
+  }
+}
+
+// debug / parity: the label map pse()/pa() return (cv2 ids), at processing resolution
+__global__ void __launch_bounds__(kRunBlk) ex_labels_kernel(ExParams p) {
+  const int n = blockIdx.y;
+  const int nr = p.nruns[n * 2 + 0];
+  const size_t ro = (size_t)(n * 2 + 0) * p.R, so = (size_t)n * p.R;
+  const uint32_t* st = p.st + (size_t)n * p.H * p.W;
+  int32_t* lab = p.labels_dbg + (size_t)n * p.H * p.W;
+  const int lane = threadIdx.x & 31, wpb = kRunBlk / 32;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < nr; r += kImgCtas * wpb) {
+    if (!p.t_seen[so + p.par[ro + r]]) continue;
+    const size_t row = (size_t)p.run_y[ro + r] * p.W;
+    for (int x = p.run_xs[ro + r] + lane; x <= (int)p.run_xe[ro + r]; x += 32) {
+      const uint32_t v = st[row + x];
+      if (is_labelled(v)) lab[row + x] = p.s_cid[so + (v & 0x7fffffffu) - 1];
+    }
+  }
+}
+
+size_t ex_carve(ExParams& p, void* ws) {
+  Carver c{(char*)ws, 0};
+  const size_t N = p.N, R = p.R, E = p.E, HW = (size_t)p.H * p.W;
+  p.g_nwork = c.take<int32_t>(64);  // g_nwork | g_next | g_arena_used(2 words) + per-image counters below
+  p.g_next = p.g_nwork ? p.g_nwork + 1 : nullptr;
+  p.g_arena_used = p.g_nwork ? reinterpret_cast<unsigned long long*>(p.g_nwork + 2) : nullptr;
+  p.nruns = c.take<int32_t>(5 * N);  // nruns[2N] | ext_alloc | imgflags | ncand, cleared together
+  p.ext_alloc = p.nruns ? p.nruns + 2 * N : nullptr;
+  p.imgflags = p.nruns ? p.nruns + 3 * N : nullptr;
+  p.ncand = p.nruns ? p.nruns + 4 * N : nullptr;
+  p.kb = c.take<uint8_t>(N * HW);
+  p.st = c.take<uint32_t>(N * HW);
+  p.bits = c.take<uint32_t>(N * 2 * p.H * p.Wd);
+  p.rowptr = c.take<int32_t>(N * 2 * (p.H + 1));
+  p.run_xs = c.take<uint16_t>(N * 2 * R);
+  p.run_xe = c.take<uint16_t>(N * 2 * R);
+  p.run_y = c.take<uint16_t>(N * 2 * R);
+  p.par = c.take<int32_t>(N * 2 * R);
+  p.t_area = c.take<int32_t>(N * R);
+  p.t_xmin = c.take<int32_t>(N * R);
+  p.t_xmax = c.take<int32_t>(N * R);
+  p.t_ymax = c.take<int32_t>(N * R);
+  p.t_seen = c.take<int32_t>(N * R);
+  p.t_amin = c.take<int32_t>(N * R);
+  p.t_amax = c.take<int32_t>(N * R);
+  p.s_area = c.take<int32_t>(N * R);
+  p.s_cc = c.take<int32_t>(N * R);
+  p.s_cid = c.take<int32_t>(N * R);
+  p.s_alive = c.take<int32_t>(N * R);
+  p.s_flag = c.take<int32_t>(N * R);
+  p.s_emb = c.take<double>(p.mode == kModePan ? N * R * 4 : 4);
+  p.l_area = c.take<int32_t>(N * R);
+  p.l_ymin = c.take<int32_t>(N * R);
+  p.l_ymax = c.take<int32_t>(N * R);
+  p.l_rowoff = c.take<int32_t>(N * R);
+  p.l_sum = c.take<long long>(N * R);
+  p.ext_l = c.take<int32_t>(N * E);
+  p.ext_r = c.take<int32_t>(N * E);
+  p.hull = c.take<P2i>(N * E * 8);
+  p.cand = c.take<int32_t>(N * p.maxc);
+  p.res_keep = c.take<int32_t>(N * p.maxc);
+  p.res_box = c.take<int16_t>(N * p.maxc * 8);
+  p.res_boxf = c.take<float>(N * p.maxc * 8);
+  p.res_score = c.take<float>(N * p.maxc);
+  p.work = c.take<int2>(N * R);
+  p.arena = c.take<uint32_t>((size_t)p.arena_cap);
+  return align_up(c.off, 256);
+}
+
+int ex_resolve_runs(int H, int W, int max_runs) {
+  const long long worst = (long long)H * ((W + 1) / 2);  // foreground runs only
+  if (max_runs <= 0 || max_runs > worst) return (int)worst;
+  return max_runs;
+}
+
+long long ex_resolve_arena(int N, int H, int W, long long arena_elems) {
+  const long long worst = 4ll * N * H * W;
+  if (arena_elems <= 0 || arena_elems > worst) return worst;
+  return arena_elems;
+}
+
+void ex_fill(ExParams& p, int mode, int N, int C, int K, int h, int w, int fin, int fout, int max_boxes,
+             int max_runs, long long arena_elems) {
+  p.mode = mode;
+  p.N = N; p.C = C; p.K = K; p.h = h; p.w = w; p.fin = fin; p.fout = fout;
+  p.H = h * fin; p.W = w * fin; p.Wd = (p.W + 31) / 32;
+  p.R = ex_resolve_runs(p.H, p.W, max_runs);
+  p.E = 2 * p.R + 4;
+  p.maxc = max_boxes;
+  p.seed_bit = mode == kModePse ? K - 1 : 1;
+  p.arena_cap = ex_resolve_arena(N, p.H, p.W, arena_elems);
+}
+
+template <typename T>
+int ex_launch(ExParams& p, cudaStream_t s, bool vec) {
+  OCRPP_CUDA(cudaMemsetAsync(p.g_nwork, 0, sizeof(int32_t) * 64, s));
+  OCRPP_CUDA(cudaMemsetAsync(p.nruns, 0, sizeof(int32_t) * 5 * p.N, s));
+  ProfileScope prof(s);
+  const int N = p.N;
+  {
+    dim3 grid((p.H + kBinWarps - 1) / kBinWarps, N);
+    if (vec) ex_binarize_kernel<T, true><<<grid, kBinWarps * 32, 0, s>>>(p);
+    else ex_binarize_kernel<T, false><<<grid, kBinWarps * 32, 0, s>>>(p);
+    OCRPP_LAUNCHED();
+    prof.mark("ex_binarize");
+  }
+  ex_runs_kernel<<<dim3(N, 2), kRunThreads, sizeof(int) * (p.H + 1), s>>>(p);
+  OCRPP_LAUNCHED();
+  prof.mark("ex_runs");
+  const dim3 rgrid2(kImgCtas, N, 2), rgrid(kImgCtas, N);
+  ex_link_kernel<<<rgrid2, kRunBlk, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  prof.mark("ex_link");
+  ex_flatten_kernel<<<rgrid2, kRunBlk, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  prof.mark("ex_flatten");
+  ex_seed_kernel<<<N, kRunThreads, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  prof.mark("ex_seed");
+  if (p.mode == kModePan) {
+    ex_pan_flag_kernel<T><<<rgrid, kRunBlk, 0, s>>>(p);
+    OCRPP_LAUNCHED();
+  }
+  ex_paint_kernel<<<rgrid, kRunBlk, 0, s>>>(p, 0);
+  OCRPP_LAUNCHED();
+  ex_paint_kernel<<<rgrid, kRunBlk, 0, s>>>(p, 1);
+  OCRPP_LAUNCHED();
+  prof.mark("ex_paint");
+  ex_expand_kernel<T><<<kNumSMs * 8, kExThreads, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  prof.mark("ex_expand");
+  ex_stats_kernel<T, 1><<<rgrid, kRunBlk, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  prof.mark("ex_stats");
+  ex_cand_kernel<<<N, kRunThreads, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  prof.mark("ex_cand");
+  ex_stats_kernel<T, 2><<<rgrid, kRunBlk, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  prof.mark("ex_extents");
+  ex_geometry_kernel<<<dim3(16, N), kGeoWarps * 32, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  prof.mark("ex_geometry");
+  ex_compact_kernel<<<N, kRunThreads, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  prof.mark("ex_compact");
+  if (p.labels_dbg) {
+    OCRPP_CUDA(cudaMemsetAsync(p.labels_dbg, 0, sizeof(int32_t) * (size_t)N * p.H * p.W, s));
+    ex_labels_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
+    OCRPP_LAUNCHED();
+  }
+  return OCRPP_OK;
+}
+
+int ex_postprocess(int mode, const void* maps_dev, int dtype, int N, int C, int K, int h, int w,
+                   int64_t stride_n, int64_t stride_c, int64_t stride_h, int fin, int fout,
+                   const double* shape_dev, float thresh, float box_thresh, float min_area_seed,
+                   float min_area_box, int max_boxes, int max_runs, int64_t arena_elems,
+                   int16_t* boxes_out_dev, float* scores_out_dev, int32_t* counts_out_dev,
+                   int32_t* status_out_dev, float* boxes_f_out_dev, int32_t* labels_dbg_dev,
+                   void* workspace_dev, size_t workspace_bytes, void* stream) {
+  const char* nm = mode == kModePse ? "pse" : "pan";
+  OCRPP_CHECK_ARG(dtype == OCRPP_F32 || dtype == OCRPP_F16, "%s: dtype must be OCRPP_F32 or OCRPP_F16", nm);
+  OCRPP_CHECK_ARG(N >= 0 && h > 0 && w > 0, "%s: bad shape N=%d h=%d w=%d", nm, N, h, w);
+  OCRPP_CHECK_ARG(fin >= 1 && fin <= 4 && fout >= 1 && fout <= 4, "%s: upsample factors must be in [1,4]", nm);
+  OCRPP_CHECK_ARG(K >= 1 && K <= kMaxK, "%s: kernel_num must be in [1,%d]", nm, kMaxK);
+  OCRPP_CHECK_ARG((long long)h * fin * fout < 32768 && (long long)w * fin * fout < 32768,
+                  "%s: output resolution must be below 32768 x 32768", nm);
+  OCRPP_CHECK_ARG(max_boxes > 0, "%s: max_boxes must be positive", nm);
+  if (N == 0) return OCRPP_OK;
+  OCRPP_CHECK_ARG(maps_dev && shape_dev && boxes_out_dev && scores_out_dev && counts_out_dev && status_out_dev && workspace_dev,
+                  "%s: null pointer argument", nm);
+  ExParams p{};
+  ex_fill(p, mode, N, C, K, h, w, fin, fout, max_boxes, max_runs, arena_elems);
+  p.maps = maps_dev; p.stride_n = stride_n; p.stride_c = stride_c; p.stride_h = stride_h; p.shape = shape_dev;
+  p.thresh = thresh; p.box_thresh = box_thresh; p.min_area_seed = min_area_seed; p.min_area_box = min_area_box;
+  const size_t need = ex_carve(p, workspace_dev);
+  if (need > workspace_bytes)
+    return set_error(OCRPP_ERR_WORKSPACE_TOO_SMALL, "%s: workspace needs %zu bytes, got %zu", nm, need, workspace_bytes);
+  p.boxes_out = boxes_out_dev; p.scores_out = scores_out_dev; p.counts_out = counts_out_dev;
+  p.status_out = status_out_dev; p.boxes_f_out = boxes_f_out_dev; p.labels_dbg = labels_dbg_dev;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool vec = dtype == OCRPP_F32 && fin == 1 && ((uintptr_t)maps_dev % 16 == 0) && stride_n % 4 == 0 &&
+                   stride_c % 4 == 0 && stride_h % 4 == 0 && p.W % 4 == 0;
+  if (dtype == OCRPP_F32) return ex_launch<float>(p, s, vec);
+  return ex_launch<__half>(p, s, false);
+}
+
+}  // namespace
+}  // namespace ocrpp
+
+extern "C" size_t ocrpp_pse_workspace_bytes(int N, int K, int h, int w, int upsample_in, int max_boxes,
+                                            int max_runs, int64_t arena_elems) {
+  using namespace ocrpp;
+  if (N <= 0 || h <= 0 || w <= 0 || upsample_in < 1 || max_boxes <= 0) return 0;
+  ExParams p{};
+  ex_fill(p, kModePse, N, K, K, h, w, upsample_in, 1, max_boxes, max_runs, arena_elems);
+  return ex_carve(p, nullptr);
+}
+
+extern "C" int ocrpp_pse_postprocess(const void* maps_dev, int dtype, int N, int K, int h, int w,
+                                     int64_t stride_n, int64_t stride_c, int64_t stride_h,
+                                     int upsample_in, int upsample_out, const double* shape_dev,
+                                     float thresh, float box_thresh, float min_area_seed,
+                                     float min_area_box, int max_boxes, int max_runs, int64_t arena_elems,
+                                     int16_t* boxes_out_dev, float* scores_out_dev,
+                                     int32_t* counts_out_dev, int32_t* status_out_dev,
+                                     float* boxes_f_out_dev, int32_t* labels_dbg_dev,
+                                     void* workspace_dev, size_t workspace_bytes, void* stream) {
+  return ocrpp::ex_postprocess(ocrpp::kModePse, maps_dev, dtype, N, K, K, h, w, stride_n, stride_c, stride_h,
+                               upsample_in, upsample_out, shape_dev, thresh, box_thresh, min_area_seed,
+                               min_area_box, max_boxes, max_runs, arena_elems, boxes_out_dev, scores_out_dev,
+                               counts_out_dev, status_out_dev, boxes_f_out_dev, labels_dbg_dev,
+                               workspace_dev, workspace_bytes, stream);
+}
+
+extern "C" size_t ocrpp_pan_workspace_bytes(int N, int h, int w, int upsample_in, int max_boxes,
+                                            int max_runs, int64_t arena_elems) {
+  using namespace ocrpp;
+  if (N <= 0 || h <= 0 || w <= 0 || upsample_in < 1 || max_boxes <= 0) return 0;
+  ExParams p{};
+  ex_fill(p, kModePan, N, 6, 2, h, w, upsample_in, 1, max_boxes, max_runs, arena_elems);
+  return ex_carve(p, nullptr);
+}
+
+extern "C" int ocrpp_pan_postprocess(const void* maps_dev, int dtype, int N, int h, int w,
+                                     int64_t stride_n, int64_t stride_c, int64_t stride_h,
+                                     int upsample_in, int upsample_out, const double* shape_dev,
+                                     float thresh, float box_thresh, float min_kernel_area,
+                                     float min_area_box, int max_boxes, int max_runs, int64_t arena_elems,
+                                     int16_t* boxes_out_dev, float* scores_out_dev,
+                                     int32_t* counts_out_dev, int32_t* status_out_dev,
+                                     float* boxes_f_out_dev, int32_t* labels_dbg_dev,
+                                     void* workspace_dev, size_t workspace_bytes, void* stream) {
+  return ocrpp::ex_postprocess(ocrpp::kModePan, maps_dev, dtype, N, 6, 2, h, w, stride_n, stride_c, stride_h,
+                               upsample_in, upsample_out, shape_dev, thresh, box_thresh, min_kernel_area,
+                               min_area_box, max_boxes, max_runs, arena_elems, boxes_out_dev, scores_out_dev,
+                               counts_out_dev, status_out_dev, boxes_f_out_dev, labels_dbg_dev,
+                               workspace_dev, workspace_bytes, stream);
+}

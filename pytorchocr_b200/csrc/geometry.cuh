@@ -200,6 +200,24 @@ OCRPP_HD void min_area_rect(const P2i* h, int n, Rect* r) {
   rect_from_fit(h, n, best, bf, r);
 }
 
+// cv::boxPoints corner ORDER for a rectangle found by cv::minAreaRect (angle in [-90, 0)): index 0 is
+// the lowest corner (largest y; the right one when two share it, i.e. axis-aligned), then clockwise
+// on screen: left-most, top-most, right-most. Rect's own corner sequence is already screen-clockwise,
+// so this is a rotation of the indices. The order only matters where a later argmin/argmax or stable
+// sort over the corners meets an exact tie (45-degree "diamonds": order_points_clockwise then repeats
+// a corner exactly as the reference does).
+OCRPP_HD void cv_box_order(const Rect& r, double* ox, double* oy) {
+  int i0 = 0;
+  for (int i = 1; i < 4; ++i) {
+    const double dy = r.cy[i] - r.cy[i0];
+    if (dy > 1e-7 || (dy >= -1e-7 && r.cx[i] > r.cx[i0])) i0 = i;
+  }
+  for (int k = 0; k < 4; ++k) {
+    ox[k] = r.cx[(i0 + k) & 3];
+    oy[k] = r.cy[(i0 + k) & 3];
+  }
+}
+
 // GetMiniBoxes ordering (db_postprocess.cpp:165-190): stable sort by x, then
 // [TL, TR, BR, BL] from the y order inside the left pair and the right pair.
 OCRPP_HD void mini_box(const float* cx, const float* cy, float* ox, float* oy) {

@@ -106,7 +106,7 @@ def db_batch(n, seed=BASE_SEED, H=736, W=1280, n_regions=200, dtype=np.float32):
     return out
 
 
-def pse_maps(seed, H=736, W=1280, n_regions=200, K=7):
+def pse_maps(seed, H=736, W=1280, n_regions=200, K=7, hh_rng=(5, 10), hw_rng=(15, 37), n_abs=None):
     """PSENet logits [K,H,W] at processing resolution (SURVEY §8(d) Cfg 3 generator): channel k is
     the rectangle shrunk to (1 - 0.1k); +4 inside / -4 outside + N(0,0.5); 20% of regions placed
     as touching pairs (merged text masks => contested expansion); 5% with text logit +1
@@ -114,7 +114,8 @@ def pse_maps(seed, H=736, W=1280, n_regions=200, K=7):
     rng = np.random.default_rng(seed)
     scale = (H * W) / float(736 * 1280)
     n = n_regions if scale >= 1 else max(2, int(round(n_regions * scale)))
-    rects = _place_rects(rng, H, W, n, margin=6)
+    n = n_abs if n_abs is not None else n
+    rects = _place_rects(rng, H, W, n, hh_rng, hw_rng, margin=6)
     masks = np.zeros((K, H, W), np.uint8)
     weak = np.zeros((H, W), np.uint8)
     for r in rects:
@@ -147,7 +148,7 @@ def pse_maps(seed, H=736, W=1280, n_regions=200, K=7):
     return logits
 
 
-def pan_maps(seed, H=736, W=1280, n_regions=200):
+def pan_maps(seed, H=736, W=1280, n_regions=200, hh_rng=(5, 10), hw_rng=(15, 37), n_abs=None):
     """PAN++ maps [6,H,W] (SURVEY §8(d) Cfg 4 generator): ch0 text logit, ch1 kernel logit
     (half-sizes x0.5), ch2-5 embedding = per-instance centre (pairwise distance >= 6) + N(0,0.25);
     no pixel within 0.05 of the distance-3 gate; 10% of touching pairs carry a 1-px kernel blob
@@ -155,7 +156,8 @@ def pan_maps(seed, H=736, W=1280, n_regions=200):
     rng = np.random.default_rng(seed)
     scale = (H * W) / float(736 * 1280)
     n = n_regions if scale >= 1 else max(2, int(round(n_regions * scale)))
-    rects = _place_rects(rng, H, W, n, margin=6)
+    n = n_abs if n_abs is not None else n
+    rects = _place_rects(rng, H, W, n, hh_rng, hw_rng, margin=6)
     text = np.zeros((H, W), np.uint8)
     kern = np.zeros((H, W), np.uint8)
     inst = np.zeros((H, W), np.int32)
@@ -178,18 +180,20 @@ def pan_maps(seed, H=736, W=1280, n_regions=200):
             _fill_rect(m, g, 1)
             text |= m
             inst[m > 0] = iid
-            if u < 0.02 and gi == 1:
-                gx, gy = int(g[0]), int(g[1])
-                if 1 <= gy < H - 1 and 1 <= gx < W - 1:
-                    kern[gy, gx] = 1          # 1-px kernel blob
-            elif u < 0.02 and gi == 0 and big_done < 4 and H >= 200:
-                # oversized kernel (>= 1025 px) so that area ratio vs the 1-px blob exceeds 1024
-                big = (g[0], g[1], max(g[2], 30), max(g[3], 10), g[4])
+            if u < 0.02 and gi == 0 and big_done < 4 and H >= 200 and W >= 400:
+                # ratio-flag scene (pa.pyx:42-54): one long text region holding a >= 3073-px kernel and a
+                # 3-px kernel blob (3 >= min_kernel_area 2.6 survives; 3 * 1024 < big area => both flagged)
+                a = math.radians(g[4])
+                ca, sa = math.cos(a), math.sin(a)
+                bx, by = min(max(g[0], 100.0), W - 100.0), min(max(g[1], 50.0), H - 50.0)
+                trect = (bx, by, 90, 14, g[4])
                 mb = np.zeros((H, W), np.uint8)
-                _fill_rect(mb, big, 1)
+                _fill_rect(mb, trect, 1)
                 text |= mb
-                inst[(mb > 0) & (inst == 0)] = iid
-                _fill_rect(kern, big, 1, 0.95)
+                inst[mb > 0] = iid
+                _fill_rect(kern, (bx - 10 * ca, by - 10 * sa, 75, 12, g[4]), 1, 0.95)
+                qx, qy = int(round(bx + 80 * ca)), int(round(by + 80 * sa))
+                kern[qy, qx - 1:qx + 2] = 1
                 big_done += 1
             else:
                 _fill_rect(kern, g, 1, 0.5)

@@ -25,6 +25,30 @@ int shim_min_area_rect(const int* xy, int n, double* corners, double* wh) {
   return hn;
 }
 
+// points -> corners in cv2.boxPoints order, then order_points_clockwise (float32) -> oxy[8]
+void shim_generate_box(const int* xy, int n, float* box_cv, float* box_ordered) {
+  std::vector<P2i> p(n), h(n + 2);
+  for (int i = 0; i < n; ++i) p[i] = P2i{xy[2 * i], xy[2 * i + 1]};
+  sort_points_yx(p.data(), n);
+  int hn = hull_sorted(p.data(), n, h.data());
+  Rect r;
+  min_area_rect(h.data(), hn, &r);
+  double bx[4], by[4];
+  cv_box_order(r, bx, by);
+  float cx[4], cy[4], ox[4], oy[4];
+  for (int k = 0; k < 4; ++k) {
+    cx[k] = (float)bx[k];
+    cy[k] = (float)by[k];
+    box_cv[2 * k] = cx[k];
+    box_cv[2 * k + 1] = cy[k];
+  }
+  order_points_clockwise(cx, cy, ox, oy);
+  for (int k = 0; k < 4; ++k) {
+    box_ordered[2 * k] = ox[k];
+    box_ordered[2 * k + 1] = oy[k];
+  }
+}
+
 int shim_do_offset(const int* quad_xy, double delta, int* out_xy, int cap) {
   P2i q[4];
   for (int i = 0; i < 4; ++i) q[i] = P2i{quad_xy[2 * i], quad_xy[2 * i + 1]};

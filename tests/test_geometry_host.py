@@ -135,3 +135,47 @@ def test_box_orderings_and_rounding(shim):
     for v in (0.5, 1.5, 2.5, -0.5, -1.5, 0.49999997, 3.4999998, 1e6 + 0.5):
         assert shim.shim_roundf(v) == db_oracle.roundf(np.float32(v))
         assert shim.shim_round_half_even(v) == np.round(v)
+
+
+def test_box_points_order_matches_cv2(shim):
+    """cv_box_order reproduces the corner ORDER of cv2.boxPoints(cv2.minAreaRect(.)), including exact
+    45-degree diamonds where order_points_clockwise (utility.py:21-29) meets ties and repeats a corner."""
+    rng = np.random.default_rng(11)
+    n_diamond = 0
+    for i in range(1500):
+        if i % 3 == 0:   # lattice diamond: all edges at +-45 degrees
+            c = rng.integers(10, 60, 2)
+            a, b = int(rng.integers(1, 15)), int(rng.integers(1, 15))
+            corners = np.array([c, c + [a, a], c + [a - b, a + b], c + [-b, b]])
+            m = np.zeros((120, 120), np.uint8)
+            cv2.fillPoly(m, [corners.astype(np.int32)], 1)
+            ys, xs = np.nonzero(m)
+            pts = np.stack([xs, ys], 1)
+        elif i % 3 == 1:  # axis-aligned block
+            x0, y0 = rng.integers(0, 50, 2)
+            w, h = rng.integers(1, 40, 2)
+            pts = np.array([[x, y] for x in range(x0, x0 + w + 1) for y in range(y0, y0 + h + 1)])
+        else:
+            pts = _raster_blob(rng, i % 2 == 0)
+        if len(pts) < 3:
+            continue
+        pts = np.ascontiguousarray(pts, np.int32)
+        ref_cv = cv2.boxPoints(cv2.minAreaRect(pts))
+        if min(cv2.minAreaRect(pts)[1]) < 1e-6:
+            continue   # degenerate (collinear) sets: cv2's angle is arbitrary
+        box_cv = np.zeros((4, 2), np.float32)
+        box_o = np.zeros((4, 2), np.float32)
+        shim.shim_generate_box(pts.ctypes.data_as(C.c_void_p), len(pts), box_cv.ctypes.data_as(C.c_void_p),
+                               box_o.ctypes.data_as(C.c_void_p))
+        if _set_dist(ref_cv, box_cv) > 1e-3:
+            continue   # equal-area tie: a different rectangle (counted elsewhere)
+        assert np.abs(ref_cv - box_cv).max() < 1e-3, (i, ref_cv, box_cv)
+        want = order_points_clockwise(ref_cv)
+        s = ref_cv.sum(1)
+        d = ref_cv[:, 1] - ref_cv[:, 0]
+        noisy_tie = any(0 < abs(v[i] - v[j]) < 1e-4 for v in (s, d) for i in range(4) for j in range(i))
+        if not noisy_tie:   # cv2's float32 noise decides near-ties; exact ties and clear cases must match
+            assert np.abs(want - box_o).max() < 1e-3, (i, want, box_o)
+        if i % 3 == 0:
+            n_diamond += 1
+    assert n_diamond > 300
