@@ -33,7 +33,7 @@ def _check(maps, shape_list, loose=0.02, expect_flags=False, **kw):
     for n in range(len(want)):
         assert np.array_equal(want[n]["label_proc"], ex["labels"][n]), "label map differs (image %d)" % n
         k = int(counts[n])
-        merge(tot, compare_image(boxes[n, :k], ex["boxes_f"][n, :k], scores[n, :k], want[n]))
+        merge(tot, compare_image(boxes[n, :k], ex["boxes_f"][n, :k], scores[n, :k], want[n], np.asarray(shape_list, np.float64)[n]))
         flags += int(want[n]["flag"].sum())
     assert tot.get("tie", 0) + tot.get("ordering", 0) <= max(1, loose * tot.get("n", 0)), sorted(tot.items())
     if expect_flags:
