@@ -1,13 +1,15 @@
 #!/usr/bin/env python
-"""Benchmark of the post-processing hot path (contract: see the task statement / DESIGN.md §Measurement).
+"""Benchmark of the post-processing hot path (contract: see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload db|ctc]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload db|pse|pan|ctc] [--batch B] [--no-cpu]
 
-A "step" is one pass of the hot path over one batch of synthetic input. Default workload =
+A "step" is one pass of the hot path over one batch of synthetic input. The default workload is
 BASELINE.json configs[1]: DB++ r18 post-process, batch 256 synthetic 736x1280 maps (~200 text
-regions each) per GPU. Scaling is WEAK: every rank processes its own batch of 256 (the path shards
-by image, no collective on the data path); `value` = images all ranks processed / max-over-ranks
-device time. One JSON line is printed by rank 0.
+regions each) per GPU. The other workloads are BASELINE.json configs[2..4] (PSE, PAN, CTC).
+Scaling is WEAK: every rank processes its own batch (the path shards by image / text line, no
+collective on the data path); `value` = units all ranks processed / max-over-ranks device time.
+Rank 0 prints ONE JSON line.
 """
 import argparse
 import json
@@ -24,42 +26,80 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 H, W = 736, 1280
+SEED = 20221001
 DB_CFG = dict(thresh=0.3, box_thresh=0.5, max_candidates=1000, unclip_ratio=1.7, score_mode="poly", cpp_speedup=True)
+PSE_CFG = dict(thresh=0, box_thresh=0.85, min_area=16, scale=1)                          # det_r50_pse.yml:56-62
+PAN_CFG = dict(thresh=0, box_thresh=0.85, min_area=16, min_kernel_area=2.6, scale=1)     # det_r18_pan.yml:62-69 at full res
+CTC_T, CTC_C = 80, 6623
 
 
 # ----------------------------------------------------------------------------------------------
-# synthetic inputs / CPU legs (run BEFORE CUDA is initialised: they fork worker processes)
+# host-side workers (fork pool; run BEFORE CUDA is initialised)
 # ----------------------------------------------------------------------------------------------
-def _gen_one(args):
-    seed, h, w = args
+def _gen_db(seed):
     from pytorchocr_b200 import synth
-    return synth.db_map(seed, h, w)
+    return synth.db_map(seed, H, W)
 
 
-def _oracle_one(m):
+def _gen_pse_scene(seed):
+    from pytorchocr_b200 import synth
+    return synth.pse_scene(seed, H, W)[:2]
+
+
+def _gen_pan_scene(seed):
+    from pytorchocr_b200 import synth
+    return synth.pan_scene(seed, H, W)[:4]
+
+
+def _cpu_db(m):
     import cv2
     cv2.setNumThreads(1)
     from oracle.db_oracle import DBPostProcessOracle
-    op = DBPostProcessOracle(**DB_CFG)
-    r = op({"maps": m[None, None]}, [[m.shape[0], m.shape[1], 1.0, 1.0]])
+    r = DBPostProcessOracle(**DB_CFG)({"maps": m[None, None]}, [[H, W, 1.0, 1.0]])
     return len(r[0]["points"])
 
 
-def make_db_maps(batch, seed0, pool):
-    maps = pool.map(_gen_one, [(seed0 + i, H, W) for i in range(batch)], chunksize=4)
-    return np.stack(maps)[:, None]  # [B,1,H,W] f32
-
-
-def cpu_db_rate(maps, pool, cores, repeat=1):
-    """images/s of the CPU oracle (port of the reference's C++/OpenCV path) on `cores` processes."""
-    imgs = [maps[i, 0] for i in range(maps.shape[0])]
-    pool.map(_oracle_one, imgs[:cores])  # warm the workers (imports, page-in)
+def _cpu_pse(seed):
+    import cv2
+    cv2.setNumThreads(1)
+    from oracle.pse_oracle import PSEPostProcessOracle
+    from pytorchocr_b200 import synth
+    m = synth.pse_maps(seed, H, W)
     t0 = time.perf_counter()
-    n = 0
-    for _ in range(repeat):
-        n += len(pool.map(_oracle_one, imgs, chunksize=max(1, len(imgs) // (cores * 4))))
+    r = PSEPostProcessOracle(maps_at_processing_res=True, **PSE_CFG)({"maps": m[None]}, [[H, W, 1.0, 1.0]])
+    return time.perf_counter() - t0, len(r[0]["points"])
+
+
+def _cpu_pan(seed):
+    import cv2
+    cv2.setNumThreads(1)
+    from oracle.pan_oracle import PANPostProcessOracle
+    from pytorchocr_b200 import synth
+    m = synth.pan_maps(seed, H, W)
+    t0 = time.perf_counter()
+    r = PANPostProcessOracle(maps_at_processing_res=True, **PAN_CFG)({"maps": m[None]}, [[H, W, 1.0, 1.0]])
+    return time.perf_counter() - t0, len(r[0]["points"])
+
+
+def _cpu_ctc(args):
+    seed, lines, dict_path = args
+    from oracle.ctc_oracle import CTCLabelDecodeNumpy
+    from pytorchocr_b200 import synth
+    probs, _ = synth.ctc_probs_numpy(seed, CTC_T, lines, CTC_C)
+    op = CTCLabelDecodeNumpy(dict_path)
+    x = np.ascontiguousarray(probs.transpose(1, 0, 2))   # numpy input is [B,T,C] (rec_postprocess.py:80-82)
+    t0 = time.perf_counter()
+    r = op(x)
+    return time.perf_counter() - t0, len(r)
+
+
+def _timed_pool(pool, fn, items, cores):
+    """Runs fn over items on the pool; returns (units per second of wall time, n, seconds)."""
+    pool.map(fn, items[:cores])  # warm the workers (imports, page-in)
+    t0 = time.perf_counter()
+    out = pool.map(fn, items, chunksize=1)
     dt = time.perf_counter() - t0
-    return n / dt, n, dt
+    return out, dt
 
 
 # ----------------------------------------------------------------------------------------------
@@ -114,6 +154,256 @@ class ClockSampler(object):
 
 
 # ----------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------
+class Workload(object):
+    name = None
+    unit = "images/s"
+    metric = "post-process images/sec @736x1280"
+    default_batch = 256
+    dtype = "f32"
+    stream_kernel = None     # the kernel that streams the operator input (phase 0 of the profile)
+
+    def __init__(self, args, rank, world):
+        self.args, self.rank, self.world = args, rank, world
+        self.batch = args.batch or self.default_batch
+        self.cores = max(1, (os.cpu_count() or 1) // max(1, world))
+
+    # per-unit algorithmic bytes: the operator input at processing resolution read once
+    def alg_bytes_per_unit(self):
+        raise NotImplementedError
+
+
+class DetWorkload(Workload):
+    """Shared plumbing of the three detection workloads."""
+    channels = 1
+    op_name = None
+    cfg = None
+
+    def alg_bytes_per_unit(self):
+        return self.channels * H * W * 4
+
+    def device_prepare(self, dev):
+        import torch
+        from pytorchocr_b200.postprocess import build_post_process
+        self.torch, self.dev = torch, dev
+        self.op = build_post_process(dict(self.cfg, name=self.op_name, cuda_speedup=True, **self.extra_cfg()))
+        self.dev_maps = self.make_device_maps(dev)
+        self.host_maps = torch.empty(self.dev_maps.shape, dtype=torch.float32, pin_memory=True)
+        self.host_maps.copy_(self.dev_maps)
+        self.shape_list = np.array([[H, W, 1.0, 1.0]] * self.batch, np.float64)
+        res = self.op({"maps": self.dev_maps}, self.shape_list)   # allocates/caches buffers, settles capacities
+        self.n_boxes = int(sum(len(r["points"]) for r in res))
+        self.buf = next(iter(self.op._cache.values()))
+        self.key = next(iter(self.op._cache))
+
+    def extra_cfg(self):
+        return {}
+
+    def e2e_step(self):
+        d = self.host_maps.to(self.dev, non_blocking=True)       # H2D of this step's maps from pinned memory
+        return self.op({"maps": d}, self.shape_list)             # kernels + D2H of boxes/counts + host assembly
+
+    def h2d_bytes(self):
+        return int(self.host_maps.numel() * 4 + self.shape_list.size * 8)
+
+    def d2h_bytes(self):
+        return int(self.buf["out_host"].numel())
+
+    def config(self):
+        return {"batch_per_gpu": self.batch, "H": H, "W": W, "boxes_per_step_rank0": self.n_boxes,
+                "l2": "inputs (%.0f MB per GPU) larger than the 126 MB L2; no flush needed"
+                      % (self.batch * self.alg_bytes_per_unit() / 1e6),
+                "timed_region": "device maps -> boxes/scores/counts in pinned host memory"}
+
+
+class DbWorkload(DetWorkload):
+    name = "db"
+    default_batch = 256
+    op_name = "DBPostProcess"
+    cfg = DB_CFG
+    stream_kernel = "db_binarize_kernel"
+    workload = ("DB++ r18 post-process, batch 256 synthetic 736x1280 maps with ~200 text regions each per GPU "
+                "(BASELINE.json configs[1])")
+    cpu_note = ("oracle/db_oracle.py (cv2-python restatement of db_postprocess.cpp + the reference's own "
+                "Clipper): the C++ module needs OpenCV C++ and cannot be built here")
+
+    def host_prepare(self, pool, want_cpu):
+        maps = pool.map(_gen_db, [SEED + self.rank * self.batch + i for i in range(self.batch)], chunksize=4)
+        self.maps = np.stack(maps)[:, None]
+        if not want_cpu:
+            return None
+        imgs = [self.maps[i, 0] for i in range(self.batch)]
+        _, dt = _timed_pool(pool, _cpu_db, imgs, self.cores)
+        return {"value": len(imgs) / dt, "unit": self.unit, "cores": self.cores, "kind": "port",
+                "sample": "%d of this step's 736x1280 maps in %.1f s, multiprocessing.Pool(%d), cv2.setNumThreads(1); %s"
+                          % (len(imgs), dt, self.cores, self.cpu_note)}
+
+    def make_device_maps(self, dev):
+        return self.torch.from_numpy(self.maps).pin_memory().to(dev)
+
+    def device_step(self, L, stream):
+        from pytorchocr_b200 import _lib
+        buf, m = self.buf, self.dev_maps
+        o_box, o_sc, o_cnt, o_st = buf["offs"]
+        base = buf["out_dev"].data_ptr()
+        _lib.check(L.ocrpp_db_postprocess(
+            m.data_ptr(), _lib.F32, self.batch, H, W, m.stride(0), m.stride(2), buf["wh_dev"].data_ptr(),
+            DB_CFG["thresh"], DB_CFG["box_thresh"], DB_CFG["unclip_ratio"], DB_CFG["max_candidates"], self.key[4],
+            base + o_box, base + o_sc, base + o_cnt, base + o_st, None, None,
+            buf["ws"].data_ptr(), buf["ws_bytes"], stream.cuda_stream))
+        buf["out_host"].copy_(buf["out_dev"], non_blocking=True)
+
+
+class ExpandWorkload(DetWorkload):
+    def extra_cfg(self):
+        return {"maps_at_processing_res": True}
+
+    def device_step(self, L, stream):
+        from pytorchocr_b200 import _lib
+        op, buf, m = self.op, self.buf, self.dev_maps
+        _, N, C, h, w, fin, cap, R, arena = self.key
+        _lib.check(op._call_lib(L, m, N, C, h, w, fin, op.scale, buf, cap, R, arena, None, None, stream))
+        buf["out_host"].copy_(buf["out_dev"], non_blocking=True)
+
+
+class PseWorkload(ExpandWorkload):
+    name = "pse"
+    default_batch = 16
+    channels = 7
+    op_name = "PSEPostProcess"
+    cfg = PSE_CFG
+    stream_kernel = "ex_binarize_kernel"
+    workload = ("PSENet r50 progressive scale expansion, 7 kernel maps at processing resolution 736x1280, "
+                "~200 text regions each, batch 16 per GPU = 128 over 8 B200 (BASELINE.json configs[2])")
+
+    def host_prepare(self, pool, want_cpu):
+        self.scenes = pool.map(_gen_pse_scene, [SEED + self.rank * self.batch + i for i in range(self.batch)])
+        if not want_cpu:
+            return None
+        n = max(self.cores, 8)
+        out, dt = _timed_pool(pool, _cpu_pse, [SEED + i for i in range(n)], self.cores)
+        return {"value": n / dt, "unit": self.unit, "cores": self.cores, "kind": "port",
+                "sample": "%d maps [7,736,1280] from the same generator in %.1f s, multiprocessing.Pool(%d); "
+                          "oracle/pse_oracle.py (C restatement of pse.pyx pinned against the compiled reference + "
+                          "numpy/cv2 generate_box without the reference's O(labels*H*W) scans); mean %.2f s/image/core"
+                          % (n, dt, self.cores, float(np.mean([o[0] for o in out])))}
+
+    def make_device_maps(self, dev):
+        from pytorchocr_b200 import synth
+        return synth.pse_maps_torch(self.scenes, SEED + self.rank, dev)
+
+
+class PanWorkload(ExpandWorkload):
+    name = "pan"
+    default_batch = 128
+    channels = 6
+    op_name = "PANPostProcess"
+    cfg = PAN_CFG
+    stream_kernel = "ex_binarize_kernel"
+    workload = ("PAN++ r18 pixel aggregation with 4-d embeddings, [6,736,1280] maps at processing resolution, "
+                "~200 text regions each, batch 128 per GPU (BASELINE.json configs[3])")
+
+    def host_prepare(self, pool, want_cpu):
+        self.scenes = pool.map(_gen_pan_scene, [SEED + self.rank * self.batch + i for i in range(self.batch)])
+        if not want_cpu:
+            return None
+        n = max(self.cores, 8)
+        out, dt = _timed_pool(pool, _cpu_pan, [SEED + i for i in range(n)], self.cores)
+        return {"value": n / dt, "unit": self.unit, "cores": self.cores, "kind": "port",
+                "sample": "%d maps [6,736,1280] from the same generator in %.1f s, multiprocessing.Pool(%d); "
+                          "oracle/pan_oracle.py (numpy pre-pass + C restatement of pa.pyx pinned against the compiled "
+                          "reference + generate_box without the O(labels*H*W) scans); mean %.2f s/image/core"
+                          % (n, dt, self.cores, float(np.mean([o[0] for o in out])))}
+
+    def make_device_maps(self, dev):
+        from pytorchocr_b200 import synth
+        return synth.pan_maps_torch(self.scenes, SEED + self.rank, dev)
+
+    def alg_bytes_per_unit(self):
+        return 6 * H * W * 4
+
+
+class CtcWorkload(Workload):
+    name = "ctc"
+    unit = "lines/s"
+    metric = "CTC greedy decode text lines/sec (T=80, 6623 classes)"
+    default_batch = 8192
+    stream_kernel = "ctc_argmax_kernel"
+    workload = ("CRNN vgg CTC greedy decode, T=80, 6623 classes, 8192 text lines (17.4 GB) per GPU = 65536 over "
+                "8 B200 (BASELINE.json configs[4])")
+    e2e_lines = 512
+
+    def alg_bytes_per_unit(self):
+        return CTC_T * CTC_C * 4
+
+    def host_prepare(self, pool, want_cpu):
+        import tempfile
+        from pytorchocr_b200 import synth
+        self.dict_path = synth.write_char_dict(os.path.join(tempfile.mkdtemp(), "dict.txt"), CTC_C)
+        if not want_cpu:
+            return None
+        per, n = 128, self.cores * 2
+        out, dt = _timed_pool(pool, _cpu_ctc, [(SEED + i, per, self.dict_path) for i in range(n)], self.cores)
+        inner = sum(o[0] for o in out)
+        return {"value": per * n / (inner / self.cores), "unit": self.unit, "cores": self.cores, "kind": "port",
+                "sample": "%d chunks of %d lines [80,%d,6623] from the same generator, multiprocessing.Pool(%d), decode "
+                          "time only (%.1f s summed); oracle/ctc_oracle.py CTCLabelDecodeNumpy = the reference's numpy "
+                          "argmax + pure-Python collapse loop restated line by line" % (n, per, per, self.cores, inner)}
+
+    def device_prepare(self, dev):
+        import torch
+        from pytorchocr_b200 import synth
+        from pytorchocr_b200.postprocess import build_post_process
+        self.torch, self.dev = torch, dev
+        self.op = build_post_process({"name": "CTCLabelDecode", "character_dict_path": self.dict_path,
+                                      "use_space_char": False, "cuda_speedup": True})
+        B = self.batch
+        self.probs = synth.ctc_probs_torch(SEED + self.rank, CTC_T, B, CTC_C, dev)
+        self.idx = torch.empty(B * CTC_T + B, dtype=torch.int32, device=dev)
+        self.pf = torch.empty(B * CTC_T + B, dtype=torch.float32, device=dev)
+        self.idx_host = torch.empty(B * CTC_T + B, dtype=torch.int32, pin_memory=True)
+        self.conf_host = torch.empty(B, dtype=torch.float32, pin_memory=True)
+        e = min(self.e2e_lines, B)
+        self.host_chunk = torch.empty((CTC_T, e, CTC_C), dtype=torch.float32, pin_memory=True)
+        self.host_chunk.copy_(self.probs[:, :e])
+        self.n_boxes = 0
+        self.op(self.probs[:, :e])
+
+    def device_step(self, L, stream):
+        from pytorchocr_b200 import _lib
+        B, x = self.batch, self.probs
+        _lib.check(L.ocrpp_ctc_greedy(x.data_ptr(), _lib.F32, CTC_T, B, CTC_C, x.stride(0), x.stride(1),
+                                      self.idx.data_ptr(), self.pf.data_ptr(), self.idx.data_ptr() + 4 * B * CTC_T,
+                                      self.pf.data_ptr() + 4 * B * CTC_T, None, stream.cuda_stream))
+        self.idx_host.copy_(self.idx, non_blocking=True)
+        self.conf_host.copy_(self.pf[B * CTC_T:], non_blocking=True)
+
+    def e2e_step(self):
+        d = self.host_chunk.to(self.dev, non_blocking=True)
+        return self.op(d)     # kernels + D2H of ids/lengths/confidences + host string assembly
+
+    e2e_units = property(lambda self: self.host_chunk.shape[1])
+
+    def h2d_bytes(self):
+        return int(self.host_chunk.numel() * 4)
+
+    def d2h_bytes(self):
+        e = self.host_chunk.shape[1]
+        return int((e * CTC_T + e) * 4 + e * 4)
+
+    def config(self):
+        return {"batch_per_gpu": self.batch, "T": CTC_T, "C": CTC_C,
+                "l2": "inputs (%.1f GB per GPU) larger than the 126 MB L2; no flush needed"
+                      % (self.batch * self.alg_bytes_per_unit() / 1e9),
+                "timed_region": "device probabilities -> kept class ids / lengths / confidences in pinned host memory",
+                "e2e_region": "%d-line chunks: pinned host probabilities -> python strings" % self.host_chunk.shape[1]}
+
+
+WORKLOADS = {"db": DbWorkload, "pse": PseWorkload, "pan": PanWorkload, "ctc": CtcWorkload}
+
+
+# ----------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU implementation of the path on the host cores
 # ----------------------------------------------------------------------------------------------
 def run_reference(args):
@@ -122,31 +412,46 @@ def run_reference(args):
         return 0
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    sample = 64 if args.workload == "db" else 0
+    wl = WORKLOADS[args.workload](args, 0, 1)
     with mp.get_context("fork").Pool(cores) as pool:
-        maps = make_db_maps(sample, 20221001, pool)
-        imgs = [maps[i, 0] for i in range(sample)]
-        pool.map(_oracle_one, imgs[:cores])
+        if args.workload == "db":
+            sample = 64
+            items = pool.map(_gen_db, [SEED + i for i in range(sample)], chunksize=4)
+            fn, units = _cpu_db, sample
+            what = "%d maps" % sample
+        elif args.workload in ("pse", "pan"):
+            sample = max(8, cores)
+            items = [SEED + i for i in range(sample)]
+            fn, units = (_cpu_pse if args.workload == "pse" else _cpu_pan), sample
+            what = "%d maps" % sample
+        else:
+            import tempfile
+            from pytorchocr_b200 import synth
+            dict_path = synth.write_char_dict(os.path.join(tempfile.mkdtemp(), "dict.txt"), CTC_C)
+            per, n = 128, cores * 2
+            items = [(SEED + i, per, dict_path) for i in range(n)]
+            fn, units = _cpu_ctc, per * n
+            what = "%d chunks of %d lines" % (n, per)
+        pool.map(fn, items[:cores])
         for _ in range(args.warmup):
-            pool.map(_oracle_one, imgs, chunksize=1)
+            pool.map(fn, items, chunksize=1)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            pool.map(_oracle_one, imgs, chunksize=1)
+            pool.map(fn, items, chunksize=1)
         dt = time.perf_counter() - t0
-    rate = sample * args.steps / dt
+    rate = units * args.steps / dt
     line = {
-        "impl": "reference", "metric": "post-process images/sec @736x1280", "value": rate, "unit": "images/s",
+        "impl": "reference", "metric": wl.metric, "value": rate, "unit": wl.unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DB++ r18 post-process, synthetic 736x1280 maps (BASELINE.json configs[1]); "
-                               "each step = a bounded sample of %d maps on the host cores" % sample,
-                   "batch_per_step": sample, "H": H, "W": W},
-        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": "%d maps x %d steps, multiprocessing.Pool(%d), cv2.setNumThreads(1); "
-                                   "oracle/db_oracle.py (cv2-python restatement of db_postprocess.cpp + the "
-                                   "reference's own Clipper): the C++ module needs OpenCV C++ and cannot be built here"
-                                   % (sample, args.steps, cores)},
-        "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
+        "config": {"workload": wl.workload + "; each step = a bounded sample (%s) on the host cores" % what,
+                   "H": H, "W": W},
+        "cpu_baseline": {"value": rate, "unit": wl.unit, "cores": cores, "kind": "port",
+                         "sample": "%s x %d steps, multiprocessing.Pool(%d), cv2.setNumThreads(1); the oracle port of "
+                                   "the reference's CPU path (oracle/): db_postprocess.cpp needs OpenCV C++ and cannot be "
+                                   "built here, pse.pyx/pa.pyx are restated in C and pinned against the compiled reference"
+                                   % (what, args.steps, cores)},
+        "e2e": {"value": rate, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -160,27 +465,17 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    batch = args.batch
-    cores = os.cpu_count() or 1
+    wl = WORKLOADS[args.workload](args, rank, world)
 
     # ---- host phase (fork pool; CUDA not initialised yet) ----
     import multiprocessing as mp
-    nproc = max(1, cores // max(1, world))
-    cpu_base = None
-    with mp.get_context("fork").Pool(nproc) as pool:
-        maps = make_db_maps(batch, 20221001 + rank * batch, pool)
-        if rank == 0 and world == 1 and not args.no_cpu:
-            rate, n, dt = cpu_db_rate(maps, pool, nproc, repeat=1)
-            cpu_base = {"value": rate, "unit": "images/s", "cores": nproc, "kind": "port",
-                        "sample": "%d of this step's 736x1280 maps in %.1f s, multiprocessing.Pool(%d), "
-                                  "cv2.setNumThreads(1); oracle/db_oracle.py (cv2-python restatement of "
-                                  "db_postprocess.cpp + the reference's own Clipper)" % (n, dt, nproc)}
+    with mp.get_context("fork").Pool(wl.cores) as pool:
+        cpu_base = wl.host_prepare(pool, rank == 0 and world == 1 and not args.no_cpu)
 
     # ---- device phase ----
     import torch
     import torch.distributed as dist
     from pytorchocr_b200 import _lib
-    from pytorchocr_b200.postprocess import build_post_process
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -192,33 +487,13 @@ def run_ours(args):
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
-    op = build_post_process(dict(DB_CFG, name="DBPostProcess", cuda_speedup=True))
-    host_maps = torch.from_numpy(maps).pin_memory()
-    dev_maps = host_maps.to(dev, non_blocking=True)
-    shape_list = np.array([[H, W, 1.0, 1.0]] * batch, np.float64)
+    wl.device_prepare(dev)
     L = _lib.lib()
     stream = torch.cuda.current_stream()
 
-    # one full call through the operator: allocates/caches buffers, checks capacity flags
-    res = op({"maps": dev_maps}, shape_list)
-    n_boxes = int(sum(len(r["points"]) for r in res))
-    key = next(iter(op._cache))
-    buf = op._cache[key]
-    R = key[4]
-    o_box, o_sc, o_cnt, o_st = buf["offs"]
-    base = buf["out_dev"].data_ptr()
-
-    def device_step():
-        _lib.check(L.ocrpp_db_postprocess(
-            dev_maps.data_ptr(), _lib.F32, batch, H, W, dev_maps.stride(0), dev_maps.stride(2),
-            buf["wh_dev"].data_ptr(), DB_CFG["thresh"], DB_CFG["box_thresh"], DB_CFG["unclip_ratio"],
-            DB_CFG["max_candidates"], R, base + o_box, base + o_sc, base + o_cnt, base + o_st, None, None,
-            buf["ws"].data_ptr(), buf["ws_bytes"], stream.cuda_stream))
-        buf["out_host"].copy_(buf["out_dev"], non_blocking=True)   # results -> pinned host
-
-    # ---- device-resident timing: inputs already in HBM (965 MB per GPU >> 126 MB L2) ----
+    # ---- device-resident timing: inputs already in HBM and larger than the 126 MB L2 ----
     for _ in range(args.warmup):
-        device_step()
+        wl.device_step(L, stream)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -229,7 +504,7 @@ def run_ours(args):
     barrier()
     e0.record(stream)
     for _ in range(args.steps):
-        device_step()
+        wl.device_step(L, stream)
     e1.record(stream)
     barrier()
     L.ocrpp_profile_enable(0)
@@ -238,22 +513,17 @@ def run_ours(args):
     calls, phases = _lib.profile_read()
 
     # ---- end-to-end timing through the operator with HOST buffers ----
-    def e2e_step():
-        d = host_maps.to(dev, non_blocking=True)          # H2D of this step's maps from pinned memory
-        return op({"maps": d}, shape_list)                # kernels + D2H of boxes/counts + host assembly
-
-    for _ in range(max(1, args.warmup // 2)):
-        e2e_step()
+    for _ in range(2):
+        wl.e2e_step()
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 5))
     for _ in range(e2e_steps):
-        r = e2e_step()
+        wl.e2e_step()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     sampler.stop()
 
-    # max over ranks
     t = torch.tensor([ms_dev, t_e2e * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -266,35 +536,32 @@ def run_ours(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-        alg_bytes = batch * H * W * 4
+        peak_src = ("MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks
+                    else "fallback 6.65 TB/s (B200_PROFILING.md)")
+        alg_bytes = wl.batch * wl.alg_bytes_per_unit()
         k1_ms = phases[0][1] / max(1, calls) if phases else None
         achieved = alg_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms else None
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "db_binarize_traffic.json")))["dram_bytes_per_launch"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[wl.name]["dram_bytes_per_launch"]
         except Exception:
             pass
-        value = world * batch * args.steps / (ms_dev_max * 1e-3)
+        value = world * wl.batch * args.steps / (ms_dev_max * 1e-3)
+        e2e_units = getattr(wl, "e2e_units", wl.batch)
+        cfg = {"workload": wl.workload}
+        cfg.update(wl.config())
         line = {
-            "metric": "post-process images/sec @736x1280", "value": value, "unit": "images/s",
+            "metric": wl.metric, "value": value, "unit": wl.unit,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev_max / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "DB++ r18 post-process, batch 256 synthetic 736x1280 maps with ~200 text regions "
-                                   "each per GPU (BASELINE.json configs[1])",
-                       "batch_per_gpu": batch, "H": H, "W": W, "boxes_per_step_rank0": n_boxes,
-                       "l2": "inputs (%.0f MB per GPU) larger than the 126 MB L2; no flush needed" % (alg_bytes / 1e6),
-                       "timed_region": "device maps -> boxes/scores/counts in pinned host memory"},
-            "roofline": {"bound": "hbm", "kernel": "db_binarize_kernel", "achieved": achieved, "peak": peak,
+            "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": cfg,
+            "roofline": {"bound": "hbm", "kernel": wl.stream_kernel, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_ms": k1_ms,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k1_ms,
                          "whole_step_frac": alg_bytes / (ms_dev_max / args.steps * 1e-3) / 1e9 / peak},
             "phases_ms": {nm: ms / max(1, calls) for nm, ms in phases},
-            "e2e": {"value": world * batch * e2e_steps / (ms_e2e_max * 1e-3), "unit": "images/s",
-                    "h2d_bytes_per_step": int(host_maps.numel() * 4 + shape_list.shape[0] * 8),
-                    "d2h_bytes_per_step": int(buf["out_host"].numel()), "steps": e2e_steps},
+            "e2e": {"value": world * e2e_units * e2e_steps / (ms_e2e_max * 1e-3), "unit": wl.unit,
+                    "h2d_bytes_per_step": wl.h2d_bytes(), "d2h_bytes_per_step": wl.d2h_bytes(), "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
@@ -312,8 +579,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="db", choices=["db"])
-    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--workload", default="db", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="units per GPU per step (0 = the workload's default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -323,7 +590,8 @@ def main():
     if args.gpus > 1 and world == 1:
         # not launched by torchrun: re-exec one rank per GPU on this node
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
-               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000),
+               os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
     return run_ours(args)
 

@@ -215,6 +215,7 @@ extern "C" int ocrpp_ctc_greedy(const void* probs_dev, int dtype, int T, int B, 
   const long long rows = (long long)T * B;
   const long long blocks = (rows * 32 + kCtcThreads - 1) / kCtcThreads;
   OCRPP_CHECK_ARG(blocks < (1ll << 31), "ctc: too many rows");
+  ProfileScope prof(s);
   if (dtype == OCRPP_F32)
     ctc_argmax_kernel<float><<<(unsigned)blocks, kCtcThreads, 0, s>>>(
         (const float*)probs_dev, T, B, C, stride_t, stride_b, idx_out_dev, prob_out_dev, raw_idx_out_dev);
@@ -222,7 +223,9 @@ extern "C" int ocrpp_ctc_greedy(const void* probs_dev, int dtype, int T, int B, 
     ctc_argmax_kernel<__half><<<(unsigned)blocks, kCtcThreads, 0, s>>>(
         (const __half*)probs_dev, T, B, C, stride_t, stride_b, idx_out_dev, prob_out_dev, raw_idx_out_dev);
   OCRPP_LAUNCHED();
+  prof.mark("ctc_argmax");
   ctc_collapse_kernel<<<(B * 32 + 127) / 128, 128, 0, s>>>(T, B, idx_out_dev, prob_out_dev, len_out_dev, conf_out_dev);
   OCRPP_LAUNCHED();
+  prof.mark("ctc_collapse");
   return OCRPP_OK;
 }

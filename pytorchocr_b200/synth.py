@@ -106,11 +106,9 @@ def db_batch(n, seed=BASE_SEED, H=736, W=1280, n_regions=200, dtype=np.float32):
     return out
 
 
-def pse_maps(seed, H=736, W=1280, n_regions=200, K=7, hh_rng=(5, 10), hw_rng=(15, 37), n_abs=None):
-    """PSENet logits [K,H,W] at processing resolution (SURVEY §8(d) Cfg 3 generator): channel k is
-    the rectangle shrunk to (1 - 0.1k); +4 inside / -4 outside + N(0,0.5); 20% of regions placed
-    as touching pairs (merged text masks => contested expansion); 5% with text logit +1
-    (score 0.73 => rejected); 5% whose smallest kernel is < 16 px (seed dropped)."""
+def pse_scene(seed, H=736, W=1280, n_regions=200, K=7, hh_rng=(5, 10), hw_rng=(15, 37), n_abs=None):
+    """Geometry of one PSENet scene: masks u8 [K,H,W] (channel k = rectangles shrunk to 1 - 0.1k),
+    `weak` u8 [H,W] (regions whose text logit is only +1) and the rng to continue with."""
     rng = np.random.default_rng(seed)
     scale = (H * W) / float(736 * 1280)
     n = n_regions if scale >= 1 else max(2, int(round(n_regions * scale)))
@@ -140,6 +138,15 @@ def pse_maps(seed, H=736, W=1280, n_regions=200, K=7, hh_rng=(5, 10), hw_rng=(15
                 _fill_rect(masks[k], g, 1, s)
             if 0.20 <= u < 0.25:
                 _fill_rect(weak, g, 1)
+    return masks, weak, rng
+
+
+def pse_maps(seed, H=736, W=1280, n_regions=200, K=7, hh_rng=(5, 10), hw_rng=(15, 37), n_abs=None):
+    """PSENet logits [K,H,W] at processing resolution (SURVEY §8(d) Cfg 3 generator): channel k is
+    the rectangle shrunk to (1 - 0.1k); +4 inside / -4 outside + N(0,0.5); 20% of regions placed
+    as touching pairs (merged text masks => contested expansion); 5% with text logit +1
+    (score 0.73 => rejected); 5% whose smallest kernel is < 16 px (seed dropped)."""
+    masks, weak, rng = pse_scene(seed, H, W, n_regions, K, hh_rng, hw_rng, n_abs)
     logits = np.where(masks > 0, 4.0, -4.0).astype(np.float32)
     logits += rng.normal(0.0, 0.5, size=logits.shape).astype(np.float32)
     # low text score regions: logit +1 on the text channel only
@@ -148,11 +155,25 @@ def pse_maps(seed, H=736, W=1280, n_regions=200, K=7, hh_rng=(5, 10), hw_rng=(15
     return logits
 
 
-def pan_maps(seed, H=736, W=1280, n_regions=200, hh_rng=(5, 10), hw_rng=(15, 37), n_abs=None):
-    """PAN++ maps [6,H,W] (SURVEY §8(d) Cfg 4 generator): ch0 text logit, ch1 kernel logit
-    (half-sizes x0.5), ch2-5 embedding = per-instance centre (pairwise distance >= 6) + N(0,0.25);
-    no pixel within 0.05 of the distance-3 gate; 10% of touching pairs carry a 1-px kernel blob
-    next to a >= 1025-px kernel so that the area-ratio flag and the embedding gate fire."""
+def pse_maps_torch(scenes, seed, device):
+    """Same distribution as pse_maps for a batch of scenes [(masks, weak), ...], with the noise drawn
+    on `device` (bench inputs: 26 MB of normals per image are too slow to draw on the host)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    masks = torch.from_numpy(np.stack([sc[0] for sc in scenes])).to(device)
+    weak = torch.from_numpy(np.stack([sc[1] for sc in scenes])).to(device)
+    logits = torch.where(masks > 0, 4.0, -4.0).to(torch.float32)
+    logits += 0.5 * torch.randn(logits.shape, generator=g, device=device, dtype=torch.float32)
+    sel = (weak > 0) & (masks[:, 0] > 0)
+    t = logits[:, 0]
+    t[sel] = (1.0 + 0.1 * torch.randn(t.shape, generator=g, device=device, dtype=torch.float32))[sel]
+    return logits
+
+
+def pan_scene(seed, H=736, W=1280, n_regions=200, hh_rng=(5, 10), hw_rng=(15, 37), n_abs=None):
+    """Geometry of one PAN++ scene: text u8 [H,W], kernel u8 [H,W], instance id i32 [H,W], embedding
+    centres f32 [n_inst+1,4] and the rng to continue with."""
     rng = np.random.default_rng(seed)
     scale = (H * W) / float(736 * 1280)
     n = n_regions if scale >= 1 else max(2, int(round(n_regions * scale)))
@@ -198,19 +219,49 @@ def pan_maps(seed, H=736, W=1280, n_regions=200, hh_rng=(5, 10), hw_rng=(15, 37)
             else:
                 _fill_rect(kern, g, 1, 0.5)
     kern &= text
+    return text, kern, inst, np.stack(centres), rng
+
+
+def pan_maps(seed, H=736, W=1280, n_regions=200, hh_rng=(5, 10), hw_rng=(15, 37), n_abs=None):
+    """PAN++ maps [6,H,W] (SURVEY §8(d) Cfg 4 generator): ch0 text logit, ch1 kernel logit
+    (half-sizes x0.5), ch2-5 embedding = per-instance centre (pairwise distance >= 6) + N(0,0.25);
+    no pixel within 0.2 of the distance-3 gate; a few long text regions per image hold a >= 3073-px
+    kernel next to a 3-px kernel blob so that the area-ratio flag and the embedding gate fire."""
+    text, kern, inst, C, rng = pan_scene(seed, H, W, n_regions, hh_rng, hw_rng, n_abs)
     out = np.empty((6, H, W), np.float32)
     out[0] = np.where(text > 0, 4.0, -4.0) + rng.normal(0, 0.5, (H, W))
     out[1] = np.where(kern > 0, 4.0, -4.0) + rng.normal(0, 0.5, (H, W))
-    C = np.stack(centres)  # [n_inst+1, 4]
     emb = C[inst].transpose(2, 0, 1) + rng.normal(0, 0.25, (4, H, W)).astype(np.float32)
-    # enforce the gate margin: push pixels whose distance to ANY centre is within 0.05 of 3 back
-    # onto their own centre (cheap and sufficient: gates compare against kernel means ~ centres)
+    # enforce the gate margin: push pixels whose distance to their own centre is within 0.2 of 3 back
+    # onto the centre (cheap and sufficient: gates compare against kernel means ~ centres)
     flat = emb.reshape(4, -1).T
     d_own = np.linalg.norm(flat - C[inst.reshape(-1)], axis=1)
     bad = np.abs(d_own - 3.0) <= 0.2
     flat[bad] = C[inst.reshape(-1)][bad]
     out[2:] = flat.T.reshape(4, H, W)
     return out.astype(np.float32)
+
+
+def pan_maps_torch(scenes, seed, device):
+    """Same distribution as pan_maps for a batch of scenes [(text, kern, inst, centres), ...] with the
+    noise drawn on `device` (bench inputs)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    N = len(scenes)
+    H, W = scenes[0][0].shape
+    out = torch.empty((N, 6, H, W), dtype=torch.float32, device=device)
+    for i, (text, kern, inst, C) in enumerate(scenes):
+        t = torch.from_numpy(text).to(device) > 0
+        k = torch.from_numpy(kern).to(device) > 0
+        out[i, 0] = torch.where(t, 4.0, -4.0) + 0.5 * torch.randn((H, W), generator=g, device=device)
+        out[i, 1] = torch.where(k, 4.0, -4.0) + 0.5 * torch.randn((H, W), generator=g, device=device)
+        cen = torch.from_numpy(C).to(device)[torch.from_numpy(inst).to(device).long()]      # [H,W,4]
+        noise = 0.25 * torch.randn((H, W, 4), generator=g, device=device)
+        bad = (noise.norm(dim=2) - 3.0).abs() <= 0.2
+        noise[bad] = 0.0
+        out[i, 2:] = (cen + noise).permute(2, 0, 1)
+    return out
 
 
 def char_dict(n=6623):
