@@ -1,0 +1,170 @@
+"""Generates tests/golden/*.npz by running the REFERENCE ITSELF in the authoring container.
+
+    python tests/golden/make_golden.py          (needs /root/reference and oracle/_ref built)
+
+What runs unmodified from /root/reference (imported in place, nothing is copied):
+  * pytocr.postprocess.pse_postprocess.PSEPostProcess    (whole operator incl. generate_box)
+  * pytocr.postprocess.pan_postprocess.PANPostProcess
+  * pytocr.postprocess.rec_postprocess.CTCLabelDecode
+  * pytocr.postprocess.db_postprocess.DBPostProcess.__call__ (cpp_speedup=True wrapper semantics)
+  * the compiled pse.pyx / pa.pyx (oracle/_ref, built unmodified by oracle/build_ref.py) behind the
+    package names the operators import them from
+What is stubbed and why: `pyclipper` / `shapely` (absent; only the non-cpp_speedup DB
+branch uses them), and `pytocr.postprocess.db_postprocess_fast.cpp_boxes_from_bitmap` (the C++ module
+needs OpenCV C++ headers, absent) -> oracle/db_oracle.boxes_from_bitmap, the cv2-python restatement
+that calls the reference's own compiled Clipper. So the DB fixture pins the operator wrapper, not the
+C++ box extraction (DB parity stays "unpinned upstream", see oracle/__init__.py).
+
+The fixtures are small (inputs + outputs, a few hundred KB) and are checked by
+tests/test_golden.py against the oracle (CPU) and against the CUDA path (-m gpu).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("OCR_REFERENCE_ROOT", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+
+
+def import_reference():
+    import torch  # noqa: F401
+    for name in ("pyclipper", "shapely", "shapely.geometry"):
+        sys.modules[name] = types.ModuleType(name)
+    sys.modules["shapely.geometry"].Polygon = object
+    import pa as pa_mod
+    import pse as pse_mod
+    from oracle import db_oracle
+
+    def cpp_boxes_from_bitmap(pred, bitmap, box_thresh, det_db_unclip_ratio, src_w, src_h, use_padding_resize=False):
+        # same signature and uint8 cast as db_postprocess_fast/__init__.py:10-22
+        return db_oracle.boxes_from_bitmap(pred, bitmap.astype(np.uint8), box_thresh, det_db_unclip_ratio,
+                                           src_w, src_h, use_padding_resize)
+    for pkg, attr, fn in (("pytocr.postprocess.pse_postprocess_fast", "pse", pse_mod.pse),
+                          ("pytocr.postprocess.pan_postprocess_fast", "pa", pa_mod.pa),
+                          ("pytocr.postprocess.db_postprocess_fast", "cpp_boxes_from_bitmap",
+                           cpp_boxes_from_bitmap)):
+        m = types.ModuleType(pkg)
+        setattr(m, attr, fn)
+        sys.modules[pkg] = m
+    sys.path.insert(0, REF)
+    import warnings
+    warnings.filterwarnings("ignore")
+    from pytocr.postprocess import build_post_process
+    return build_post_process
+
+
+def main():
+    import torch
+    from pytorchocr_b200 import synth
+    build = import_reference()
+    out = {}
+
+    # ---- PSE: API-faithful 1/4-resolution head output, the three scales ----
+    # (maps are stored as float16 and the reference runs on the up-cast values: exact round trip)
+    h, w = 72, 120
+    maps = np.stack([synth.pse_maps(7 + i, h, w, n_abs=40, hh_rng=(3, 5), hw_rng=(6, 10)) for i in range(2)])
+    maps = maps.astype(np.float16).astype(np.float32)
+    sl = np.array([[4 * h, 4 * w, 1.0, 1.0], [432, 600, 1.0 / 1.5, 1.0 / 1.25]], np.float64)
+    out["pse_maps"], out["pse_shape"] = maps.astype(np.float16), sl
+    for scale in (1, 2, 4):
+        op = build({"name": "PSEPostProcess", "thresh": 0, "box_thresh": 0.85, "min_area": 16, "scale": scale})
+        res = op({"maps": torch.from_numpy(maps)}, sl)
+        for n, r in enumerate(res):
+            out["pse_s%d_points_%d" % (scale, n)] = np.asarray(r["points"], np.int16).reshape(-1, 4, 2)
+            out["pse_s%d_scores_%d" % (scale, n)] = np.asarray(r["scores"], np.float32)
+
+    # ---- PAN: shipped config (scale 4) and full-res processing (scale 1) ----
+    maps = np.stack([synth.pan_maps(11 + i, h, w, n_abs=40, hh_rng=(3, 5), hw_rng=(6, 10)) for i in range(2)])
+    maps = maps.astype(np.float16).astype(np.float32)
+    out["pan_maps"], out["pan_shape"] = maps.astype(np.float16), sl
+    for scale in (1, 2, 4):
+        op = build({"name": "PANPostProcess", "thresh": 0, "box_thresh": 0.85, "min_area": 16,
+                    "min_kernel_area": 2.6, "scale": scale})
+        res = op({"maps": torch.from_numpy(maps)}, sl)
+        for n, r in enumerate(res):
+            out["pan_s%d_points_%d" % (scale, n)] = np.asarray(r["points"], np.int16).reshape(-1, 4, 2)
+            out["pan_s%d_scores_%d" % (scale, n)] = np.asarray(r["scores"], np.float32)
+
+    # ---- CTC: [T,B,C] softmax rows; the reference's real dictionary is data under /root/reference and is
+    #      not copied, so the fixture stores the decoded CLASS IDS (via a private-use dictionary) ----
+    T, B, Cn = 25, 16, 97
+    probs, _ = synth.ctc_probs_numpy(3, T, B, Cn)
+    probs[:, 3] = 0.0
+    probs[:, 3, 0] = 1.0            # an all-blank line -> ("", nan)
+    dict_path = os.path.join(HERE, "_dict_tmp.txt")
+    synth.write_char_dict(dict_path, Cn - 1)
+    op = build({"name": "CTCLabelDecode", "character_dict_path": dict_path, "use_space_char": False})
+    res = op(torch.from_numpy(probs))
+    os.remove(dict_path)
+    out["ctc_probs"] = probs
+    out["ctc_text"] = np.array([r[0] for r in res])
+    out["ctc_conf"] = np.array([r[1] for r in res], np.float32)
+
+    # ---- DB: operator wrapper semantics (cpp_speedup=True; box extraction = the restatement) ----
+    Hd, Wd = 160, 256
+    maps = synth.db_batch(2, seed=5, H=Hd, W=Wd)
+    sl_db = np.array([[Hd, Wd, 1.0, 1.0], [240, 320, 1.5, 1.25]], np.float64)
+    op = build({"name": "DBPostProcess", "thresh": 0.3, "box_thresh": 0.5, "max_candidates": 1000,
+                "unclip_ratio": 1.7, "score_mode": "poly", "cpp_speedup": True})
+    res = op({"maps": torch.from_numpy(maps)}, sl_db)
+    out["db_maps"], out["db_shape"] = maps.astype(np.float16), sl_db      # fp16 storage: exact round trip below
+    res = op({"maps": torch.from_numpy(out["db_maps"].astype(np.float32))}, sl_db)
+    for n, r in enumerate(res):
+        out["db_points_%d" % n] = np.asarray(r["points"], np.int16).reshape(-1, 4, 2)
+        out["db_scores_%d" % n] = np.asarray(r["scores"], np.float32)
+
+    # ---- the compiled Cython modules themselves on adversarial fields: label maps are the bit-exact gate ----
+    import cv2
+    import pa as pa_mod
+    import pse as pse_mod
+    rng = np.random.default_rng(4242)
+    for i in range(4):
+        K = [7, 4, 7, 3][i]
+        base = cv2.GaussianBlur(rng.random((72, 96)).astype(np.float32), (0, 0), [1.0, 2.0, 0.6, 1.5][i])
+        qs = np.quantile(base, np.linspace(0.35, 0.8, K))
+        kernels = np.stack([(base > q) for q in qs])
+        if i % 2:   # non-nested: independent random masks inside the text mask
+            kernels = (rng.random((K, 72, 96)) > 0.45) & kernels[0]
+        kernels = kernels.astype(np.uint8)
+        out["exp_pse_kernels_%d" % i] = np.packbits(kernels, axis=None)
+        out["exp_pse_shape_%d" % i] = np.array(kernels.shape)
+        for ma in (0, 5):
+            out["exp_pse_label_%d_ma%d" % (i, ma)] = pse_mod.pse(kernels.copy(), float(ma)).astype(np.int16)
+    for i in range(4):
+        Hh, Ww = 96, 128
+        if i < 2:
+            base = cv2.GaussianBlur(rng.random((Hh, Ww)).astype(np.float32), (0, 0), 2.0)
+            text = base > np.quantile(base, 0.35)
+            kern = (rng.random((Hh, Ww)) > 0.6) & text
+        else:       # one text component with a large, a 1-px and a medium kernel: ratio flags + gate
+            text = np.zeros((Hh, Ww), bool)
+            text[4:60, 4:120] = True
+            text[70:90, 10:100] = True
+            kern = np.zeros((Hh, Ww), bool)
+            kern[6:40, 6:60] = True
+            kern[50, 100] = True
+            kern[52:55, 70:74] = True
+            kern[75:85, 20:60] = True
+        inst = rng.integers(0, 4, (Hh, Ww)) if i < 2 else (np.arange(Ww)[None, :] >= 64) + 2 * (np.arange(Hh)[:, None] >= 44)
+        centres = np.array([[0, 0, 0, 0], [6, 0, 0, 0], [0, 6, 0, 0], [0, 0, 6, 0]], np.float32)
+        emb = (centres[inst].transpose(2, 0, 1) + rng.normal(0, 0.25, (4, Hh, Ww))).astype(np.float16).astype(np.float32)
+        kernels = np.stack([text, kern & text]).astype(np.uint8)
+        emb_m = emb * text[None].astype(np.float32)
+        out["exp_pa_kernels_%d" % i] = np.packbits(kernels, axis=None)
+        out["exp_pa_emb_%d" % i] = emb.astype(np.float16)
+        for ma in (0.0, 2.6):
+            lab = pa_mod.pa(kernels.copy(), emb_m.copy(), ma)
+            out["exp_pa_label_%d_ma%d" % (i, int(ma))] = lab.astype(np.int16)
+
+    np.savez_compressed(os.path.join(HERE, "reference_outputs.npz"), **out)
+    print("wrote", os.path.join(HERE, "reference_outputs.npz"),
+          {k: v.shape for k, v in out.items() if "points" in k})
+
+
+if __name__ == "__main__":
+    main()
