@@ -13,13 +13,14 @@
 //   fill(outer C)   = C + everything C encloses + "stair" pixels of the 4-connected fillPoly boundary
 //   fill(hole C,h)  = h + islands in h + ring + stair pixels
 //
-// Data layout: the map is read ONCE at full HBM rate into a 1-bit/pixel mask (db_binarize_kernel);
-// everything after works on horizontal RUNS of equal bits (a few thousand per image, L2 resident):
+// Data layout: the map is read ONCE at full HBM rate (db_scan_kernel) into a 1-bit/pixel mask, the
+// table of horizontal RUNS of equal bits and the pixel sum of every run; everything after works on
+// those runs (a few thousand per image, L2 resident):
 // run union-find for both polarities, per-component reductions keyed by the root run, a parent tree
 // between foreground components and holes, per-component row extents -> convex hull -> min-area
 // rectangle -> unclip -> rectangle -> rescale. Scores are accumulated in 32.32 fixed point (exact for
 // probabilities >= 2^-9, order independent => deterministic). Algorithmic bytes per image:
-// H*W*sizeof(elem), the probability map, read once by db_binarize_kernel.
+// H*W*sizeof(elem), the probability map, read once by db_scan_kernel.
 #include "common.cuh"
 #include "dev_common.cuh"
 #include "dev_geom.cuh"
@@ -38,10 +39,13 @@ struct DbParams {
   const void* maps;
   long long stride_n, stride_h;
   const int32_t* src_wh;
-  int N, H, W, Wd, R, maxc;
+  int N, H, W, Wd, R, maxc, cap, epl;
   float thresh, box_thresh, unclip_ratio;
   // per-image workspace (index with n * count)
-  uint32_t* bits;        // [H*Wd]
+  uint32_t* bits;        // [H*Wd] lane-major bit mask (see db_scan_kernel)
+  unsigned long long* scum;  // [H*(cap+1)] per-row run starts: x << 48 | cumulative row sum before x (2^-23 units)
+  int32_t* srow_cnt;     // [H] runs in the row | first pixel bit << 31
+  long long* run_sum;    // [R] pixel sum of every run (32.32 fixed point)
   int32_t* rowptr;       // [H+1]
   uint16_t *run_xs, *run_xe, *run_yf;  // [R]
   int32_t* par;          // [R]
@@ -79,179 +83,260 @@ __device__ __forceinline__ float load_px(const void* maps, long long off) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: threshold -> bit mask. One warp per image row; 128-bit loads, nibble/byte gather by shuffles.
+// K1: the ONE pass over the probability map. One warp per image row, kEpl pixels per lane per group
+// (128-bit loads). Per group of 32*kEpl pixels it produces, from kEpl ballots:
+//   * the 1-bit mask, stored "lane-major": word g*kEpl + k, bit l  <->  pixel x = g*32*kEpl + l*kEpl + k
+//   * the run boundaries of the row (both polarities): transitions are XORs of the ballot words
+//   * the running sum of the row in 2^-23 fixed point (probabilities are in [0,1], checked): one
+//     32-bit warp prefix scan per group; every run start stores the cumulative sum BEFORE it, so the
+//     sum over any run is the difference of two adjacent entries and no later kernel re-reads pixels
+// into a per-row segment (one 64-bit entry per run: x << 48 | cumulative sum) of fixed capacity (row_cap runs; overflow is flagged and the caller retries).
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-struct PxVec;
-template <>
-struct PxVec<float> {
-  static constexpr int kElems = 4;
-  __device__ static __forceinline__ unsigned bits(const uint4& u, float th, bool& bad) {
-    const float a = __uint_as_float(u.x), b = __uint_as_float(u.y), c = __uint_as_float(u.z), d = __uint_as_float(u.w);
-    bad |= !(fabsf(a) <= 1024.f) | !(fabsf(b) <= 1024.f) | !(fabsf(c) <= 1024.f) | !(fabsf(d) <= 1024.f);
-    return (a > th ? 1u : 0u) | (b > th ? 2u : 0u) | (c > th ? 4u : 0u) | (d > th ? 8u : 0u);
-  }
-};
-template <>
-struct PxVec<__half> {
-  static constexpr int kElems = 8;
-  __device__ static __forceinline__ unsigned bits(const uint4& u, float th, bool& bad) {
-    const float f[8] = {h2f_lo(u.x), h2f_hi(u.x), h2f_lo(u.y), h2f_hi(u.y), h2f_lo(u.z), h2f_hi(u.z), h2f_lo(u.w), h2f_hi(u.w)};
-    unsigned r = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      bad |= !(fabsf(f[k]) <= 1024.f);
-      r |= (f[k] > th ? 1u : 0u) << k;
-    }
-    return r;
-  }
-};
-
 constexpr int kBinWarps = 8;
+constexpr float kFix23 = 8388608.f;   // 2^23: a 256-pixel group of ones still fits 32 bits
 
-template <typename T, bool kVec>
-__global__ void __launch_bounds__(kBinWarps * 32) db_binarize_kernel(DbParams p) {
+template <typename T, int kEpl>
+struct RowLoader;
+template <>
+struct RowLoader<float, 4> {
+  __device__ static __forceinline__ void load(const float* row, int x, int W, float* v) {
+    const uint4 u = x < W ? ldg_stream_u4(row + x) : make_uint4(0, 0, 0, 0);
+    v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+  }
+};
+template <>
+struct RowLoader<__half, 8> {
+  __device__ static __forceinline__ void load(const __half* row, int x, int W, float* v) {
+    const uint4 u = x < W ? ldg_stream_u4(row + x) : make_uint4(0, 0, 0, 0);
+    v[0] = h2f_lo(u.x); v[1] = h2f_hi(u.x); v[2] = h2f_lo(u.y); v[3] = h2f_hi(u.y);
+    v[4] = h2f_lo(u.z); v[5] = h2f_hi(u.z); v[6] = h2f_lo(u.w); v[7] = h2f_hi(u.w);
+  }
+};
+template <typename T>
+struct RowLoader<T, 1> {  // unaligned / odd-width fallback: one pixel per lane
+  __device__ static __forceinline__ void load(const T* row, int x, int W, float* v) {
+    v[0] = x < W ? load_scalar<T>(row + x) : 0.f;
+  }
+};
+
+// one group of 32*kEpl pixels; kFull = every pixel of the group is inside the row
+template <int kEpl, bool kFull>
+__device__ __forceinline__ void db_scan_group(const DbParams& p, const float* v, int xg, int lane,
+                                              unsigned long long* sc, uint32_t* out,
+                                              unsigned long long& carry, unsigned& carry_bit, int& cnt,
+                                              unsigned& first_bit, unsigned& worst) {
+  constexpr int PPG = 32 * kEpl;
+  const int x = xg + lane * kEpl;
+  unsigned m[kEpl];    // ballot of pixel k of every lane
+  unsigned pre[kEpl];  // lane-local inclusive prefix of the fixed-point values
+  unsigned run = 0;
+#pragma unroll
+  for (int k = 0; k < kEpl; ++k) {
+    const float f = v[k];
+    const bool valid = kFull || x + k < p.W;
+    m[k] = __ballot_sync(0xffffffffu, valid && f > p.thresh);
+    // f in [0,1]: the mantissa of f + 1.0f is round(f * 2^23); anything else (negative, > 1, NaN, Inf)
+    // gives u > 2^23 and is reported through `worst`
+    unsigned u = __float_as_uint(f + 1.0f) - 0x3f800000u;
+    if (!kFull) u = valid ? u : 0u;
+    worst = max(worst, u);
+    run += u;
+    pre[k] = run;
+  }
+  unsigned inc = run;  // warp inclusive scan of the lane totals (<= 32 * kEpl * 2^23 <= 2^31)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  const unsigned excl = inc - run;
+  const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
+  if (xg == 0) first_bit = m[0] & 1u;
+  // transitions: pixel k differs from pixel k-1 (the previous lane's last pixel for k == 0)
+  unsigned tm[kEpl];
+  unsigned lanes = 0;
+#pragma unroll
+  for (int k = 0; k < kEpl; ++k) {
+    const unsigned prev = k == 0 ? ((m[kEpl - 1] << 1) | carry_bit) : m[k - 1];
+    tm[k] = m[k] ^ prev;
+    if (!kFull) {
+      const int nvalid = (p.W - xg - k + kEpl - 1) / kEpl;  // lanes whose pixel k is inside the row
+      tm[k] &= nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+    }
+    if (k == 0 && xg == 0) tm[k] &= ~1u;  // pixel 0 starts run 0, it is not a transition
+    lanes |= tm[k];
+  }
+  // emission: every lane that holds a transition stores (x << 48 | cumulative sum before x) at its rank
+  if (lanes) {
+    unsigned multi = 0;  // lanes holding more than one transition (rare: runs shorter than kEpl pixels)
+#pragma unroll
+    for (int k = 1; k < kEpl; ++k) {
+      unsigned lower = tm[0];
+#pragma unroll
+      for (int q = 1; q < k; ++q) lower |= tm[q];
+      multi |= tm[k] & lower;
+    }
+    const unsigned long long base = carry + excl;
+    if (multi == 0) {
+      if ((lanes >> lane) & 1u) {
+        const int j = cnt + __popc(lanes & ((1u << lane) - 1u));
+        int k = 0;
+        unsigned before = 0;
+#pragma unroll
+        for (int q = 1; q < kEpl; ++q)
+          if ((tm[q] >> lane) & 1u) {
+            k = q;
+            before = pre[q - 1];
+          }
+        if (j < p.cap) sc[j] = ((unsigned long long)(x + k) << 48) | (base + before);
+      }
+      cnt += __popc(lanes);
+    } else {
+      const unsigned lt = (1u << lane) - 1u;
+      int j = cnt, tot = 0;
+#pragma unroll
+      for (int k = 0; k < kEpl; ++k) {
+        j += __popc(tm[k] & lt);
+        tot += __popc(tm[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < kEpl; ++k) {
+        if ((tm[k] >> lane) & 1u) {
+          if (j < p.cap) sc[j] = ((unsigned long long)(x + k) << 48) | (base + (k > 0 ? pre[k - 1] : 0u));
+          ++j;
+        }
+      }
+      cnt += tot;
+    }
+  }
+  carry += total;
+  carry_bit = m[kEpl - 1] >> 31;
+  if (lane < kEpl) {
+    unsigned w = m[0];
+#pragma unroll
+    for (int k = 1; k < kEpl; ++k) w = lane == k ? m[k] : w;
+    out[(xg / PPG) * kEpl + lane] = w;
+  }
+}
+
+template <typename T, int kEpl>
+__global__ void __launch_bounds__(kBinWarps * 32) db_scan_kernel(DbParams p) {
   const int n = blockIdx.y;
   const int y = blockIdx.x * kBinWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (y >= p.H) return;
   const T* row = reinterpret_cast<const T*>(p.maps) + n * p.stride_n + y * p.stride_h;
   uint32_t* out = p.bits + ((size_t)n * p.H + y) * p.Wd;
-  bool bad = false;
-  if (kVec) {
-    constexpr int EPL = PxVec<T>::kElems;      // pixels per lane per load
-    constexpr int LPW = 32 / EPL;              // lanes per 32-bit word
-    constexpr int PPI = 32 * EPL;              // pixels per warp iteration
-    const uint4* vp = reinterpret_cast<const uint4*>(row);
-    constexpr int U = 4;
-    for (int x0 = 0; x0 < p.W; x0 += PPI * U) {
-      uint4 v[U];
+  const size_t rowid = (size_t)n * p.H + y;
+  unsigned long long* sc = p.scum + rowid * (p.cap + 1);
+  constexpr int PPG = 32 * kEpl;  // pixels per group
+  constexpr int U = kEpl == 1 ? 1 : 4;
+  unsigned worst = 0;
+  unsigned long long carry = 0;   // sum of all pixels of the row before this group (warp-uniform)
+  unsigned carry_bit = 0;         // bit of the pixel just before this group
+  int cnt = 1;                    // run 0 starts at x = 0
+  unsigned first_bit = 0;
+  if (lane == 0) sc[0] = 0ull;   // run 0: x = 0, nothing before it
+  for (int x0 = 0; x0 < p.W; x0 += PPG * U) {
+    float v[U][kEpl];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int x = x0 + u * PPI + lane * EPL;
-        v[u] = x < p.W ? ldg_stream_u4(vp + (x / EPL)) : make_uint4(0, 0, 0, 0);  // W % EPL == 0 on this path
-      }
+    for (int u = 0; u < U; ++u) RowLoader<T, kEpl>::load(row, x0 + u * PPG + lane * kEpl, p.W, v[u]);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int x = x0 + u * PPI + lane * EPL;
-        unsigned b = x < p.W ? PxVec<T>::bits(v[u], p.thresh, bad) : 0u;
-        unsigned w = b << (EPL * (lane % LPW));
-#pragma unroll
-        for (int o = 1; o < LPW; o <<= 1) w |= __shfl_xor_sync(0xffffffffu, w, o);
-        const int wi = (x0 + u * PPI) / 32 + lane / LPW;
-        if ((lane % LPW) == 0 && wi < p.Wd) out[wi] = w;
-      }
-    }
-  } else {
-    for (int x0 = 0; x0 < p.W; x0 += 32) {
-      const int x = x0 + lane;
-      float v = 0.f;
-      if (x < p.W) {
-        v = load_scalar<T>(row + x);
-        bad |= !(fabsf(v) <= 1024.f);
-      }
-      const unsigned w = __ballot_sync(0xffffffffu, x < p.W && v > p.thresh);
-      if (lane == 0) out[x0 >> 5] = w;
+    for (int u = 0; u < U; ++u) {
+      const int xg = x0 + u * PPG;          // first pixel of the group (warp-uniform)
+      if (xg >= p.W) break;
+      if (xg + PPG <= p.W) db_scan_group<kEpl, true>(p, v[u], xg, lane, sc, out, carry, carry_bit, cnt, first_bit, worst);
+      else db_scan_group<kEpl, false>(p, v[u], xg, lane, sc, out, carry, carry_bit, cnt, first_bit, worst);
     }
   }
-  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&p.imgflags[n], OCRPP_IMG_VALUE_OUT_OF_RANGE);
+  if (lane == 0) {
+    p.srow_cnt[rowid] = cnt | (first_bit << 31);
+    if (cnt <= p.cap) sc[cnt] = carry;
+  }
+  if (__any_sync(0xffffffffu, worst > 0x800000u) && lane == 0) atomicOr(&p.imgflags[n], OCRPP_IMG_VALUE_OUT_OF_RANGE);
 }
 
+// pixel (x,y) of the lane-major bit mask written by db_scan_kernel
+struct BitView {
+  const uint32_t* bits;
+  int Wd, epl;
+  __device__ __forceinline__ bool at(int x, int y) const {
+    const int ppg = 32 * epl;
+    const int g = x / ppg, r = x - g * ppg;
+    return (bits[(size_t)y * Wd + g * epl + (r % epl)] >> (r / epl)) & 1u;
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
-// K2: bit mask -> run table (both polarities, raster order). One CTA per image.
+// K2: per-row segments -> dense run table in raster order (both polarities) with per-run pixel sums.
+// kImgCtas CTAs per image: each scans the row counts (cheap) and converts its share of the rows.
 // ------------------------------------------------------------------------------------------------
 constexpr int kRunThreads = 512;
+constexpr int kImgCtas = 8;       // CTAs per image for the run-parallel kernels
 
 __global__ void __launch_bounds__(kRunThreads) db_runs_kernel(DbParams p) {
-  extern __shared__ int s_rowcnt[];  // [H+1]
-  const int n = blockIdx.x;
+  extern __shared__ int s_rowptr[];  // [H+1]
+  const int n = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kRunThreads / 32;
-  const uint32_t* bits = p.bits + (size_t)n * p.H * p.Wd;
+  const int32_t* rc = p.srow_cnt + (size_t)n * p.H;
   int32_t* rowptr = p.rowptr + (size_t)n * (p.H + 1);
-
-  for (int y = warp; y < p.H; y += nw) {
-    int c = 0;
-    for (int k = lane; k < p.Wd; k += 32) {
-      const unsigned w = bits[(size_t)y * p.Wd + k];
-      const unsigned pw = k > 0 ? bits[(size_t)y * p.Wd + k - 1] : 0u;
-      c += __popc(transitions(w, pw, k, p.W));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0) s_rowcnt[y] = c + 1;
-  }
-  __syncthreads();
-  // exclusive scan over rows: each thread owns a contiguous chunk
   const int chunk = (p.H + kRunThreads - 1) / kRunThreads;
   const int y0 = threadIdx.x * chunk, y1 = min(p.H, y0 + chunk);
-  int local = 0;
-  for (int y = y0; y < y1; ++y) local += s_rowcnt[y];
+  int local = 0, over = 0;
+  for (int y = y0; y < y1; ++y) {
+    const int c = rc[y] & 0x7fffffff;
+    over |= c > p.cap;
+    local += c;
+  }
   int total;
   int base = block_exclusive_scan(local, &total);
   for (int y = y0; y < y1; ++y) {
-    const int c = s_rowcnt[y];
-    s_rowcnt[y] = base;
-    base += c;
+    s_rowptr[y] = base;
+    base += rc[y] & 0x7fffffff;
   }
-  if (threadIdx.x == 0) s_rowcnt[p.H] = total;
-  __syncthreads();
-  if (total > p.R) {
-    if (threadIdx.x == 0) {
-      atomicOr(&p.imgflags[n], OCRPP_IMG_RUN_OVERFLOW);
-      p.nruns[n] = 0;
+  if (threadIdx.x == 0) s_rowptr[p.H] = total;
+  over = __syncthreads_or(over);
+  if (over || total > p.R) {
+    if (blockIdx.x == 0) {
+      if (threadIdx.x == 0) {
+        atomicOr(&p.imgflags[n], OCRPP_IMG_RUN_OVERFLOW);
+        p.nruns[n] = 0;
+      }
+      for (int y = threadIdx.x; y <= p.H; y += kRunThreads) rowptr[y] = 0;
     }
-    for (int y = threadIdx.x; y <= p.H; y += kRunThreads) rowptr[y] = 0;
     return;
   }
-  for (int y = threadIdx.x; y <= p.H; y += kRunThreads) rowptr[y] = s_rowcnt[y];
-  if (threadIdx.x == 0) p.nruns[n] = total;
-
+  if (blockIdx.x == 0) {
+    for (int y = threadIdx.x; y <= p.H; y += kRunThreads) rowptr[y] = s_rowptr[y];
+    if (threadIdx.x == 0) p.nruns[n] = total;
+  }
   const size_t ro = (size_t)n * p.R;
-  for (int y = warp; y < p.H; y += nw) {
-    const int rbase = s_rowcnt[y];
-    int carry = 0;  // starts seen in earlier words of this row
-    for (int k0 = 0; k0 < p.Wd; k0 += 32) {
-      const int k = k0 + lane;
-      unsigned w = 0, S = 0;
-      if (k < p.Wd) {
-        w = bits[(size_t)y * p.Wd + k];
-        const unsigned pw = k > 0 ? bits[(size_t)y * p.Wd + k - 1] : 0u;
-        S = transitions(w, pw, k, p.W) | (k == 0 ? 1u : 0u);
-      }
-      const int cnt = __popc(S);
-      int inc = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      int j = carry + inc - cnt;
-      carry += __shfl_sync(0xffffffffu, inc, 31);
-      while (S) {
-        const int b = __ffs(S) - 1;
-        S &= S - 1;
-        const int x = k * 32 + b;
-        const size_t r = ro + rbase + j;
-        const int fg = (w >> b) & 1u;
-        p.run_xs[r] = (uint16_t)x;
-        p.run_yf[r] = (uint16_t)(y | (fg << 15));
-        if (j > 0) p.run_xe[r - 1] = (uint16_t)(x - 1);
-        // per-run / per-component slots
-        p.par[r] = rbase + j;
-        p.area[r] = 0;
-        p.xmin[r] = 0x7fffffff; p.xmax[r] = -1; p.ymax[r] = -1;
-        p.dmin[r] = 0x7fffffff; p.dmax[r] = -0x7fffffff;
-        p.smin[r] = 0x7fffffff; p.smax[r] = -0x7fffffff;
-        p.sum[r] = 0; p.fcnt[r] = 0; p.fsum[r] = 0; p.xcnt[r] = 0; p.xsum[r] = 0;
-        p.cpar[r] = -1; p.cflag[r] = 0; p.rowoff[r] = -1;
-        ++j;
-      }
+  for (int y = blockIdx.x * nw + warp; y < p.H; y += kImgCtas * nw) {
+    const int rbase = s_rowptr[y];
+    const int c = rc[y] & 0x7fffffff;
+    const int first = (unsigned)rc[y] >> 31;
+    const size_t rowid = (size_t)n * p.H + y;
+    const unsigned long long* sc = p.scum + rowid * (p.cap + 1);
+    constexpr unsigned long long kCumMask = (1ull << 48) - 1ull;
+    for (int j = lane; j < c; j += 32) {
+      const size_t r = ro + rbase + j;
+      const int fg = first ^ (j & 1);
+      const unsigned long long e0 = sc[j], e1 = sc[j + 1];   // x << 48 | cumulative sum before x
+      p.run_xs[r] = (uint16_t)(e0 >> 48);
+      p.run_xe[r] = j + 1 < c ? (uint16_t)((e1 >> 48) - 1) : (uint16_t)(p.W - 1);
+      p.run_yf[r] = (uint16_t)(y | (fg << 15));
+      p.run_sum[r] = (long long)(((e1 & kCumMask) - (e0 & kCumMask)) << 9);   // 2^-23 units -> 32.32 fixed point
+      p.par[r] = rbase + j;
+      p.area[r] = 0;
+      p.xmin[r] = 0x7fffffff; p.xmax[r] = -1; p.ymax[r] = -1;
+      p.dmin[r] = 0x7fffffff; p.dmax[r] = -0x7fffffff;
+      p.smin[r] = 0x7fffffff; p.smax[r] = -0x7fffffff;
+      p.sum[r] = 0; p.fcnt[r] = 0; p.fsum[r] = 0; p.xcnt[r] = 0; p.xsum[r] = 0;
+      p.cpar[r] = -1; p.cflag[r] = 0; p.rowoff[r] = -1;
     }
-    if (lane == 0) p.run_xe[ro + s_rowcnt[y + 1] - 1] = (uint16_t)(p.W - 1);
   }
 }
 
-constexpr int kImgCtas = 8;       // CTAs per image for the run-parallel kernels
 constexpr int kRunBlk = 256;
 
 #define FOR_EACH_RUN(r, nr) for (int r = blockIdx.x * kRunBlk + threadIdx.x; r < (nr); r += kImgCtas * kRunBlk)
@@ -296,38 +381,28 @@ __global__ void __launch_bounds__(kRunBlk) db_flatten_kernel(DbParams p) {
   }
 }
 
-// K4b: per-component reductions. One warp per run: pixel sums of foreground runs and of hole runs.
-template <typename T>
+// K4b: per-component reductions from the per-run sums (no pixel is read again). One thread per run.
 __global__ void __launch_bounds__(kRunBlk) db_stats_kernel(DbParams p) {
   const int n = blockIdx.y;
   const int nr = p.nruns[n];
   const size_t ro = (size_t)n * p.R;
   const uint16_t *xs = p.run_xs + ro, *xe = p.run_xe + ro, *yf = p.run_yf + ro;
-  const int lane = threadIdx.x & 31;
-  const int wpb = kRunBlk / 32;
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < nr; r += kImgCtas * wpb) {
+  FOR_EACH_RUN(r, nr) {
     const int root = p.par[ro + r];
     const int y = yf[r] & 0x7fff, fg = yf[r] >> 15;
     if (!fg && (p.cflag[ro + root] & kOutFlag)) continue;
     const int a = xs[r], b = xe[r];
-    long long s = 0;
-    const long long off = n * p.stride_n + y * p.stride_h;
-    for (int x = a + lane; x <= b; x += 32) s += to_fixed(load_px<T>(p.maps, off + x));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
-      const size_t c = ro + root;
-      atomicAdd(&p.area[c], b - a + 1);
-      atomicAdd((unsigned long long*)&p.sum[c], (unsigned long long)s);
-      atomicMin(&p.xmin[c], a);
-      atomicMax(&p.xmax[c], b);
-      atomicMax(&p.ymax[c], y);
-      if (fg) {
-        atomicMin(&p.dmin[c], a - y);
-        atomicMax(&p.dmax[c], b - y);
-        atomicMin(&p.smin[c], a + y);
-        atomicMax(&p.smax[c], b + y);
-      }
+    const size_t c = ro + root;
+    atomicAdd(&p.area[c], b - a + 1);
+    atomicAdd((unsigned long long*)&p.sum[c], (unsigned long long)p.run_sum[ro + r]);
+    atomicMin(&p.xmin[c], a);
+    atomicMax(&p.xmax[c], b);
+    atomicMax(&p.ymax[c], y);
+    if (fg) {
+      atomicMin(&p.dmin[c], a - y);
+      atomicMax(&p.dmax[c], b - y);
+      atomicMin(&p.smin[c], a + y);
+      atomicMax(&p.smax[c], b + y);
     }
   }
 }
@@ -401,9 +476,6 @@ __global__ void __launch_bounds__(kRunBlk) db_fill_kernel(DbParams p) {
   }
 }
 
-__device__ __forceinline__ bool bit_at(const uint32_t* bits, int Wd, int x, int y) {
-  return (bits[(size_t)y * Wd + (x >> 5)] >> (x & 31)) & 1u;
-}
 
 // K7: row extents of every candidate's point set, stair pixels, hole rings. One thread per run.
 template <typename T>
@@ -414,17 +486,17 @@ __global__ void __launch_bounds__(kRunBlk) db_extents_kernel(DbParams p) {
   const int32_t* rowptr = p.rowptr + (size_t)n * (p.H + 1);
   const uint16_t *xs = p.run_xs + ro, *xe = p.run_xe + ro, *yf = p.run_yf + ro;
   const int32_t* par = p.par + ro;
-  const uint32_t* bits = p.bits + (size_t)n * p.H * p.Wd;
+  const BitView bv{p.bits + (size_t)n * p.H * p.Wd, p.Wd, p.epl};
   int32_t* ext_l = p.ext_l + (size_t)n * p.E;
   int32_t* ext_r = p.ext_r + (size_t)n * p.E;
-  const int H = p.H, W = p.W, Wd = p.Wd;
+  const int H = p.H, W = p.W;
   const long long img = n * p.stride_n;
 
   auto px = [&](int x, int y) { return to_fixed(load_px<T>(p.maps, img + y * p.stride_h + x)); };
   // is pixel (x,y) a background pixel of hole region h ?
   auto in_hole = [&](int x, int y, int h) {
     if (x < 0 || y < 0 || x >= W || y >= H) return false;
-    if (bit_at(bits, Wd, x, y)) return false;
+    if (bv.at(x, y)) return false;
     return par[run_at(rowptr, xs, y, x)] == h;
   };
 
@@ -445,7 +517,7 @@ __global__ void __launch_bounds__(kRunBlk) db_extents_kernel(DbParams p) {
     // (a) stair pixel of the OUTER contour of the component to the left: e = (a, y)
     if (a > 0) {
       const int C = par[r - 1];
-      const bool updn = (y > 0 && bit_at(bits, Wd, a, y - 1)) || (y < H - 1 && bit_at(bits, Wd, a, y + 1));
+      const bool updn = (y > 0 && bv.at(a, y - 1)) || (y < H - 1 && bv.at(a, y + 1));
       if (updn) {
         const int pc = p.cpar[ro + C];
         const bool outer_region = pc < 0 ? (p.cflag[ro + root] & kOutFlag) != 0 : (root == pc);
@@ -465,7 +537,7 @@ __global__ void __launch_bounds__(kRunBlk) db_extents_kernel(DbParams p) {
     int cnt = 0;
     long long s = 0;
     // foreground pixel of the enclosing component (islands inside the hole are not ring pixels)
-    auto in_C = [&](int x, int yy) { return bit_at(bits, Wd, x, yy) && par[run_at(rowptr, xs, yy, x)] == C; };
+    auto in_C = [&](int x, int yy) { return bv.at(x, yy) && par[run_at(rowptr, xs, yy, x)] == C; };
     auto ring = [&](int x, int yy) {
       ++cnt;
       s += px(x, yy);
@@ -493,9 +565,9 @@ __global__ void __launch_bounds__(kRunBlk) db_extents_kernel(DbParams p) {
       const int ex = b + 1, ey = y + dy;
       if (dy == -1) {
         // the same e is produced from o' = (b, y-2) with dy=+1 when that qualifies: count it there
-        if (in_hole(b, y - 2, h) && bit_at(bits, Wd, b + 1, y - 2)) continue;
+        if (in_hole(b, y - 2, h) && bv.at(b + 1, y - 2)) continue;
       }
-      if (bit_at(bits, Wd, ex, ey)) {
+      if (bv.at(ex, ey)) {
         // foreground e already belongs to the ring when one of its other neighbours is in h
         if (in_hole(ex + 1, ey, h) || in_hole(ex, ey + dy, h)) continue;
       } else {
@@ -850,6 +922,9 @@ size_t carve(DbParams& p, void* ws) {
   Carver c{(char*)ws, 0};
   const size_t N = p.N, R = p.R, E = p.E;
   p.bits = c.take<uint32_t>(N * p.H * p.Wd);
+  p.scum = c.take<unsigned long long>(N * p.H * (p.cap + 1));
+  p.srow_cnt = c.take<int32_t>(N * p.H);
+  p.run_sum = c.take<long long>(N * R);
   p.rowptr = c.take<int32_t>(N * (p.H + 1));
   p.run_xs = c.take<uint16_t>(N * R);
   p.run_xe = c.take<uint16_t>(N * R);
@@ -888,6 +963,15 @@ size_t carve(DbParams& p, void* ws) {
   return align_up(c.off, 256);
 }
 
+int db_words_per_row(int W) { return 8 * ((W + 255) / 256); }  // covers the 1-, 4- and 8-pixel-per-lane layouts
+
+int db_row_cap(int H, int W, int R) {
+  long long c = 4ll * R / H;
+  if (c < 32) c = 32;
+  if (c > W) c = W;
+  return (int)c;
+}
+
 int resolve_max_runs(int H, int W, int max_runs) {
   const long long worst = (long long)H * (W + 1);
   if (max_runs <= 0 || max_runs > worst) return (int)worst;
@@ -901,8 +985,9 @@ extern "C" size_t ocrpp_db_workspace_bytes(int N, int H, int W, int max_runs) {
   using namespace ocrpp;
   if (N <= 0 || H <= 0 || W <= 0) return 0;
   DbParams p{};
-  p.N = N; p.H = H; p.W = W; p.Wd = (W + 31) / 32;
+  p.N = N; p.H = H; p.W = W; p.Wd = db_words_per_row(W);
   p.R = resolve_max_runs(H, W, max_runs);
+  p.cap = db_row_cap(H, W, p.R);
   p.E = 4 * p.R + 4;
   p.maxc = 1000;  // max_candidates is capped at the reference constant
   return carve(p, nullptr);
@@ -926,8 +1011,9 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
                   "db: null pointer argument");
   DbParams p{};
   p.maps = maps_dev; p.stride_n = stride_n; p.stride_h = stride_h; p.src_wh = src_wh_dev;
-  p.N = N; p.H = H; p.W = W; p.Wd = (W + 31) / 32;
+  p.N = N; p.H = H; p.W = W; p.Wd = db_words_per_row(W);
   p.R = resolve_max_runs(H, W, max_runs);
+  p.cap = db_row_cap(H, W, p.R);
   p.E = 4 * p.R + 4;
   p.maxc = max_candidates;
   p.thresh = thresh; p.box_thresh = box_thresh; p.unclip_ratio = unclip_ratio;
@@ -946,17 +1032,18 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
   (void)esz;
   {
     dim3 grid((H + kBinWarps - 1) / kBinWarps, N);
+    p.epl = vec ? epl : 1;
     if (dtype == OCRPP_F32) {
-      if (vec) db_binarize_kernel<float, true><<<grid, kBinWarps * 32, 0, s>>>(p);
-      else db_binarize_kernel<float, false><<<grid, kBinWarps * 32, 0, s>>>(p);
+      if (vec) db_scan_kernel<float, 4><<<grid, kBinWarps * 32, 0, s>>>(p);
+      else db_scan_kernel<float, 1><<<grid, kBinWarps * 32, 0, s>>>(p);
     } else {
-      if (vec) db_binarize_kernel<__half, true><<<grid, kBinWarps * 32, 0, s>>>(p);
-      else db_binarize_kernel<__half, false><<<grid, kBinWarps * 32, 0, s>>>(p);
+      if (vec) db_scan_kernel<__half, 8><<<grid, kBinWarps * 32, 0, s>>>(p);
+      else db_scan_kernel<__half, 1><<<grid, kBinWarps * 32, 0, s>>>(p);
     }
     OCRPP_LAUNCHED();
-    prof.mark("db_binarize");
+    prof.mark("db_scan");
   }
-  db_runs_kernel<<<N, kRunThreads, sizeof(int) * (H + 1), s>>>(p);
+  db_runs_kernel<<<dim3(kImgCtas, N), kRunThreads, sizeof(int) * (H + 1), s>>>(p);
   OCRPP_LAUNCHED();
   prof.mark("db_runs");
   dim3 rgrid(kImgCtas, N);
@@ -966,8 +1053,7 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
   db_flatten_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
   OCRPP_LAUNCHED();
   prof.mark("db_flatten");
-  if (dtype == OCRPP_F32) db_stats_kernel<float><<<rgrid, kRunBlk, 0, s>>>(p);
-  else db_stats_kernel<__half><<<rgrid, kRunBlk, 0, s>>>(p);
+  db_stats_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
   OCRPP_LAUNCHED();
   prof.mark("db_stats");
   db_tree_kernel<<<rgrid, kRunBlk, 0, s>>>(p);

@@ -130,6 +130,7 @@ def main():
         kernels = np.stack([(base > q) for q in qs])
         if i % 2:   # non-nested: independent random masks inside the text mask
             kernels = (rng.random((K, 72, 96)) > 0.45) & kernels[0]
+            kernels = kernels & kernels[0:1]   # the operator multiplies every kernel by the text mask (:41-42)
         kernels = kernels.astype(np.uint8)
         out["exp_pse_kernels_%d" % i] = np.packbits(kernels, axis=None)
         out["exp_pse_shape_%d" % i] = np.array(kernels.shape)
