@@ -93,7 +93,6 @@ __device__ __forceinline__ float load_px(const void* maps, long long off) {
 // into a per-row segment (one 64-bit entry per run: x << 48 | cumulative sum) of fixed capacity (row_cap runs; overflow is flagged and the caller retries).
 // ------------------------------------------------------------------------------------------------
 constexpr int kBinWarps = 8;
-constexpr float kFix23 = 8388608.f;   // 2^23: a 256-pixel group of ones still fits 32 bits
 
 template <typename T, int kEpl>
 struct RowLoader;
@@ -377,8 +376,132 @@ __global__ void __launch_bounds__(kRunBlk) db_flatten_kernel(DbParams p) {
     const int root = uf_find(par, r);
     par[r] = root;
     const int y = yf[r] & 0x7fff, fg = yf[r] >> 15;
-    if (!fg && (y == 0 || y == p.H - 1 || xs[r] == 0 || xe[r] == p.W - 1)) p.cflag[ro + root] = kOutFlag;
+    if (!fg && (y == 0 || y == p.H - 1 || xs[r] == 0 || xe[r] == p.W - 1) &&
+        !(__ldcg(&p.cflag[ro + root]) & kOutFlag))
+      p.cflag[ro + root] = kOutFlag;   // test first: same-address stores serialise in L2
   }
+}
+
+// K3+K4a fused, shared-memory variant: ONE CTA per image keeps the union-find parent array of the
+// whole image in shared memory (4 bytes per run; used when it fits), so the pointer chasing of link and
+// flatten runs at shared-memory latency instead of L2 latency. Same result as db_link_kernel +
+// db_flatten_kernel (the root of a set is its smallest run index in both).
+constexpr int kCclThreads = 1024;
+
+__device__ __forceinline__ int uf_find_s(volatile int* par, int x) {  // with path halving
+  int q = par[x];
+  while (q != x) {
+    const int g = par[q];
+    if (g != q) par[x] = g;
+    x = q;
+    q = g;
+  }
+  return x;
+}
+
+__device__ __forceinline__ void uf_union_s(int* par, int a, int b) {
+  while (true) {
+    a = uf_find_s(par, a);
+    b = uf_find_s(par, b);
+    if (a == b) return;
+    if (a > b) {
+      const int t = a;
+      a = b;
+      b = t;
+    }
+    const int old = atomicMin(par + b, a);
+    if (old == b) return;
+    b = old;
+  }
+}
+
+__global__ void __launch_bounds__(kCclThreads) db_ccl_kernel(DbParams p) {
+  extern __shared__ int s_par[];  // [R] parents, then [R/32+1] words of per-run / per-root flags
+  const int n = blockIdx.x;
+  const int nr = p.nruns[n];
+  const size_t ro = (size_t)n * p.R;
+  const int32_t* rowptr = p.rowptr + (size_t)n * (p.H + 1);
+  const uint16_t *xs = p.run_xs + ro, *xe = p.run_xe + ro, *yf = p.run_yf + ro;
+  unsigned* s_flag = reinterpret_cast<unsigned*>(s_par + p.R);
+  const int nwords = (nr + 31) / 32;
+  for (int w = threadIdx.x; w < nwords; w += kCclThreads) s_flag[w] = 0u;
+  __syncthreads();
+  // pass 1: every run points at the FIRST overlapping run of the same polarity in the row above (a
+  // smaller index), or at itself. No find, no atomic: most runs of a text map overlap exactly one run.
+  // Runs with further overlaps are flagged for pass 3.
+  for (int r = threadIdx.x; r < nr; r += kCclThreads) {
+    const int y = yf[r] & 0x7fff, fg = yf[r] >> 15;
+    int first = r;
+    if (y > 0) {
+      const int lo = (int)xs[r] - fg, hi = (int)xe[r] + fg;
+      int l = rowptr[y - 1], h = rowptr[y];
+      const int b = h;
+      while (l < h) {
+        const int m = (l + h) >> 1;
+        if ((int)xe[m] < lo) l = m + 1; else h = m;
+      }
+      bool more = false;
+      for (int q = l; q < b && (int)xs[q] <= hi; ++q)
+        if ((yf[q] >> 15) == fg) {
+          if (first == r) first = q;
+          else more = true;
+        }
+      if (more) atomicOr(&s_flag[r >> 5], 1u << (r & 31));
+    }
+    s_par[r] = first;
+  }
+  __syncthreads();
+  // pass 2: pointer jumping until every run points at the top of its chain (the background region
+  // forms chains as long as the image is high: log2(H) rounds, no divergence)
+  while (true) {
+    int changed = 0;
+    for (int r = threadIdx.x; r < nr; r += kCclThreads) {
+      const int q = s_par[r];
+      const int g = s_par[q];
+      if (g != q) {
+        s_par[r] = g;
+        changed = 1;
+      }
+    }
+    if (!__syncthreads_or(changed)) break;
+  }
+  // pass 3: the remaining overlaps merge chains (atomicMin linking of roots, smallest index wins)
+  for (int r = threadIdx.x; r < nr; r += kCclThreads) {
+    if (!((s_flag[r >> 5] >> (r & 31)) & 1u)) continue;
+    const int y = yf[r] & 0x7fff, fg = yf[r] >> 15;
+    const int lo = (int)xs[r] - fg, hi = (int)xe[r] + fg;
+    int l = rowptr[y - 1], h = rowptr[y];
+    const int b = h;
+    while (l < h) {
+      const int m = (l + h) >> 1;
+      if ((int)xe[m] < lo) l = m + 1; else h = m;
+    }
+    bool skipped = false;
+    for (int q = l; q < b && (int)xs[q] <= hi; ++q)
+      if ((yf[q] >> 15) == fg) {
+        if (skipped) uf_union_s(s_par, q, r);
+        skipped = true;
+      }
+  }
+  __syncthreads();
+  // pass 4: flatten; background regions that touch the frame are OUT. Thousands of runs share the root
+  // of the outside region: the flag is collected in the shared bitmap (test before set) and written once
+  // per root, because same-address global stores from a whole CTA serialise in L2.
+  for (int w = threadIdx.x; w < nwords; w += kCclThreads) s_flag[w] = 0u;
+  __syncthreads();
+  for (int r = threadIdx.x; r < nr; r += kCclThreads) {
+    const int root = uf_find_s(s_par, r);
+    s_par[r] = root;
+    p.par[ro + r] = root;
+    const int y = yf[r] & 0x7fff, fg = yf[r] >> 15;
+    if (!fg && (y == 0 || y == p.H - 1 || xs[r] == 0 || xe[r] == p.W - 1)) {
+      const unsigned bit = 1u << (root & 31);
+      if (!(reinterpret_cast<volatile unsigned*>(s_flag)[root >> 5] & bit)) atomicOr(&s_flag[root >> 5], bit);
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < nr; r += kCclThreads)
+    if (s_par[r] == r && ((s_flag[r >> 5] >> (r & 31)) & 1u)) p.cflag[ro + r] = kOutFlag;
 }
 
 // K4b: per-component reductions from the per-run sums (no pixel is read again). One thread per run.
@@ -1047,12 +1170,23 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
   OCRPP_LAUNCHED();
   prof.mark("db_runs");
   dim3 rgrid(kImgCtas, N);
-  db_link_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
-  OCRPP_LAUNCHED();
-  prof.mark("db_link");
-  db_flatten_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
-  OCRPP_LAUNCHED();
-  prof.mark("db_flatten");
+  const size_t ccl_smem = sizeof(int) * ((size_t)p.R + (p.R + 31) / 32 + 1);
+  if (ccl_smem <= 200 * 1024) {
+    static bool attr_set = false;   // opt in to > 48 KB of dynamic shared memory once
+    if (!attr_set) {
+      OCRPP_CUDA(cudaFuncSetAttribute(db_ccl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    db_ccl_kernel<<<N, kCclThreads, ccl_smem, s>>>(p);
+    OCRPP_LAUNCHED();
+    prof.mark("db_ccl");
+  } else {
+    db_link_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
+    OCRPP_LAUNCHED();
+    db_flatten_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
+    OCRPP_LAUNCHED();
+    prof.mark("db_ccl");
+  }
   db_stats_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
   OCRPP_LAUNCHED();
   prof.mark("db_stats");

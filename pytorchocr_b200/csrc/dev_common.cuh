@@ -61,10 +61,25 @@ __device__ __forceinline__ int uf_find(const int32_t* par, int x) {
   return x;
 }
 
+// find with intermediate pointer jumping (path halving): every node visited is re-pointed to its
+// grandparent. Parents only ever decrease towards the root, so the plain stores are benign under the
+// concurrent atomicMin linking (as in ECL-CC); long chains (the background region spans every row of
+// the image) collapse after a few finds.
+__device__ __forceinline__ int uf_find_compress(int32_t* par, int x) {
+  int p = __ldcg(par + x);
+  while (p != x) {
+    const int g = __ldcg(par + p);
+    if (g != p) par[x] = g;
+    x = p;
+    p = g;
+  }
+  return x;
+}
+
 __device__ void uf_union(int32_t* par, int a, int b) {
   while (true) {
-    a = uf_find(par, a);
-    b = uf_find(par, b);
+    a = uf_find_compress(par, a);
+    b = uf_find_compress(par, b);
     if (a == b) return;
     if (a > b) {
       const int t = a;
