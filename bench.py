@@ -222,7 +222,7 @@ class DbWorkload(DetWorkload):
     default_batch = 256
     op_name = "DBPostProcess"
     cfg = DB_CFG
-    stream_kernel = "db_binarize_kernel"
+    stream_kernel = "db_scan_kernel"
     workload = ("DB++ r18 post-process, batch 256 synthetic 736x1280 maps with ~200 text regions each per GPU "
                 "(BASELINE.json configs[1])")
     cpu_note = ("oracle/db_oracle.py (cv2-python restatement of db_postprocess.cpp + the reference's own "

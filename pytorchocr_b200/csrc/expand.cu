@@ -58,7 +58,7 @@ struct ExParams {
   uint16_t *run_xs, *run_xe, *run_y;  // [N][2][R]
   int32_t* par;     // [N][2][R]
   // text-root slots [N][R]
-  int32_t *t_area, *t_xmin, *t_xmax, *t_ymax, *t_seen, *t_amin, *t_amax;
+  int32_t *t_area, *t_xmin, *t_xmax, *t_ymax, *t_seen, *t_amin, *t_amax, *t_nseed, *t_lab;
   // seed-root slots [N][R]
   int32_t *s_area, *s_cc, *s_cid, *s_alive, *s_flag;
   double* s_emb;    // [N][R][4] embedding sums of flagged kernels
@@ -74,9 +74,10 @@ struct ExParams {
   float* res_boxf;
   float* res_score;
   // batch-global
-  int2* work;              // [N*R] (image, text root)
-  int32_t* g_nwork;        // [1]
-  int32_t* g_next;         // [1]
+  int2* work;              // [N*R] (image, text root): padded bounding box <= kSmallCap pixels
+  int2* work_big;          // [N*R] the larger ones
+  int32_t* g_nwork;        // [2] small, big
+  int32_t* g_next;         // [2]
   unsigned long long* g_arena_used;  // [1]
   uint32_t* arena;         // [arena_cap]
   // outputs
@@ -102,6 +103,7 @@ __device__ __forceinline__ float ex_load(const ExParams& p, int n, int c, int y,
 // ------------------------------------------------------------------------------------------------
 constexpr int kBinWarps = 8;
 constexpr int kMaxK = 8;
+constexpr int kSmallCap = 7936;   // expansion, small tiles: pixels of the padded bounding box (4 CTAs of 55 KB per SM)
 
 template <typename T, bool kVec>
 __global__ void __launch_bounds__(kBinWarps * 32) ex_binarize_kernel(ExParams p) {
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(kRunThreads) ex_runs_kernel(ExParams p) {
         const size_t q = so + rbase + js;
         if (m == 0) {
           p.t_area[q] = 0; p.t_xmin[q] = 0x7fffffff; p.t_xmax[q] = -1; p.t_ymax[q] = -1;
-          p.t_seen[q] = 0; p.t_amin[q] = 0x7fffffff; p.t_amax[q] = 0;
+          p.t_seen[q] = 0; p.t_amin[q] = 0x7fffffff; p.t_amax[q] = 0; p.t_nseed[q] = 0; p.t_lab[q] = 0;
         } else {
           p.s_area[q] = 0; p.s_cc[q] = -1; p.s_cid[q] = 0; p.s_alive[q] = 0; p.s_flag[q] = 0;
           p.l_area[q] = 0; p.l_ymin[q] = 0x7fffffff; p.l_ymax[q] = -1; p.l_rowoff[q] = -1; p.l_sum[q] = 0;
@@ -357,14 +359,30 @@ __global__ void __launch_bounds__(kRunThreads) ex_seed_kernel(ExParams p) {
     const int cc = p.par[to + ex_run_at(t_rowptr, p.run_xs + to, y, x)];
     p.s_cc[so + r] = cc;
     p.s_alive[so + r] = 1;
-    if (atomicExch(&p.t_seen[so + cc], 1) == 0) {
-      const int slot = atomicAdd(p.g_nwork, 1);
-      p.work[slot] = make_int2(n, cc);
-    }
+    p.t_seen[so + cc] = 1;
+    atomicAdd(&p.t_nseed[so + cc], 1);
+    p.t_lab[so + cc] = r + 1;   // only read when the component owns exactly one seed
     if (p.mode == kModePan) {
       atomicMin(&p.t_amin[so + cc], area);
       atomicMax(&p.t_amax[so + cc], area);
     }
+  }
+  __syncthreads();
+  // PAN: a text component that owns exactly ONE surviving kernel needs no expansion at all: the only
+  // level runs over the text mask itself (pa.pyx:72), every queued pixel tries all four neighbours, the
+  // component is 4-connected, nobody contests it and a label is only gated when a second kernel shares
+  // its component (pa.pyx:42-54), so every pixel ends with that kernel's label; ex_paint_kernel writes it
+  // directly and only components with two or more kernels become work items of ex_expand_kernel.
+  // PSE has no such shortcut: a pixel that claimed a neighbour is not revisited at later levels
+  // (pse.pyx:47,58-60), so which text pixels stay unlabelled depends on the pop order even for one seed.
+  const int nt = p.nruns[n * 2 + 0];
+  const int min_seeds = p.mode == kModePan ? 2 : 1;
+  for (int r = threadIdx.x; r < nt; r += kRunThreads) {
+    if (p.par[to + r] != r || p.t_nseed[so + r] < min_seeds) continue;
+    const long long tile_px = (long long)(p.t_xmax[so + r] - p.t_xmin[so + r] + 3) *
+                              (p.t_ymax[so + r] - (int)p.run_y[to + r] + 3);
+    if (tile_px <= kSmallCap) p.work[atomicAdd(&p.g_nwork[0], 1)] = make_int2(n, r);
+    else p.work_big[atomicAdd(&p.g_nwork[1], 1)] = make_int2(n, r);
   }
 }
 
@@ -394,9 +412,10 @@ __global__ void __launch_bounds__(kRunBlk) ex_pan_flag_kernel(ExParams p) {
   }
 }
 
-// E7: paint the state map: every text pixel -> kUnset (m == 0; also components without a seed: the
-// bounding-box scan of a neighbouring component reads them), then the surviving seed pixels ->
-// their label (m == 1). One warp per run.
+// E7: paint the state map: every text pixel -> kUnset, or (PAN) directly the label when its component
+// owns exactly one kernel (m == 0; components without a seed are painted too: the bounding-box scan of a
+// neighbouring component reads them), then the surviving seed pixels -> their label (m == 1).
+// One warp per run.
 __global__ void __launch_bounds__(kRunBlk) ex_paint_kernel(ExParams p, int m) {
   const int n = blockIdx.y;
   const int nr = p.nruns[n * 2 + m];
@@ -407,7 +426,7 @@ __global__ void __launch_bounds__(kRunBlk) ex_paint_kernel(ExParams p, int m) {
     const int root = p.par[ro + r];
     uint32_t v;
     if (m == 0) {
-      v = kUnset;
+      v = (p.mode == kModePan && p.t_nseed[so + root] == 1) ? (kLabelBit | (uint32_t)p.t_lab[so + root]) : kUnset;
     } else {
       if (!p.s_alive[so + root]) continue;
       v = kLabelBit | (uint32_t)(root + 1);
@@ -418,207 +437,380 @@ __global__ void __launch_bounds__(kRunBlk) ex_paint_kernel(ExParams p, int m) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// E8: the expansion. Persistent CTAs pull text components from the work list.
+// E8: the expansion. Persistent CTAs pull text components from the work list. A component whose
+// padded bounding box fits the shared-memory tile is expanded entirely in shared memory (state,
+// kernel bits and the four queues); anything larger, or a queue overflow, takes the global-memory
+// path, which has the same structure with the queues in a batch-wide arena.
 // ------------------------------------------------------------------------------------------------
-constexpr int kExThreads = 256;
 constexpr int kStrip = 8;
+constexpr int kSmallThreads = 128;
+constexpr int kBigCap = 18432;    // big tiles (merged text regions): 2 CTAs of 106 KB per SM
+constexpr int kBigThreads = 256;
+constexpr int kListCap = 2048;    // entries per queue of the tile path
+constexpr uint32_t kClaimed = 0x40000000u;  // tile path: label written during this expansion
+constexpr size_t ex_smem_bytes(int cap) { return (size_t)cap * 5 + (size_t)kListCap * 2 * 4; }
 
 __device__ __forceinline__ uint32_t pack_yx(int y, int x) { return ((uint32_t)y << 16) | (uint32_t)x; }
 
+struct ExItem {
+  int n, a, x0, x1, y0, y1, area;
+};
+
+// pa.pyx:86-87: a flagged label only claims pixels whose embedding lies within distance 3 of its mean
 template <typename T>
-__global__ void __launch_bounds__(kExThreads) ex_expand_kernel(ExParams p) {
-  __shared__ int s_item;
+__device__ __forceinline__ bool ex_gate_blocks(const ExParams& p, int n, size_t sr, int ty, int tx) {
+  const double ar = (double)p.s_area[sr];
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float mean = (float)(p.s_emb[sr * 4 + c] / ar);
+    const float d = __fsub_rn(ex_load<T>(p, n, 2 + c, ty, tx), mean);
+    ss = __fadd_rn(ss, __fmul_rn(d, d));
+  }
+  return __fsqrt_rn(ss) > 3.f;
+}
+
+// ---- shared-memory path. Returns false (nothing written to global memory) when a queue overflows.
+template <typename T, int kTileCap, int kExThreads>
+__device__ bool ex_expand_tile(const ExParams& p, const ExItem& it, unsigned char* smem) {
+  __shared__ int s_fail;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kExThreads / 32;
+  const int W = p.W, H = p.H;
+  const int tw = it.x1 - it.x0 + 3, th = it.y1 - it.y0 + 3;  // 1-pixel border of non-text
+  uint32_t* t_st = reinterpret_cast<uint32_t*>(smem);
+  uint16_t* lists = reinterpret_cast<uint16_t*>(t_st + kTileCap);
+  uint8_t* t_kb = reinterpret_cast<uint8_t*>(lists + 4 * kListCap);
+  const size_t so = (size_t)it.n * p.R;
+  const uint8_t* kb = p.kb + (size_t)it.n * H * W;
+  uint32_t* st = p.st + (size_t)it.n * H * W;
+  if (tid == 0) s_fail = 0;
+  // load the tile (rows are contiguous in global memory)
+  for (int ty = warp; ty < th; ty += nwarps) {
+    const int gy = it.y0 - 1 + ty;
+    for (int tx = lane; tx < tw; tx += 32) {
+      const int gx = it.x0 - 1 + tx;
+      unsigned kv = 0;
+      uint32_t sv = 0;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W && ty > 0 && ty < th - 1 && tx > 0 && tx < tw - 1) {
+        kv = kb[(size_t)gy * W + gx];
+        if (kv & 1u) sv = __ldcg(st + (size_t)gy * W + gx);
+      }
+      t_kb[ty * tw + tx] = (uint8_t)kv;
+      t_st[ty * tw + tx] = sv;
+    }
+  }
+  __syncthreads();
+  const int nb4[4] = {-tw, tw, -1, 1};  // pse.pyx:29-30: up, down, left, right
+  uint16_t *Qc = lists, *Qn = lists + kListCap, *X = lists + 2 * kListCap, *Y = lists + 3 * kListCap;
+  // initial queue: surviving seed pixels of this component in raster order that still have a free
+  // text neighbour
+  int nq = 0;
+  {
+    const int bw = tw - 2;
+    const int spr = (bw + kStrip - 1) / kStrip;
+    const int total = spr * (th - 2);
+    for (int s0 = 0; s0 < total; s0 += kExThreads) {
+      const int s = s0 + tid;
+      unsigned mask = 0;
+      int base = 0;
+      if (s < total) {
+        const int ty = 1 + s / spr, tx0 = 1 + (s % spr) * kStrip;
+        base = ty * tw + tx0;
+#pragma unroll
+        for (int i = 0; i < kStrip; ++i) {
+          if (tx0 + i > bw) break;
+          const int q = base + i;
+          if (!(t_kb[q] & 1u)) continue;
+          const uint32_t v = t_st[q];
+          if (!is_labelled(v)) continue;
+          if (p.s_cc[so + (v & 0x3fffffffu) - 1] != it.a) continue;
+          bool alive = false;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) alive |= (t_kb[q + nb4[j]] & 1u) && t_st[q + nb4[j]] == kUnset;
+          if (alive) mask |= 1u << i;
+        }
+      }
+      int tot;
+      int pos = nq + block_exclusive_scan(__popc(mask), &tot);
+      if (nq + tot > kListCap) {
+        s_fail = 1;   // every thread sees the same totals: uniform exit below
+      } else {
+        while (mask) {
+          const int i = __ffs(mask) - 1;
+          mask &= mask - 1;
+          Qc[pos++] = (uint16_t)(base + i);
+        }
+      }
+      nq += tot;
+      if (nq > kListCap) break;
+    }
+    __syncthreads();
+    if (s_fail) return false;
+  }
+  for (int level = (p.mode == kModePse ? p.K - 2 : 0); level >= 0 && nq > 0; --level) {
+    const uint16_t* wave = Qc;
+    int nw = nq, nqn = 0;
+    uint16_t* nxt = X;
+    while (nw > 0) {
+      int nn = 0;
+      for (int c0 = 0; c0 < nw; c0 += kExThreads) {
+        const int r = c0 + tid;
+        const bool active = r < nw;
+        int q = 0;
+        uint32_t lab = 0;
+        if (active) {
+          q = wave[r];
+          lab = t_st[q];
+          bool gated = false;
+          size_t sr = 0;
+          if (p.mode == kModePan) {
+            sr = so + (lab & 0x3fffffffu) - 1;
+            gated = p.s_flag[sr] != 0;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int t = q + nb4[j];
+            if (!((t_kb[t] >> level) & 1u)) continue;
+            if (is_labelled(reinterpret_cast<volatile uint32_t*>(t_st)[t])) continue;
+            if (gated) {
+              const int ty = t / tw, tx = t - ty * tw;
+              if (ex_gate_blocks<T>(p, it.n, sr, it.y0 - 1 + ty, it.x0 - 1 + tx)) continue;
+            }
+            atomicMin(t_st + t, (uint32_t)(r * 4 + j));
+          }
+        }
+        __syncthreads();
+        unsigned win = 0;
+        bool alive = false;
+        if (active) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int t = q + nb4[j];
+            if (!(t_kb[t] & 1u)) continue;
+            const uint32_t v = t_st[t];
+            if (v == kUnset) alive = true;
+            else if (v == (uint32_t)(r * 4 + j)) win |= 1u << j;
+          }
+        }
+        const bool requeue = active && win == 0 && alive;
+        int tot;
+        const int ex = block_exclusive_scan(__popc(win) | (requeue ? 0x10000 : 0), &tot);
+        if (nn + (tot & 0xffff) > kListCap || nqn + (tot >> 16) > kListCap) return false;  // uniform
+        if (active) {
+          int pos = nn + (ex & 0xffff);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (win & (1u << j)) {
+              nxt[pos++] = (uint16_t)(q + nb4[j]);
+              t_st[q + nb4[j]] = lab | kClaimed;
+            }
+          if (requeue) Qn[nqn + (ex >> 16)] = (uint16_t)q;
+        }
+        nn += tot & 0xffff;
+        nqn += tot >> 16;
+        __syncthreads();
+      }
+      wave = nxt;
+      nw = nn;
+      nxt = (nxt == X) ? Y : X;
+    }
+    uint16_t* tmp = Qc;
+    Qc = Qn;
+    Qn = tmp;
+    nq = nqn;
+  }
+  __syncthreads();
+  // write the labels claimed by this expansion back to the global state map
+  for (int ty = 1 + warp; ty < th - 1; ty += nwarps) {
+    const size_t grow = (size_t)(it.y0 - 1 + ty) * W + (it.x0 - 1);
+    for (int tx = 1 + lane; tx < tw - 1; tx += 32) {
+      const uint32_t v = t_st[ty * tw + tx];
+      if ((v & kClaimed) && is_labelled(v)) st[grow + tx] = v & ~kClaimed;
+    }
+  }
+  return true;
+}
+
+// ---- global-memory path (any size)
+template <typename T, int kExThreads>
+__device__ void ex_expand_global(const ExParams& p, const ExItem& it) {
   __shared__ long long s_base;
   const int tid = threadIdx.x;
   const int H = p.H, W = p.W;
   const int dy4[4] = {-1, 1, 0, 0}, dx4[4] = {0, 0, -1, 1};  // pse.pyx:29-30: up, down, left, right
+  const int n = it.n, a = it.a, x0 = it.x0, x1 = it.x1, y0 = it.y0, y1 = it.y1, area = it.area;
+  const size_t so = (size_t)n * p.R;
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned long long b = atomicAdd(p.g_arena_used, 4ull * (unsigned long long)area);
+    if ((long long)(b + 4ull * area) <= p.arena_cap) s_base = (long long)b;
+    else {
+      s_base = -1;
+      atomicOr(&p.imgflags[n], OCRPP_IMG_RUN_OVERFLOW);
+    }
+  }
+  __syncthreads();
+  if (s_base < 0) return;
+  uint32_t* Qc = p.arena + s_base;
+  uint32_t* Qn = Qc + area;
+  uint32_t* X = Qn + area;
+  uint32_t* Y = X + area;
+  const uint8_t* kb = p.kb + (size_t)n * H * W;
+  uint32_t* st = p.st + (size_t)n * H * W;
+
+  // ---- initial queue: surviving seed pixels of this text component in raster order (pse.pyx:33-37),
+  //      minus the ones that have no free text neighbour (they can never claim anything)
+  int nq = 0;
+  {
+    const int spr = (x1 - x0 + kStrip) / kStrip;
+    const int total = spr * (y1 - y0 + 1);
+    for (int s0 = 0; s0 < total; s0 += kExThreads) {
+      const int s = s0 + tid;
+      unsigned mask = 0;
+      int y = 0, xb = 0;
+      if (s < total) {
+        y = y0 + s / spr;
+        xb = x0 + (s % spr) * kStrip;
+#pragma unroll
+        for (int i = 0; i < kStrip; ++i) {
+          const int x = xb + i;
+          if (x > x1) break;
+          const size_t q = (size_t)y * W + x;
+          if (!(kb[q] & 1u)) continue;
+          const uint32_t v = __ldcg(st + q);
+          if (!is_labelled(v)) continue;
+          if (p.s_cc[so + (v & 0x7fffffffu) - 1] != a) continue;
+          bool alive = false;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ty = y + dy4[j], tx = x + dx4[j];
+            if (ty < 0 || ty >= H || tx < 0 || tx >= W) continue;
+            const size_t t = (size_t)ty * W + tx;
+            if ((kb[t] & 1u) && __ldcg(st + t) == kUnset) alive = true;
+          }
+          if (alive) mask |= 1u << i;
+        }
+      }
+      int tot;
+      int pos = nq + block_exclusive_scan(__popc(mask), &tot);
+      while (mask) {
+        const int i = __ffs(mask) - 1;
+        mask &= mask - 1;
+        Qc[pos++] = pack_yx(y, xb + i);
+      }
+      nq += tot;
+    }
+    __syncthreads();  // queue entries visible to every thread of the CTA
+  }
+
+  // ---- levels (PSE: K-2 .. 0, level K-1 is a no-op that only re-queues every seed in order,
+  //      SURVEY H2; PAN: the text mask only, pa.pyx:72)
+  for (int level = (p.mode == kModePse ? p.K - 2 : 0); level >= 0 && nq > 0; --level) {
+    const uint32_t* wave = Qc;
+    int nw = nq, nqn = 0;
+    uint32_t* nxt = X;
+    while (nw > 0) {
+      int nn = 0;
+      for (int c0 = 0; c0 < nw; c0 += kExThreads) {
+        const int r = c0 + tid;
+        const bool active = r < nw;
+        int qy = 0, qx = 0;
+        uint32_t lab = 0, q = 0;
+        if (active) {
+          q = wave[r];
+          qy = q >> 16;
+          qx = q & 0xffffu;
+          lab = __ldcg(st + (size_t)qy * W + qx);
+          // phase 1: propose key 4r+j to every free neighbour that is inside kernel `level`
+          bool gated = false;
+          size_t sr = 0;
+          if (p.mode == kModePan) {
+            sr = so + (lab & 0x7fffffffu) - 1;
+            gated = p.s_flag[sr] != 0;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ty = qy + dy4[j], tx = qx + dx4[j];
+            if (ty < 0 || ty >= H || tx < 0 || tx >= W) continue;
+            const size_t t = (size_t)ty * W + tx;
+            if (!((kb[t] >> level) & 1u)) continue;
+            if (is_labelled(__ldcg(st + t))) continue;
+            if (gated && ex_gate_blocks<T>(p, n, sr, ty, tx)) continue;
+            atomicMin(st + t, (uint32_t)(r * 4 + j));
+          }
+        }
+        __syncthreads();
+        // phase 2: owners collect their pixels; alive = some text neighbour is still free
+        unsigned win = 0;
+        bool alive = false;
+        if (active) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ty = qy + dy4[j], tx = qx + dx4[j];
+            if (ty < 0 || ty >= H || tx < 0 || tx >= W) continue;
+            const size_t t = (size_t)ty * W + tx;
+            if (!(kb[t] & 1u)) continue;
+            const uint32_t v = __ldcg(st + t);
+            if (v == kUnset) alive = true;
+            else if (v == (uint32_t)(r * 4 + j)) win |= 1u << j;
+          }
+        }
+        const bool requeue = active && win == 0 && alive;  // is_edge (pse.pyx:47,58-60)
+        int tot;
+        const int ex = block_exclusive_scan(__popc(win) | (requeue ? 0x10000 : 0), &tot);
+        if (active) {
+          int pos = nn + (ex & 0xffff);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (win & (1u << j)) {
+              const int ty = qy + dy4[j], tx = qx + dx4[j];
+              nxt[pos++] = pack_yx(ty, tx);
+              st[(size_t)ty * W + tx] = lab;
+            }
+          if (requeue) Qn[nqn + (ex >> 16)] = q;
+        }
+        nn += tot & 0xffff;
+        nqn += tot >> 16;
+        __syncthreads();  // labels visible to the next block of pops
+      }
+      wave = nxt;
+      nw = nn;
+      nxt = (nxt == X) ? Y : X;
+    }
+    uint32_t* tmp = Qc;
+    Qc = Qn;
+    Qn = tmp;
+    nq = nqn;
+  }
+}
+
+// kBig selects the work list (components whose padded bounding box exceeds kSmallCap pixels)
+template <typename T, int kTileCap, int kExThreads, bool kBig>
+__global__ void __launch_bounds__(kExThreads) ex_expand_kernel(ExParams p) {
+  extern __shared__ __align__(16) unsigned char ex_smem[];
+  __shared__ int s_item;
+  const int tid = threadIdx.x;
+  const int2* work = kBig ? p.work_big : p.work;
+  int32_t* next = kBig ? p.g_next + 1 : p.g_next;
+  const int nwork = kBig ? p.g_nwork[1] : p.g_nwork[0];
   while (true) {
     __syncthreads();
-    if (tid == 0) s_item = atomicAdd(p.g_next, 1);
+    if (tid == 0) s_item = atomicAdd(next, 1);
     __syncthreads();
     const int item = s_item;
-    if (item >= *p.g_nwork) return;
-    const int n = p.work[item].x, a = p.work[item].y;
-    const size_t to = (size_t)(n * 2 + 0) * p.R, so = (size_t)n * p.R;
-    const int x0 = p.t_xmin[so + a], x1 = p.t_xmax[so + a];
-    const int y0 = p.run_y[to + a], y1 = p.t_ymax[so + a];
-    const int area = p.t_area[so + a];
-#ifdef OCRPP_CHECKS
-    if (tid == 0 && (n < 0 || n >= p.N || a < 0 || a >= p.R || x0 < 0 || x1 >= W || x0 > x1 || y0 < 0 || y1 >= H || y0 > y1 || area <= 0 || area > H * W))
-      printf("expand: bad item %d n=%d a=%d x=[%d,%d] y=[%d,%d] area=%d nwork=%d\n", item, n, a, x0, x1, y0, y1, area, *p.g_nwork);
-#endif
-    if (tid == 0) {
-      const unsigned long long b = atomicAdd(p.g_arena_used, 4ull * (unsigned long long)area);
-      if ((long long)(b + 4ull * area) <= p.arena_cap) s_base = (long long)b;
-      else {
-        s_base = -1;
-        atomicOr(&p.imgflags[n], OCRPP_IMG_RUN_OVERFLOW);
-      }
-    }
-    __syncthreads();
-    if (s_base < 0) continue;
-    uint32_t* Qc = p.arena + s_base;
-    uint32_t* Qn = Qc + area;
-    uint32_t* X = Qn + area;
-    uint32_t* Y = X + area;
-    const uint8_t* kb = p.kb + (size_t)n * H * W;
-    uint32_t* st = p.st + (size_t)n * H * W;
-
-    // ---- initial queue: surviving seed pixels of this text component in raster order (pse.pyx:33-37),
-    //      minus the ones that have no free text neighbour (they can never claim anything)
-    int nq = 0;
-    {
-      const int spr = (x1 - x0 + kStrip) / kStrip;
-      const int total = spr * (y1 - y0 + 1);
-      for (int s0 = 0; s0 < total; s0 += kExThreads) {
-        const int s = s0 + tid;
-        unsigned mask = 0;
-        int y = 0, xb = 0;
-        if (s < total) {
-          y = y0 + s / spr;
-          xb = x0 + (s % spr) * kStrip;
-#pragma unroll
-          for (int i = 0; i < kStrip; ++i) {
-            const int x = xb + i;
-            if (x > x1) break;
-            const size_t q = (size_t)y * W + x;
-            if (!(kb[q] & 1u)) continue;
-            const uint32_t v = __ldcg(st + q);
-            if (!is_labelled(v)) continue;
-#ifdef OCRPP_CHECKS
-            if ((v & 0x7fffffffu) - 1 >= (unsigned)p.R) { printf("expand: bad label %x at (%d,%d) n=%d\n", v, y, x, n); continue; }
-#endif
-            if (p.s_cc[so + (v & 0x7fffffffu) - 1] != a) continue;
-            bool alive = false;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int ty = y + dy4[j], tx = x + dx4[j];
-              if (ty < 0 || ty >= H || tx < 0 || tx >= W) continue;
-              const size_t t = (size_t)ty * W + tx;
-              if ((kb[t] & 1u) && __ldcg(st + t) == kUnset) alive = true;
-            }
-            if (alive) mask |= 1u << i;
-          }
-        }
-        int tot;
-        int pos = nq + block_exclusive_scan(__popc(mask), &tot);
-        while (mask) {
-          const int i = __ffs(mask) - 1;
-          mask &= mask - 1;
-#ifdef OCRPP_CHECKS
-          if (pos >= area) { printf("expand: init queue overflow pos=%d area=%d\n", pos, area); break; }
-#endif
-          Qc[pos++] = pack_yx(y, xb + i);
-        }
-        nq += tot;
-      }
-      __syncthreads();  // queue entries visible to every thread of the CTA
-    }
-
-    // ---- levels (PSE: K-2 .. 0, level K-1 is a no-op that only re-queues every seed in order,
-    //      SURVEY H2; PAN: the text mask only, pa.pyx:72)
-    for (int level = (p.mode == kModePse ? p.K - 2 : 0); level >= 0 && nq > 0; --level) {
-      const uint32_t* wave = Qc;
-      int nw = nq, nqn = 0;
-      uint32_t* nxt = X;
-      while (nw > 0) {
-        int nn = 0;
-        for (int c0 = 0; c0 < nw; c0 += kExThreads) {
-          const int r = c0 + tid;
-          const bool active = r < nw;
-          int qy = 0, qx = 0;
-          uint32_t lab = 0, q = 0;
-          if (active) {
-            q = wave[r];
-            qy = q >> 16;
-            qx = q & 0xffffu;
-#ifdef OCRPP_CHECKS
-            if (qy >= H || qx >= W) { printf("expand: bad wave entry %x r=%d nw=%d level=%d\n", q, r, nw, level); }
-#endif
-            lab = __ldcg(st + (size_t)qy * W + qx);
-#ifdef OCRPP_CHECKS
-            if (!is_labelled(lab)) printf("expand: unlabelled wave entry (%d,%d) st=%x r=%d nw=%d level=%d wave0=%d item=%d bbox x[%d,%d] y[%d,%d]\n", qy, qx, lab, r, nw, level, (int)(wave == Qc), item, x0, x1, y0, y1);
-#endif
-            // phase 1: propose key 4r+j to every free neighbour that is inside kernel `level`
-            bool gated = false;
-            float mean[4] = {0.f, 0.f, 0.f, 0.f};
-            if (p.mode == kModePan) {
-              const size_t sr = so + (lab & 0x7fffffffu) - 1;
-              if (p.s_flag[sr]) {
-                gated = true;
-                const double ar = (double)p.s_area[sr];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) mean[c] = (float)(p.s_emb[sr * 4 + c] / ar);
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int ty = qy + dy4[j], tx = qx + dx4[j];
-              if (ty < 0 || ty >= H || tx < 0 || tx >= W) continue;
-              const size_t t = (size_t)ty * W + tx;
-              if (!((kb[t] >> level) & 1u)) continue;
-              if (is_labelled(__ldcg(st + t))) continue;
-              if (gated) {  // pa.pyx:86-87: ||emb[:,t] - mean_emb[label]||_2 > 3 blocks the claim
-                float ss = 0.f;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  const float d = __fsub_rn(ex_load<T>(p, n, 2 + c, ty, tx), mean[c]);
-                  ss = __fadd_rn(ss, __fmul_rn(d, d));
-                }
-                if (__fsqrt_rn(ss) > 3.f) continue;
-              }
-              atomicMin(st + t, (uint32_t)(r * 4 + j));
-            }
-          }
-          __syncthreads();
-          // phase 2: owners collect their pixels; alive = some text neighbour is still free
-          unsigned win = 0;
-          bool alive = false;
-          if (active) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int ty = qy + dy4[j], tx = qx + dx4[j];
-              if (ty < 0 || ty >= H || tx < 0 || tx >= W) continue;
-              const size_t t = (size_t)ty * W + tx;
-              if (!(kb[t] & 1u)) continue;
-              const uint32_t v = __ldcg(st + t);
-              if (v == kUnset) alive = true;
-              else if (v == (uint32_t)(r * 4 + j)) win |= 1u << j;
-            }
-          }
-          const bool requeue = active && win == 0 && alive;  // is_edge (pse.pyx:47,58-60)
-          int tot;
-          const int ex = block_exclusive_scan(__popc(win) | (requeue ? 0x10000 : 0), &tot);
-          if (active) {
-            int pos = nn + (ex & 0xffff);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (win & (1u << j)) {
-                const int ty = qy + dy4[j], tx = qx + dx4[j];
-#ifdef OCRPP_CHECKS
-                if (pos >= area) { printf("expand: wave overflow pos=%d area=%d\n", pos, area); break; }
-#endif
-                nxt[pos++] = pack_yx(ty, tx);
-                st[(size_t)ty * W + tx] = lab;
-              }
-#ifdef OCRPP_CHECKS
-            if (requeue && nqn + (ex >> 16) >= area) printf("expand: requeue overflow %d area=%d\n", nqn + (ex >> 16), area);
-#endif
-            if (requeue) Qn[nqn + (ex >> 16)] = q;
-          }
-          nn += tot & 0xffff;
-          nqn += tot >> 16;
-          __syncthreads();  // labels visible to the next block of pops
-        }
-        wave = nxt;
-        nw = nn;
-        nxt = (nxt == X) ? Y : X;
-      }
-      uint32_t* tmp = Qc;
-      Qc = Qn;
-      Qn = tmp;
-      nq = nqn;
-    }
+    if (item >= nwork) return;
+    ExItem it;
+    it.n = work[item].x;
+    it.a = work[item].y;
+    const size_t to = (size_t)(it.n * 2 + 0) * p.R, so = (size_t)it.n * p.R;
+    it.x0 = p.t_xmin[so + it.a];
+    it.x1 = p.t_xmax[so + it.a];
+    it.y0 = p.run_y[to + it.a];
+    it.y1 = p.t_ymax[so + it.a];
+    it.area = p.t_area[so + it.a];
+    const long long tile_px = (long long)(it.x1 - it.x0 + 3) * (it.y1 - it.y0 + 3);
+    if (tile_px <= kTileCap && ex_expand_tile<T, kTileCap, kExThreads>(p, it, ex_smem)) continue;
+    ex_expand_global<T, kExThreads>(p, it);
   }
 }
 
@@ -847,9 +1039,9 @@ __global__ void __launch_bounds__(kRunBlk) ex_labels_kernel(ExParams p) {
 size_t ex_carve(ExParams& p, void* ws) {
   Carver c{(char*)ws, 0};
   const size_t N = p.N, R = p.R, E = p.E, HW = (size_t)p.H * p.W;
-  p.g_nwork = c.take<int32_t>(64);  // g_nwork | g_next | g_arena_used(2 words) + per-image counters below
-  p.g_next = p.g_nwork ? p.g_nwork + 1 : nullptr;
-  p.g_arena_used = p.g_nwork ? reinterpret_cast<unsigned long long*>(p.g_nwork + 2) : nullptr;
+  p.g_nwork = c.take<int32_t>(64);  // g_nwork[2] | g_next[2] | g_arena_used (2 words), cleared together
+  p.g_next = p.g_nwork ? p.g_nwork + 2 : nullptr;
+  p.g_arena_used = p.g_nwork ? reinterpret_cast<unsigned long long*>(p.g_nwork + 4) : nullptr;
   p.nruns = c.take<int32_t>(5 * N);  // nruns[2N] | ext_alloc | imgflags | ncand, cleared together
   p.ext_alloc = p.nruns ? p.nruns + 2 * N : nullptr;
   p.imgflags = p.nruns ? p.nruns + 3 * N : nullptr;
@@ -869,6 +1061,8 @@ size_t ex_carve(ExParams& p, void* ws) {
   p.t_seen = c.take<int32_t>(N * R);
   p.t_amin = c.take<int32_t>(N * R);
   p.t_amax = c.take<int32_t>(N * R);
+  p.t_nseed = c.take<int32_t>(N * R);
+  p.t_lab = c.take<int32_t>(N * R);
   p.s_area = c.take<int32_t>(N * R);
   p.s_cc = c.take<int32_t>(N * R);
   p.s_cid = c.take<int32_t>(N * R);
@@ -889,6 +1083,7 @@ size_t ex_carve(ExParams& p, void* ws) {
   p.res_boxf = c.take<float>(N * p.maxc * 8);
   p.res_score = c.take<float>(N * p.maxc);
   p.work = c.take<int2>(N * R);
+  p.work_big = c.take<int2>(N * R);
   p.arena = c.take<uint32_t>((size_t)p.arena_cap);
   return align_up(c.off, 256);
 }
@@ -952,8 +1147,21 @@ int ex_launch(ExParams& p, cudaStream_t s, bool vec) {
   ex_paint_kernel<<<rgrid, kRunBlk, 0, s>>>(p, 1);
   OCRPP_LAUNCHED();
   prof.mark("ex_paint");
-  ex_expand_kernel<T><<<kNumSMs * 8, kExThreads, 0, s>>>(p);
-  OCRPP_LAUNCHED();
+  {
+    static bool attr_set = false;   // opt in to > 48 KB of dynamic shared memory once per instantiation
+    auto small_k = ex_expand_kernel<T, kSmallCap, kSmallThreads, false>;
+    auto big_k = ex_expand_kernel<T, kBigCap, kBigThreads, true>;
+    if (!attr_set) {
+      OCRPP_CUDA(cudaFuncSetAttribute(small_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem_bytes(kSmallCap)));
+      OCRPP_CUDA(cudaFuncSetAttribute(big_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem_bytes(kBigCap)));
+      attr_set = true;
+    }
+    big_k<<<kNumSMs * 2, kBigThreads, ex_smem_bytes(kBigCap), s>>>(p);   // long items first
+    OCRPP_LAUNCHED();
+    prof.mark("ex_expand_big");
+    small_k<<<kNumSMs * 4, kSmallThreads, ex_smem_bytes(kSmallCap), s>>>(p);
+    OCRPP_LAUNCHED();
+  }
   prof.mark("ex_expand");
   ex_stats_kernel<T, 1><<<rgrid, kRunBlk, 0, s>>>(p);
   OCRPP_LAUNCHED();
