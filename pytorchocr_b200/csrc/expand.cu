@@ -23,7 +23,7 @@
 //
 // Data layout per image at processing resolution H x W (H = h*upsample_in):
 //   kb  u8  [H*W]   bit k = kernel k after text masking (PSE: k < K; PAN: bit0 text, bit1 kernel)
-//   st  u32 [H*W]   state of text pixels: kUnset | proposal key (< 2^31) | kLabelBit + label
+//   st  u32 [H*W]   state of text pixels: kUnset | proposal key (< 2^31) | kLabelBit (+ kGateBit) + label
 //   1-bit masks of text and seed kernel -> run tables -> run union-find (4-connectivity)
 // Algorithmic bytes per image: C*h*w*sizeof(elem), the head output, read once by ex_binarize_kernel
 // (plus channel 0 again at text pixels for the score mean, and embeddings at gated pixels only).
@@ -37,6 +37,8 @@ namespace {
 
 constexpr uint32_t kUnset = 0xffffffffu;
 constexpr uint32_t kLabelBit = 0x80000000u;
+constexpr uint32_t kGateBit = 0x20000000u;    // PAN: the label is "flagged" (pa.pyx:42-54), claims are gated
+constexpr uint32_t kLabelMask = 0x1fffffffu;  // label = root run index of the seed mask + 1
 constexpr double kFix = 4294967296.0;  // 2^32
 
 __device__ __forceinline__ bool is_labelled(uint32_t v) { return (v & kLabelBit) && v != kUnset; }
@@ -74,10 +76,9 @@ struct ExParams {
   float* res_boxf;
   float* res_score;
   // batch-global
-  int2* work;              // [N*R] (image, text root): padded bounding box <= kSmallCap pixels
-  int2* work_big;          // [N*R] the larger ones
-  int32_t* g_nwork;        // [2] small, big
-  int32_t* g_next;         // [2]
+  int2* work;              // [4][N*R] (image, text root) by tile class: tiny, small, big, huge
+  int32_t* g_nwork;        // [4]
+  int32_t* g_next;         // [4]
   unsigned long long* g_arena_used;  // [1]
   uint32_t* arena;         // [arena_cap]
   // outputs
@@ -103,7 +104,9 @@ __device__ __forceinline__ float ex_load(const ExParams& p, int n, int c, int y,
 // ------------------------------------------------------------------------------------------------
 constexpr int kBinWarps = 8;
 constexpr int kMaxK = 8;
-constexpr int kSmallCap = 7936;   // expansion, small tiles: pixels of the padded bounding box (4 CTAs of 55 KB per SM)
+constexpr int kTinyCap = 4096;    // expansion, tiny tiles: pixels of the padded bounding box (9 CTAs of 24 KB per SM)
+constexpr int kSmallCap = 7936;   // small tiles (4 CTAs of 47 KB per SM)
+constexpr int kBigCap = 18432;    // big tiles (merged text regions): 2 CTAs of 88 KB per SM
 
 template <typename T, bool kVec>
 __global__ void __launch_bounds__(kBinWarps * 32) ex_binarize_kernel(ExParams p) {
@@ -381,8 +384,8 @@ __global__ void __launch_bounds__(kRunThreads) ex_seed_kernel(ExParams p) {
     if (p.par[to + r] != r || p.t_nseed[so + r] < min_seeds) continue;
     const long long tile_px = (long long)(p.t_xmax[so + r] - p.t_xmin[so + r] + 3) *
                               (p.t_ymax[so + r] - (int)p.run_y[to + r] + 3);
-    if (tile_px <= kSmallCap) p.work[atomicAdd(&p.g_nwork[0], 1)] = make_int2(n, r);
-    else p.work_big[atomicAdd(&p.g_nwork[1], 1)] = make_int2(n, r);
+    const int cls = tile_px <= kTinyCap ? 0 : (tile_px <= kSmallCap ? 1 : (tile_px <= kBigCap ? 2 : 3));
+    p.work[(size_t)cls * p.N * p.R + atomicAdd(&p.g_nwork[cls], 1)] = make_int2(n, r);
   }
 }
 
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(kRunBlk) ex_paint_kernel(ExParams p, int m) {
       v = (p.mode == kModePan && p.t_nseed[so + root] == 1) ? (kLabelBit | (uint32_t)p.t_lab[so + root]) : kUnset;
     } else {
       if (!p.s_alive[so + root]) continue;
-      v = kLabelBit | (uint32_t)(root + 1);
+      v = kLabelBit | (p.s_flag[so + root] ? kGateBit : 0u) | (uint32_t)(root + 1);
     }
     const size_t row = (size_t)p.run_y[ro + r] * p.W;
     for (int x = p.run_xs[ro + r] + lane; x <= (int)p.run_xe[ro + r]; x += 32) st[row + x] = v;
@@ -444,11 +447,13 @@ __global__ void __launch_bounds__(kRunBlk) ex_paint_kernel(ExParams p, int m) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kStrip = 8;
 constexpr int kSmallThreads = 128;
-constexpr int kBigCap = 18432;    // big tiles (merged text regions): 2 CTAs of 106 KB per SM
 constexpr int kBigThreads = 256;
-constexpr int kListCap = 2048;    // entries per queue of the tile path
-constexpr uint32_t kClaimed = 0x40000000u;  // tile path: label written during this expansion
-constexpr size_t ex_smem_bytes(int cap) { return (size_t)cap * 5 + (size_t)kListCap * 2 * 4; }
+constexpr int kHugeCap = 53248;   // huge tiles (many merged regions): 1 CTA of 224 KB per SM
+constexpr int kHugeThreads = 512;
+constexpr int kTinyThreads = 128;
+constexpr int kTinyList = 1024;   // entries per queue, tiny tiles
+constexpr int kListCap = 2048;    // entries per queue, small and big tiles
+constexpr size_t ex_smem_bytes(int cap, int list) { return (size_t)cap * 4 + (size_t)list * 2 * 4; }
 
 __device__ __forceinline__ uint32_t pack_yx(int y, int x) { return ((uint32_t)y << 16) | (uint32_t)x; }
 
@@ -457,51 +462,97 @@ struct ExItem {
 };
 
 // pa.pyx:86-87: a flagged label only claims pixels whose embedding lies within distance 3 of its mean
-template <typename T>
-__device__ __forceinline__ bool ex_gate_blocks(const ExParams& p, int n, size_t sr, int ty, int tx) {
+struct ExMean {
+  float m[4];
+};
+__device__ __forceinline__ ExMean ex_mean_emb(const ExParams& p, size_t sr) {   // float32 mean (pa.pyx:50,54)
+  ExMean e;
   const double ar = (double)p.s_area[sr];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) e.m[c] = (float)(p.s_emb[sr * 4 + c] / ar);
+  return e;
+}
+template <typename T>
+__device__ __forceinline__ bool ex_gate_blocks(const ExParams& p, int n, const ExMean& e, int ty, int tx) {
   float ss = 0.f;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    const float mean = (float)(p.s_emb[sr * 4 + c] / ar);
-    const float d = __fsub_rn(ex_load<T>(p, n, 2 + c, ty, tx), mean);
+    const float d = __fsub_rn(ex_load<T>(p, n, 2 + c, ty, tx), e.m[c]);
     ss = __fadd_rn(ss, __fmul_rn(d, d));
   }
   return __fsqrt_rn(ss) > 3.f;
 }
 
 // ---- shared-memory path. Returns false (nothing written to global memory) when a queue overflows.
-template <typename T, int kTileCap, int kExThreads>
+// One 32-bit cell per pixel of the padded bounding box: kernel bits in the top byte, and in the low 24
+// bits the state: kCellUnset | proposal key (< 2^23) | kCellLabel + label (+ kCellGated, + kCellClaimed
+// when the label was written by this expansion). The top byte is the same for every proposal to a pixel, so
+// atomicMin on the whole cell orders proposals by key.
+constexpr uint32_t kCellUnset = 0x00ffffffu;
+constexpr uint32_t kCellLabel = 0x00800000u;
+constexpr uint32_t kCellClaimed = 0x00400000u;
+constexpr uint32_t kCellGated = 0x00200000u;     // copy of kGateBit
+constexpr uint32_t kCellLabMask = 0x001fffffu;   // labels (root run index + 1) must stay below 2^21
+
+__device__ __forceinline__ bool cell_labelled(uint32_t c) {
+  return (c & kCellLabel) && (c & 0x00ffffffu) != kCellUnset;
+}
+
+// exclusive prefix over the CTA (thread order) of a packed pair of small counters; `s_tot` holds one
+// slot per warp and is double-buffered by the caller so that a single barrier per call is enough
+template <int kThreads>
+__device__ __forceinline__ int ex_block_prefix(int v, int* s_tot, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_tot[warp] = inc;
+  __syncthreads();
+  int before = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const int t = s_tot[w];
+    before += w < warp ? t : 0;
+    tot += t;
+  }
+  *total = tot;
+  return before + inc - v;
+}
+
+template <typename T, int kTileCap, int kListCap, int kExThreads>
 __device__ bool ex_expand_tile(const ExParams& p, const ExItem& it, unsigned char* smem) {
-  __shared__ int s_fail;
+  __shared__ int s_tot[2][kExThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kExThreads / 32;
   const int W = p.W, H = p.H;
   const int tw = it.x1 - it.x0 + 3, th = it.y1 - it.y0 + 3;  // 1-pixel border of non-text
-  uint32_t* t_st = reinterpret_cast<uint32_t*>(smem);
-  uint16_t* lists = reinterpret_cast<uint16_t*>(t_st + kTileCap);
-  uint8_t* t_kb = reinterpret_cast<uint8_t*>(lists + 4 * kListCap);
+  uint32_t* cell = reinterpret_cast<uint32_t*>(smem);
+  uint16_t* lists = reinterpret_cast<uint16_t*>(cell + kTileCap);
   const size_t so = (size_t)it.n * p.R;
   const uint8_t* kb = p.kb + (size_t)it.n * H * W;
   uint32_t* st = p.st + (size_t)it.n * H * W;
-  if (tid == 0) s_fail = 0;
-  // load the tile (rows are contiguous in global memory)
+  // load the tile (rows are contiguous in global memory; both loads are issued unconditionally)
   for (int ty = warp; ty < th; ty += nwarps) {
     const int gy = it.y0 - 1 + ty;
     for (int tx = lane; tx < tw; tx += 32) {
-      const int gx = it.x0 - 1 + tx;
-      unsigned kv = 0;
-      uint32_t sv = 0;
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W && ty > 0 && ty < th - 1 && tx > 0 && tx < tw - 1) {
-        kv = kb[(size_t)gy * W + gx];
-        if (kv & 1u) sv = __ldcg(st + (size_t)gy * W + gx);
+      uint32_t c = 0;
+      if (ty > 0 && ty < th - 1 && tx > 0 && tx < tw - 1) {   // interior = inside the image
+        const size_t g = (size_t)gy * W + (it.x0 - 1 + tx);
+        const unsigned kv = kb[g];
+        const uint32_t sv = __ldcg(st + g);                    // garbage where kv has no text bit
+        if (kv & 1u)
+          c = (kv << 24) | (is_labelled(sv) ? (kCellLabel | ((sv & kGateBit) ? kCellGated : 0u) | (sv & kCellLabMask))
+                                            : kCellUnset);
       }
-      t_kb[ty * tw + tx] = (uint8_t)kv;
-      t_st[ty * tw + tx] = sv;
+      cell[ty * tw + tx] = c;
     }
   }
   __syncthreads();
   const int nb4[4] = {-tw, tw, -1, 1};  // pse.pyx:29-30: up, down, left, right
   uint16_t *Qc = lists, *Qn = lists + kListCap, *X = lists + 2 * kListCap, *Y = lists + 3 * kListCap;
+  int flip = 0;
   // initial queue: surviving seed pixels of this component in raster order that still have a free
   // text neighbour
   int nq = 0;
@@ -520,37 +571,33 @@ __device__ bool ex_expand_tile(const ExParams& p, const ExItem& it, unsigned cha
         for (int i = 0; i < kStrip; ++i) {
           if (tx0 + i > bw) break;
           const int q = base + i;
-          if (!(t_kb[q] & 1u)) continue;
-          const uint32_t v = t_st[q];
-          if (!is_labelled(v)) continue;
-          if (p.s_cc[so + (v & 0x3fffffffu) - 1] != it.a) continue;
+          const uint32_t v = cell[q];
+          if (!cell_labelled(v)) continue;
+          if (p.s_cc[so + (v & kCellLabMask) - 1] != it.a) continue;
           bool alive = false;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) alive |= (t_kb[q + nb4[j]] & 1u) && t_st[q + nb4[j]] == kUnset;
+          for (int j = 0; j < 4; ++j) alive |= (cell[q + nb4[j]] & 0x01ffffffu) == (0x01000000u | kCellUnset);
           if (alive) mask |= 1u << i;
         }
       }
       int tot;
-      int pos = nq + block_exclusive_scan(__popc(mask), &tot);
-      if (nq + tot > kListCap) {
-        s_fail = 1;   // every thread sees the same totals: uniform exit below
-      } else {
-        while (mask) {
-          const int i = __ffs(mask) - 1;
-          mask &= mask - 1;
-          Qc[pos++] = (uint16_t)(base + i);
-        }
+      int pos = nq + ex_block_prefix<kExThreads>(__popc(mask), s_tot[flip], &tot);
+      flip ^= 1;
+      if (nq + tot > kListCap) return false;   // uniform
+      while (mask) {
+        const int i = __ffs(mask) - 1;
+        mask &= mask - 1;
+        Qc[pos++] = (uint16_t)(base + i);
       }
       nq += tot;
-      if (nq > kListCap) break;
     }
     __syncthreads();
-    if (s_fail) return false;
   }
   for (int level = (p.mode == kModePse ? p.K - 2 : 0); level >= 0 && nq > 0; --level) {
     const uint16_t* wave = Qc;
     int nw = nq, nqn = 0;
     uint16_t* nxt = X;
+    const uint32_t lvl_bit = 0x01000000u << level;
     while (nw > 0) {
       int nn = 0;
       for (int c0 = 0; c0 < nw; c0 += kExThreads) {
@@ -560,23 +607,20 @@ __device__ bool ex_expand_tile(const ExParams& p, const ExItem& it, unsigned cha
         uint32_t lab = 0;
         if (active) {
           q = wave[r];
-          lab = t_st[q];
-          bool gated = false;
-          size_t sr = 0;
-          if (p.mode == kModePan) {
-            sr = so + (lab & 0x3fffffffu) - 1;
-            gated = p.s_flag[sr] != 0;
-          }
+          lab = cell[q] & (kCellLabMask | kCellGated);
+          const bool gated = (lab & kCellGated) != 0;
+          ExMean mean{};
+          if (gated) mean = ex_mean_emb(p, so + (lab & kCellLabMask) - 1);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int t = q + nb4[j];
-            if (!((t_kb[t] >> level) & 1u)) continue;
-            if (is_labelled(reinterpret_cast<volatile uint32_t*>(t_st)[t])) continue;
+            const uint32_t c = reinterpret_cast<volatile uint32_t*>(cell)[t];
+            if (!(c & lvl_bit) || cell_labelled(c)) continue;
             if (gated) {
               const int ty = t / tw, tx = t - ty * tw;
-              if (ex_gate_blocks<T>(p, it.n, sr, it.y0 - 1 + ty, it.x0 - 1 + tx)) continue;
+              if (ex_gate_blocks<T>(p, it.n, mean, it.y0 - 1 + ty, it.x0 - 1 + tx)) continue;
             }
-            atomicMin(t_st + t, (uint32_t)(r * 4 + j));
+            atomicMin(cell + t, (c & 0xff000000u) | (uint32_t)(r * 4 + j));
           }
         }
         __syncthreads();
@@ -585,24 +629,26 @@ __device__ bool ex_expand_tile(const ExParams& p, const ExItem& it, unsigned cha
         if (active) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int t = q + nb4[j];
-            if (!(t_kb[t] & 1u)) continue;
-            const uint32_t v = t_st[t];
-            if (v == kUnset) alive = true;
-            else if (v == (uint32_t)(r * 4 + j)) win |= 1u << j;
+            const uint32_t c = cell[q + nb4[j]];
+            if (!(c & 0x01000000u)) continue;
+            const uint32_t pay = c & 0x00ffffffu;
+            if (pay == kCellUnset) alive = true;
+            else if (pay == (uint32_t)(r * 4 + j)) win |= 1u << j;
           }
         }
         const bool requeue = active && win == 0 && alive;
         int tot;
-        const int ex = block_exclusive_scan(__popc(win) | (requeue ? 0x10000 : 0), &tot);
+        const int ex = ex_block_prefix<kExThreads>(__popc(win) | (requeue ? 0x10000 : 0), s_tot[flip], &tot);
+        flip ^= 1;
         if (nn + (tot & 0xffff) > kListCap || nqn + (tot >> 16) > kListCap) return false;  // uniform
         if (active) {
           int pos = nn + (ex & 0xffff);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (win & (1u << j)) {
-              nxt[pos++] = (uint16_t)(q + nb4[j]);
-              t_st[q + nb4[j]] = lab | kClaimed;
+              const int t = q + nb4[j];
+              nxt[pos++] = (uint16_t)t;
+              cell[t] = (cell[t] & 0xff000000u) | kCellLabel | kCellClaimed | lab;
             }
           if (requeue) Qn[nqn + (ex >> 16)] = (uint16_t)q;
         }
@@ -624,8 +670,9 @@ __device__ bool ex_expand_tile(const ExParams& p, const ExItem& it, unsigned cha
   for (int ty = 1 + warp; ty < th - 1; ty += nwarps) {
     const size_t grow = (size_t)(it.y0 - 1 + ty) * W + (it.x0 - 1);
     for (int tx = 1 + lane; tx < tw - 1; tx += 32) {
-      const uint32_t v = t_st[ty * tw + tx];
-      if ((v & kClaimed) && is_labelled(v)) st[grow + tx] = v & ~kClaimed;
+      const uint32_t c = cell[ty * tw + tx];
+      if ((c & kCellClaimed) && cell_labelled(c))
+        st[grow + tx] = kLabelBit | ((c & kCellGated) ? kGateBit : 0u) | (c & kCellLabMask);
     }
   }
   return true;
@@ -679,7 +726,7 @@ __device__ void ex_expand_global(const ExParams& p, const ExItem& it) {
           if (!(kb[q] & 1u)) continue;
           const uint32_t v = __ldcg(st + q);
           if (!is_labelled(v)) continue;
-          if (p.s_cc[so + (v & 0x7fffffffu) - 1] != a) continue;
+          if (p.s_cc[so + (v & kLabelMask) - 1] != a) continue;
           bool alive = false;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -722,12 +769,9 @@ __device__ void ex_expand_global(const ExParams& p, const ExItem& it) {
           qx = q & 0xffffu;
           lab = __ldcg(st + (size_t)qy * W + qx);
           // phase 1: propose key 4r+j to every free neighbour that is inside kernel `level`
-          bool gated = false;
-          size_t sr = 0;
-          if (p.mode == kModePan) {
-            sr = so + (lab & 0x7fffffffu) - 1;
-            gated = p.s_flag[sr] != 0;
-          }
+          const bool gated = (lab & kGateBit) != 0;
+          ExMean mean{};
+          if (gated) mean = ex_mean_emb(p, so + (lab & kLabelMask) - 1);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int ty = qy + dy4[j], tx = qx + dx4[j];
@@ -735,7 +779,7 @@ __device__ void ex_expand_global(const ExParams& p, const ExItem& it) {
             const size_t t = (size_t)ty * W + tx;
             if (!((kb[t] >> level) & 1u)) continue;
             if (is_labelled(__ldcg(st + t))) continue;
-            if (gated && ex_gate_blocks<T>(p, n, sr, ty, tx)) continue;
+            if (gated && ex_gate_blocks<T>(p, n, mean, ty, tx)) continue;
             atomicMin(st + t, (uint32_t)(r * 4 + j));
           }
         }
@@ -784,15 +828,17 @@ __device__ void ex_expand_global(const ExParams& p, const ExItem& it) {
   }
 }
 
-// kBig selects the work list (components whose padded bounding box exceeds kSmallCap pixels)
-template <typename T, int kTileCap, int kExThreads, bool kBig>
+// kClass selects the work list: 0 tiny, 1 small, 2 big, 3 huge and beyond (by the pixel count of the
+// padded bounding box)
+template <typename T, int kTileCap, int kList, int kExThreads, int kClass>
 __global__ void __launch_bounds__(kExThreads) ex_expand_kernel(ExParams p) {
   extern __shared__ __align__(16) unsigned char ex_smem[];
   __shared__ int s_item;
   const int tid = threadIdx.x;
-  const int2* work = kBig ? p.work_big : p.work;
-  int32_t* next = kBig ? p.g_next + 1 : p.g_next;
-  const int nwork = kBig ? p.g_nwork[1] : p.g_nwork[0];
+  const int2* work = p.work + (size_t)kClass * p.N * p.R;
+  int32_t* next = p.g_next + kClass;
+  const int nwork = p.g_nwork[kClass];
+  const bool tile_ok = p.R < (1 << 21);   // labels must fit the 21-bit cell field
   while (true) {
     __syncthreads();
     if (tid == 0) s_item = atomicAdd(next, 1);
@@ -809,7 +855,7 @@ __global__ void __launch_bounds__(kExThreads) ex_expand_kernel(ExParams p) {
     it.y1 = p.t_ymax[so + it.a];
     it.area = p.t_area[so + it.a];
     const long long tile_px = (long long)(it.x1 - it.x0 + 3) * (it.y1 - it.y0 + 3);
-    if (tile_px <= kTileCap && ex_expand_tile<T, kTileCap, kExThreads>(p, it, ex_smem)) continue;
+    if (tile_ok && tile_px <= kTileCap && ex_expand_tile<T, kTileCap, kList, kExThreads>(p, it, ex_smem)) continue;
     ex_expand_global<T, kExThreads>(p, it);
   }
 }
@@ -836,7 +882,7 @@ __global__ void __launch_bounds__(kRunBlk) ex_stats_kernel(ExParams p) {
       if (x <= b) {
         const uint32_t v = st[(size_t)y * p.W + x];
         if (is_labelled(v)) {
-          lab = v & 0x7fffffffu;
+          lab = v & kLabelMask;
           if (PASS == 1) {
             const float logit = ex_load<T>(p, n, 0, y, x);
             const float sc = 1.f / (1.f + expf(-logit));  // F.sigmoid (pse_postprocess.py:38)
@@ -1031,7 +1077,7 @@ __global__ void __launch_bounds__(kRunBlk) ex_labels_kernel(ExParams p) {
     const size_t row = (size_t)p.run_y[ro + r] * p.W;
     for (int x = p.run_xs[ro + r] + lane; x <= (int)p.run_xe[ro + r]; x += 32) {
       const uint32_t v = st[row + x];
-      if (is_labelled(v)) lab[row + x] = p.s_cid[so + (v & 0x7fffffffu) - 1];
+      if (is_labelled(v)) lab[row + x] = p.s_cid[so + (v & kLabelMask) - 1];
     }
   }
 }
@@ -1039,9 +1085,9 @@ __global__ void __launch_bounds__(kRunBlk) ex_labels_kernel(ExParams p) {
 size_t ex_carve(ExParams& p, void* ws) {
   Carver c{(char*)ws, 0};
   const size_t N = p.N, R = p.R, E = p.E, HW = (size_t)p.H * p.W;
-  p.g_nwork = c.take<int32_t>(64);  // g_nwork[2] | g_next[2] | g_arena_used (2 words), cleared together
-  p.g_next = p.g_nwork ? p.g_nwork + 2 : nullptr;
-  p.g_arena_used = p.g_nwork ? reinterpret_cast<unsigned long long*>(p.g_nwork + 4) : nullptr;
+  p.g_nwork = c.take<int32_t>(64);  // g_nwork[4] | g_next[4] | g_arena_used (2 words), cleared together
+  p.g_next = p.g_nwork ? p.g_nwork + 4 : nullptr;
+  p.g_arena_used = p.g_nwork ? reinterpret_cast<unsigned long long*>(p.g_nwork + 8) : nullptr;
   p.nruns = c.take<int32_t>(5 * N);  // nruns[2N] | ext_alloc | imgflags | ncand, cleared together
   p.ext_alloc = p.nruns ? p.nruns + 2 * N : nullptr;
   p.imgflags = p.nruns ? p.nruns + 3 * N : nullptr;
@@ -1082,8 +1128,7 @@ size_t ex_carve(ExParams& p, void* ws) {
   p.res_box = c.take<int16_t>(N * p.maxc * 8);
   p.res_boxf = c.take<float>(N * p.maxc * 8);
   p.res_score = c.take<float>(N * p.maxc);
-  p.work = c.take<int2>(N * R);
-  p.work_big = c.take<int2>(N * R);
+  p.work = c.take<int2>(4 * N * R);
   p.arena = c.take<uint32_t>((size_t)p.arena_cap);
   return align_up(c.off, 256);
 }
@@ -1149,17 +1194,25 @@ int ex_launch(ExParams& p, cudaStream_t s, bool vec) {
   prof.mark("ex_paint");
   {
     static bool attr_set = false;   // opt in to > 48 KB of dynamic shared memory once per instantiation
-    auto small_k = ex_expand_kernel<T, kSmallCap, kSmallThreads, false>;
-    auto big_k = ex_expand_kernel<T, kBigCap, kBigThreads, true>;
+    auto tiny_k = ex_expand_kernel<T, kTinyCap, kTinyList, kTinyThreads, 0>;
+    auto small_k = ex_expand_kernel<T, kSmallCap, kListCap, kSmallThreads, 1>;
+    auto big_k = ex_expand_kernel<T, kBigCap, kListCap, kBigThreads, 2>;
+    auto huge_k = ex_expand_kernel<T, kHugeCap, kListCap, kHugeThreads, 3>;
     if (!attr_set) {
-      OCRPP_CUDA(cudaFuncSetAttribute(small_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem_bytes(kSmallCap)));
-      OCRPP_CUDA(cudaFuncSetAttribute(big_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem_bytes(kBigCap)));
+      OCRPP_CUDA(cudaFuncSetAttribute(huge_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem_bytes(kHugeCap, kListCap)));
+      OCRPP_CUDA(cudaFuncSetAttribute(small_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem_bytes(kSmallCap, kListCap)));
+      OCRPP_CUDA(cudaFuncSetAttribute(big_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem_bytes(kBigCap, kListCap)));
       attr_set = true;
     }
-    big_k<<<kNumSMs * 2, kBigThreads, ex_smem_bytes(kBigCap), s>>>(p);   // long items first
+    huge_k<<<kNumSMs, kHugeThreads, ex_smem_bytes(kHugeCap, kListCap), s>>>(p);   // long items first
+    OCRPP_LAUNCHED();
+    big_k<<<kNumSMs * 2, kBigThreads, ex_smem_bytes(kBigCap, kListCap), s>>>(p);
     OCRPP_LAUNCHED();
     prof.mark("ex_expand_big");
-    small_k<<<kNumSMs * 4, kSmallThreads, ex_smem_bytes(kSmallCap), s>>>(p);
+    small_k<<<kNumSMs * 4, kSmallThreads, ex_smem_bytes(kSmallCap, kListCap), s>>>(p);
+    OCRPP_LAUNCHED();
+    prof.mark("ex_expand_small");
+    tiny_k<<<kNumSMs * 9, kTinyThreads, ex_smem_bytes(kTinyCap, kTinyList), s>>>(p);
     OCRPP_LAUNCHED();
   }
   prof.mark("ex_expand");

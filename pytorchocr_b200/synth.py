@@ -14,10 +14,11 @@ import numpy as np
 BASE_SEED = 20221001
 
 
-def _place_rects(rng, H, W, n, hh_rng=(5, 10), hw_rng=(15, 37), max_angle=20.0, margin=4, tries=40):
-    """Non-overlapping rotated rectangles (cx, cy, hw, hh, angle_deg); rejection-sampled on a
-    coarse occupancy grid so that neighbours stay >= margin px apart."""
-    occ = np.zeros((H, W), np.uint8)
+def _place_rects(rng, H, W, n, hh_rng=(5, 10), hw_rng=(15, 37), max_angle=20.0, margin=4, tries=40, occ=None):
+    """Non-overlapping rotated rectangles (cx, cy, hw, hh, angle_deg); rejection-sampled on an
+    occupancy grid (optionally shared between calls) so that neighbours stay >= margin px apart."""
+    if occ is None:
+        occ = np.zeros((H, W), np.uint8)
     rects = []
     for _ in range(n * tries):
         if len(rects) >= n:
@@ -178,12 +179,32 @@ def pan_scene(seed, H=736, W=1280, n_regions=200, hh_rng=(5, 10), hw_rng=(15, 37
     scale = (H * W) / float(736 * 1280)
     n = n_regions if scale >= 1 else max(2, int(round(n_regions * scale)))
     n = n_abs if n_abs is not None else n
-    rects = _place_rects(rng, H, W, n, hh_rng, hw_rng, margin=6)
+    occ = np.zeros((H, W), np.uint8)
+    # ratio-flag scenes first (they are long): up to 4 per full-size image, non-overlapping with the rest
+    longs = _place_rects(rng, H, W, 4, (14, 14), (90, 90), margin=6, occ=occ) if (H >= 200 and W >= 400) else []
+    rects = _place_rects(rng, H, W, n, hh_rng, hw_rng, margin=6, occ=occ)
     text = np.zeros((H, W), np.uint8)
     kern = np.zeros((H, W), np.uint8)
     inst = np.zeros((H, W), np.int32)
     centres = [np.zeros(4, np.float32)]
-    big_done = 0
+
+    def centre(iid):   # embedding centres on a lattice of spacing 6 in 4-d => pairwise distance >= 6
+        return np.array([(iid % 5), (iid // 5) % 5, (iid // 25) % 5, (iid // 125) % 5], np.float32) * 6.0
+
+    for (bx, by, _, _, ang) in longs:
+        # pa.pyx:42-54: one long text region holding a >= 3073-px kernel and a 3-px kernel blob
+        # (3 >= min_kernel_area 2.6 survives; 3 * 1024 < big area => both flagged)
+        iid = len(centres)
+        centres.append(centre(iid))
+        a = math.radians(ang)
+        ca, sa = math.cos(a), math.sin(a)
+        mb = np.zeros((H, W), np.uint8)
+        _fill_rect(mb, (bx, by, 90, 14, ang), 1)
+        text |= mb
+        inst[mb > 0] = iid
+        _fill_rect(kern, (bx - 10 * ca, by - 10 * sa, 75, 12, ang), 1, 0.95)
+        qx, qy = int(round(bx + 80 * ca)), int(round(by + 80 * sa))
+        kern[qy, qx - 1:qx + 2] = 1
     for r in rects:
         cx, cy, hw, hh, ang = r
         u = rng.random()
@@ -192,32 +213,14 @@ def pan_scene(seed, H=736, W=1280, n_regions=200, hh_rng=(5, 10), hw_rng=(15, 37
             a = math.radians(ang)
             d = 2 * hw - 2
             group.append((cx + d * math.cos(a), cy + d * math.sin(a), hw, hh, ang))
-        for gi, g in enumerate(group):
+        for g in group:
             iid = len(centres)
-            # embedding centres on a lattice of spacing 6 in 4-d => pairwise distance >= 6
-            c = np.array([(iid % 5), (iid // 5) % 5, (iid // 25) % 5, (iid // 125) % 5], np.float32) * 6.0
-            centres.append(c)
+            centres.append(centre(iid))
             m = np.zeros((H, W), np.uint8)
             _fill_rect(m, g, 1)
             text |= m
             inst[m > 0] = iid
-            if u < 0.02 and gi == 0 and big_done < 4 and H >= 200 and W >= 400:
-                # ratio-flag scene (pa.pyx:42-54): one long text region holding a >= 3073-px kernel and a
-                # 3-px kernel blob (3 >= min_kernel_area 2.6 survives; 3 * 1024 < big area => both flagged)
-                a = math.radians(g[4])
-                ca, sa = math.cos(a), math.sin(a)
-                bx, by = min(max(g[0], 100.0), W - 100.0), min(max(g[1], 50.0), H - 50.0)
-                trect = (bx, by, 90, 14, g[4])
-                mb = np.zeros((H, W), np.uint8)
-                _fill_rect(mb, trect, 1)
-                text |= mb
-                inst[mb > 0] = iid
-                _fill_rect(kern, (bx - 10 * ca, by - 10 * sa, 75, 12, g[4]), 1, 0.95)
-                qx, qy = int(round(bx + 80 * ca)), int(round(by + 80 * sa))
-                kern[qy, qx - 1:qx + 2] = 1
-                big_done += 1
-            else:
-                _fill_rect(kern, g, 1, 0.5)
+            _fill_rect(kern, g, 1, 0.5)
     kern &= text
     return text, kern, inst, np.stack(centres), rng
 
