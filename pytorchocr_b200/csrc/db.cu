@@ -142,14 +142,7 @@ __device__ __forceinline__ void db_scan_group(const DbParams& p, const float* v,
     run += u;
     pre[k] = run;
   }
-  unsigned inc = run;  // warp inclusive scan of the lane totals (<= 32 * kEpl * 2^23 <= 2^31)
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  const unsigned excl = inc - run;
-  const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
+  const unsigned total = __reduce_add_sync(0xffffffffu, run);  // <= 32 * kEpl * 2^23 <= 2^31
   if (xg == 0) first_bit = m[0] & 1u;
   // transitions: pixel k differs from pixel k-1 (the previous lane's last pixel for k == 0)
   unsigned tm[kEpl];
@@ -165,7 +158,9 @@ __device__ __forceinline__ void db_scan_group(const DbParams& p, const float* v,
     if (k == 0 && xg == 0) tm[k] &= ~1u;  // pixel 0 starts run 0, it is not a transition
     lanes |= tm[k];
   }
-  // emission: every lane that holds a transition stores (x << 48 | cumulative sum before x) at its rank
+  // emission: every lane that holds a transition stores (x << 48 | cumulative sum before x) at its rank.
+  // Only those (few) lanes need the sum of the lanes before them: one warp reduction per such lane
+  // instead of a full prefix scan per group.
   if (lanes) {
     unsigned multi = 0;  // lanes holding more than one transition (rare: runs shorter than kEpl pixels)
 #pragma unroll
@@ -174,6 +169,12 @@ __device__ __forceinline__ void db_scan_group(const DbParams& p, const float* v,
 #pragma unroll
       for (int q = 1; q < k; ++q) lower |= tm[q];
       multi |= tm[k] & lower;
+    }
+    unsigned excl = 0;
+    for (unsigned rest = lanes; rest; rest &= rest - 1) {
+      const int L = __ffs(rest) - 1;
+      const unsigned e = __reduce_add_sync(0xffffffffu, lane < L ? run : 0u);
+      if (lane == L) excl = e;
     }
     const unsigned long long base = carry + excl;
     if (multi == 0) {
@@ -325,14 +326,28 @@ __global__ void __launch_bounds__(kRunThreads) db_runs_kernel(DbParams p) {
       p.run_xe[r] = j + 1 < c ? (uint16_t)((e1 >> 48) - 1) : (uint16_t)(p.W - 1);
       p.run_yf[r] = (uint16_t)(y | (fg << 15));
       p.run_sum[r] = (long long)(((e1 & kCumMask) - (e0 & kCumMask)) << 9);   // 2^-23 units -> 32.32 fixed point
-      p.par[r] = rbase + j;
-      p.area[r] = 0;
-      p.xmin[r] = 0x7fffffff; p.xmax[r] = -1; p.ymax[r] = -1;
-      p.dmin[r] = 0x7fffffff; p.dmax[r] = -0x7fffffff;
-      p.smin[r] = 0x7fffffff; p.smax[r] = -0x7fffffff;
-      p.sum[r] = 0; p.fcnt[r] = 0; p.fsum[r] = 0; p.xcnt[r] = 0; p.xsum[r] = 0;
-      p.cpar[r] = -1; p.cflag[r] = 0; p.rowoff[r] = -1;
     }
+  }
+}
+
+// per-component slots live at the index of the component's ROOT run; only roots are ever read
+__device__ __forceinline__ void db_init_component(const DbParams& p, size_t r, int cflag) {
+  p.area[r] = 0;
+  p.xmin[r] = 0x7fffffff; p.xmax[r] = -1; p.ymax[r] = -1;
+  p.dmin[r] = 0x7fffffff; p.dmax[r] = -0x7fffffff;
+  p.smin[r] = 0x7fffffff; p.smax[r] = -0x7fffffff;
+  p.sum[r] = 0; p.fcnt[r] = 0; p.fsum[r] = 0; p.xcnt[r] = 0; p.xsum[r] = 0;
+  p.cpar[r] = -1; p.cflag[r] = cflag; p.rowoff[r] = -1;
+}
+
+// global-memory fallback of db_ccl_kernel, step 0: every run is its own set and owns fresh slots
+__global__ void __launch_bounds__(256) db_slots_init_kernel(DbParams p) {
+  const int n = blockIdx.y;
+  const int nr = p.nruns[n];
+  const size_t ro = (size_t)n * p.R;
+  for (int r = blockIdx.x * 256 + threadIdx.x; r < nr; r += kImgCtas * 256) {
+    p.par[ro + r] = r;
+    db_init_component(p, ro + r, 0);
   }
 }
 
@@ -501,7 +516,7 @@ __global__ void __launch_bounds__(kCclThreads) db_ccl_kernel(DbParams p) {
   }
   __syncthreads();
   for (int r = threadIdx.x; r < nr; r += kCclThreads)
-    if (s_par[r] == r && ((s_flag[r >> 5] >> (r & 31)) & 1u)) p.cflag[ro + r] = kOutFlag;
+    if (s_par[r] == r) db_init_component(p, ro + r, ((s_flag[r >> 5] >> (r & 31)) & 1u) ? kOutFlag : 0);
 }
 
 // K4b: per-component reductions from the per-run sums (no pixel is read again). One thread per run.
@@ -1181,6 +1196,8 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
     OCRPP_LAUNCHED();
     prof.mark("db_ccl");
   } else {
+    db_slots_init_kernel<<<rgrid, 256, 0, s>>>(p);
+    OCRPP_LAUNCHED();
     db_link_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
     OCRPP_LAUNCHED();
     db_flatten_kernel<<<rgrid, kRunBlk, 0, s>>>(p);

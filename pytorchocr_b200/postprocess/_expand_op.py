@@ -11,7 +11,7 @@ class ExpandOperator(object):
     R/pytocr/postprocess/pse_postprocess.py:28-53 and pan_postprocess.py:30-60."""
 
     _entry = None            # "pse" | "pan"
-    _default_boxes = 2048    # output capacity per image; doubled on OCRPP_IMG_CANDIDATES_TRUNCATED
+    _default_boxes = 512     # output capacity per image; x4 on OCRPP_IMG_CANDIDATES_TRUNCATED
 
     def _init_common(self, thresh, box_thresh, min_area, scale, out_polygon, cuda_speedup, max_runs,
                      max_boxes, maps_at_processing_res):

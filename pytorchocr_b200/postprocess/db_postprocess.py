@@ -18,7 +18,7 @@ from .. import _lib
 class DBPostProcess(object):
     def __init__(self, thresh=0.3, box_thresh=0.5, max_candidates=1000, unclip_ratio=1.5,
                  use_dilation=False, score_mode="poly", cpp_speedup=False, out_polygon=False,
-                 cuda_speedup=True, max_runs=None, **kwargs):
+                 cuda_speedup=True, max_runs=None, out_capacity=384, **kwargs):
         if not cuda_speedup:
             raise _lib.OcrppError("pytorchocr_b200 implements only the CUDA path: set PostProcess.cuda_speedup: True "
                                   "(with the flag off the reference's own DBPostProcess runs)")
@@ -37,6 +37,11 @@ class DBPostProcess(object):
         self.min_size = 3
         self.score_mode = score_mode
         self.max_runs = max_runs
+        # Output capacity per image of the device->host result block. The reference keeps up to
+        # max_candidates (1000) contours; real pages have far fewer, so the block is sized for
+        # `out_capacity` candidates and the call is repeated with the full capacity when the library
+        # reports OCRPP_IMG_CANDIDATES_TRUNCATED below it (same results, 3x less D2H traffic).
+        self.out_capacity = max(1, min(self.max_candidates, int(out_capacity or self.max_candidates)))
         self._cache = {}
 
     # -- device plumbing ------------------------------------------------------------------------
@@ -57,14 +62,13 @@ class DBPostProcess(object):
             t = t.float()
         return t
 
-    def _buffers(self, device, N, H, W, R):
+    def _buffers(self, device, N, H, W, R, cap):
         torch = _lib.require_cuda()
-        key = (str(device), N, H, W, R)
+        key = (str(device), N, H, W, R, cap)
         buf = self._cache.get(key)
         if buf is None:
             self._cache.clear()
             L = _lib.lib()
-            cap = self.max_candidates
             ws_bytes = L.ocrpp_db_workspace_bytes(N, H, W, R)
             nb, ns = N * cap * 8 * 2, N * cap * 4
             # one device block and one pinned block: [boxes i16 | scores f32 | counts i32 | status i32]
@@ -96,7 +100,7 @@ class DBPostProcess(object):
         if t.stride(3) != 1:
             t = t.contiguous()
         N, _, H, W = t.shape
-        cap = self.max_candidates
+        cap = self.out_capacity
         if N == 0:
             return (np.zeros((0, cap, 4, 2), np.int16), np.zeros((0, cap), np.float32),
                     np.zeros((0,), np.int32), np.zeros((0,), np.int32), {})
@@ -107,7 +111,7 @@ class DBPostProcess(object):
         with torch.cuda.device(t.device):
             stream = torch.cuda.current_stream()
             while True:
-                buf = self._buffers(t.device, N, H, W, R)
+                buf = self._buffers(t.device, N, H, W, R, cap)
                 o_box, o_sc, o_cnt, o_st = buf["offs"]
                 buf["wh_host"][:, 0] = torch.from_numpy(shape[:, 1].astype(np.int32))  # src_w
                 buf["wh_host"][:, 1] = torch.from_numpy(shape[:, 0].astype(np.int32))  # src_h
@@ -138,6 +142,9 @@ class DBPostProcess(object):
                     if R >= worst:
                         raise _lib.OcrppError("DB post-process: internal capacity exceeded (image too large for the unclip buffer)")
                     R = min(worst, R * 8)   # capacity retry (still the CUDA path), not a fallback
+                    continue
+                if cap < self.max_candidates and (status & _lib.IMG_CANDIDATES_TRUNCATED).any():
+                    cap = self.out_capacity = self.max_candidates
                     continue
                 break
         boxes = host[o_box:o_box + N * cap * 16].view(np.int16).reshape(N, cap, 4, 2)
