@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) db_scan_kernel(DbParams p) {
   const size_t rowid = (size_t)n * p.H + y;
   unsigned long long* sc = p.scum + rowid * (p.cap + 1);
   constexpr int PPG = 32 * kEpl;  // pixels per group
-  constexpr int U = kEpl == 1 ? 1 : 4;
+  constexpr int U = kEpl == 1 ? 1 : (kEpl * sizeof(T) > 16 ? 2 : 4);
   unsigned worst = 0;
   unsigned long long carry = 0;   // sum of all pixels of the row before this group (warp-uniform)
   unsigned carry_bit = 0;         // bit of the pixel just before this group

@@ -959,7 +959,80 @@ __global__ void __launch_bounds__(kRunThreads) ex_cand_kernel(ExParams p) {
   }
 }
 
-// E11: generate_box (pse_postprocess.py:65-105 / pan_postprocess.py:73-113), one warp per label.
+// E11: generate_box (pse_postprocess.py:65-105 / pan_postprocess.py:73-113): the area and score filters,
+// then hull -> min-area rectangle -> corner order -> rescale for labels of up to kFastRows rows, FOUR
+// labels per warp (groups of 8 lanes, 32-bit integer projections, points packed in shared memory).
+constexpr int kFastRows = 128;
+constexpr int kGeoThreads = 128;
+
+__device__ __forceinline__ void ex_emit_box(const ExParams& p, int n, size_t ko, const geom::Rect& rect, float score) {
+  double bx[4], by[4];
+  geom::cv_box_order(rect, bx, by);  // corner order of cv2.boxPoints
+  float cx[4], cy[4], ox[4], oy[4];
+  for (int q = 0; q < 4; ++q) {
+    cx[q] = (float)bx[q];
+    cy[q] = (float)by[q];
+  }
+  geom::order_points_clockwise(cx, cy, ox, oy);  // utility.py:21-29
+  const double src_h = p.shape[4 * n + 0], src_w = p.shape[4 * n + 1];
+  const double ratio_h = p.shape[4 * n + 2], ratio_w = p.shape[4 * n + 3];
+  for (int q = 0; q < 4; ++q) {  // :100-102 (float64 division under numpy 2, np.round = half to even)
+    const double fx = (double)ox[q] / ratio_w, fy = (double)oy[q] / ratio_h;
+    p.res_boxf[ko * 8 + 2 * q] = (float)fx;
+    p.res_boxf[ko * 8 + 2 * q + 1] = (float)fy;
+    p.res_box[ko * 8 + 2 * q] = (int16_t)(int)fmin(fmax(geom::round_half_even(fx), 0.0), src_w);
+    p.res_box[ko * 8 + 2 * q + 1] = (int16_t)(int)fmin(fmax(geom::round_half_even(fy), 0.0), src_h);
+  }
+  p.res_score[ko] = score;
+  p.res_keep[ko] = 1;
+}
+
+__global__ void __launch_bounds__(kGeoThreads) ex_geometry_fast_kernel(ExParams p) {
+  constexpr int kGroups = kGeoThreads / kGrp;
+  __shared__ int s_a[kGroups][2 * kFastRows];
+  __shared__ int s_b[kGroups][2 * kFastRows + 2];
+  const int n = blockIdx.y;
+  const int g = threadIdx.x / kGrp, gl = threadIdx.x % kGrp;
+  const unsigned gmask = ((1u << kGrp) - 1u) << ((threadIdx.x & 31) / kGrp * kGrp);
+  const int k = blockIdx.x * kGroups + g;
+  if (k >= p.ncand[n]) return;
+  const size_t so = (size_t)n * p.R;
+  const size_t ko = (size_t)n * p.maxc + k;
+  const int c = p.cand[ko];
+  const int f = p.fout;
+  const long long area = (long long)p.l_area[so + c] * f * f;  // label upsampled by fout (:58-62)
+  int verdict = -1;                                            // 0 drop, 2 defer, -1 go on
+  if ((double)area < (double)p.min_area_box) verdict = 0;      // points.shape[0] < min_area (:75)
+  // np.mean(score[ind]) (:79): float32 pairwise sum in the reference, exact fixed point here
+  const float score = (float)(((double)p.l_sum[so + c] / kFix) / (double)p.l_area[so + c]);
+  if (verdict < 0 && score < p.box_thresh) verdict = 0;        // :80
+  const int ymin = p.l_ymin[so + c], nrows = p.l_ymax[so + c] - ymin + 1;
+  const int off = p.l_rowoff[so + c];
+  if (verdict < 0 && (f != 1 || nrows > kFastRows || off < 0 || p.W >= 16384 || p.H >= 16384)) verdict = 2;
+  if (verdict >= 0) {
+    if (gl == 0) p.res_keep[ko] = verdict;
+    return;
+  }
+  const int32_t* ext_l = p.ext_l + (size_t)n * p.E + off;
+  const int32_t* ext_r = p.ext_r + (size_t)n * p.E + off;
+  int* A = s_a[g];
+  int* B = s_b[g];
+  for (int i = gl; i < nrows; i += kGrp) {
+    A[2 * i] = pk(ext_l[i], ymin + i);
+    A[2 * i + 1] = pk(ext_r[i], ymin + i);
+  }
+  __syncwarp(gmask);
+  int hn = 0;
+  if (gl == 0) hn = hull_sorted32(A, 2 * nrows, B);
+  hn = __shfl_sync(gmask, hn, 0, kGrp);
+  __syncwarp(gmask);
+  geom::Rect rect;
+  group_min_area_rect(B, hn, &rect, gl, gmask);   // cv2.minAreaRect + boxPoints (:85-86)
+  if (gl == 0) ex_emit_box(p, n, ko, rect, score);
+}
+
+// E11b: generate_box for the candidates the fast kernel below defers (more than kFastRows rows, an
+// up-sampled label map, or coordinates beyond the packed 16-bit range), one warp per label.
 constexpr int kGeoWarps = 4;
 constexpr int kSmallRows = 64;
 
@@ -974,12 +1047,10 @@ __global__ void __launch_bounds__(kGeoWarps * 32) ex_geometry_kernel(ExParams p)
   for (int k = blockIdx.x * kGeoWarps + wib; k < nc; k += gridDim.x * kGeoWarps) {
     const size_t ko = (size_t)n * p.maxc + k;
     const int c = p.cand[ko];
+    if (p.res_keep[ko] != 2) continue;   // decided by ex_geometry_fast_kernel
+    __syncwarp();
     if (lane == 0) p.res_keep[ko] = 0;
-    const long long area = (long long)p.l_area[so + c] * f * f;  // label upsampled by fout (:58-62)
-    if ((double)area < (double)p.min_area_box) continue;         // points.shape[0] < min_area (:75)
-    // np.mean(score[ind]) (:79): float32 pairwise sum in the reference, exact fixed point here
     const float score = (float)(((double)p.l_sum[so + c] / kFix) / (double)p.l_area[so + c]);
-    if (score < p.box_thresh) continue;                           // :80
     const int off = p.l_rowoff[so + c];
     if (off < 0) continue;  // extent arena exhausted: flagged in ex_cand_kernel
     const int ymin = p.l_ymin[so + c], nrows = p.l_ymax[so + c] - ymin + 1;
@@ -1013,27 +1084,7 @@ __global__ void __launch_bounds__(kGeoWarps * 32) ex_geometry_kernel(ExParams p)
     __syncwarp();
     geom::Rect rect;
     warp_min_area_rect(hull, hn, &rect, lane);  // cv2.minAreaRect + boxPoints (:85-86)
-    if (lane == 0) {
-      double bx[4], by[4];
-      geom::cv_box_order(rect, bx, by);  // corner order of cv2.boxPoints
-      float cx[4], cy[4], ox[4], oy[4];
-      for (int q = 0; q < 4; ++q) {
-        cx[q] = (float)bx[q];
-        cy[q] = (float)by[q];
-      }
-      geom::order_points_clockwise(cx, cy, ox, oy);  // utility.py:21-29
-      const double src_h = p.shape[4 * n + 0], src_w = p.shape[4 * n + 1];
-      const double ratio_h = p.shape[4 * n + 2], ratio_w = p.shape[4 * n + 3];
-      for (int q = 0; q < 4; ++q) {  // :100-102 (float64 division under numpy 2, np.round = half to even)
-        const double fx = (double)ox[q] / ratio_w, fy = (double)oy[q] / ratio_h;
-        p.res_boxf[ko * 8 + 2 * q] = (float)fx;
-        p.res_boxf[ko * 8 + 2 * q + 1] = (float)fy;
-        p.res_box[ko * 8 + 2 * q] = (int16_t)(int)fmin(fmax(geom::round_half_even(fx), 0.0), src_w);
-        p.res_box[ko * 8 + 2 * q + 1] = (int16_t)(int)fmin(fmax(geom::round_half_even(fy), 0.0), src_h);
-      }
-      p.res_score[ko] = score;
-      p.res_keep[ko] = 1;
-    }
+    if (lane == 0) ex_emit_box(p, n, ko, rect, score);
   }
 }
 
@@ -1225,7 +1276,9 @@ int ex_launch(ExParams& p, cudaStream_t s, bool vec) {
   ex_stats_kernel<T, 2><<<rgrid, kRunBlk, 0, s>>>(p);
   OCRPP_LAUNCHED();
   prof.mark("ex_extents");
-  ex_geometry_kernel<<<dim3(16, N), kGeoWarps * 32, 0, s>>>(p);
+  ex_geometry_fast_kernel<<<dim3((p.maxc + kGeoThreads / kGrp - 1) / (kGeoThreads / kGrp), N), kGeoThreads, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  ex_geometry_kernel<<<dim3(4, N), kGeoWarps * 32, 0, s>>>(p);
   OCRPP_LAUNCHED();
   prof.mark("ex_geometry");
   ex_compact_kernel<<<N, kRunThreads, 0, s>>>(p);
