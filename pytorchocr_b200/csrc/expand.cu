@@ -1208,6 +1208,28 @@ void ex_fill(ExParams& p, int mode, int N, int C, int K, int h, int w, int fin, 
   p.arena_cap = ex_resolve_arena(N, p.H, p.W, arena_elems);
 }
 
+// auxiliary streams / events of the current device (created once, never destroyed)
+struct ExAux {
+  cudaStream_t st[3];
+  cudaEvent_t fork, join[3];
+};
+
+ExAux* ex_aux() {
+  static ExAux aux[64];
+  static bool ready[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!ready[dev]) {
+    for (int i = 0; i < 3; ++i) {
+      if (cudaStreamCreateWithFlags(&aux[dev].st[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&aux[dev].join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&aux[dev].fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ready[dev] = true;
+  }
+  return &aux[dev];
+}
+
 template <typename T>
 int ex_launch(ExParams& p, cudaStream_t s, bool vec) {
   OCRPP_CUDA(cudaMemsetAsync(p.g_nwork, 0, sizeof(int32_t) * 64, s));
@@ -1255,16 +1277,24 @@ int ex_launch(ExParams& p, cudaStream_t s, bool vec) {
       OCRPP_CUDA(cudaFuncSetAttribute(big_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem_bytes(kBigCap, kListCap)));
       attr_set = true;
     }
+    // The four tile classes are independent persistent kernels: fork them onto auxiliary streams so that
+    // the tail of one (a few long items) overlaps the bulk of the next, and join before the statistics.
+    ExAux* aux = ex_aux();
+    OCRPP_CHECK_ARG(aux != nullptr, "expand: cannot create auxiliary streams");
+    OCRPP_CUDA(cudaEventRecord(aux->fork, s));
+    for (int i = 0; i < 3; ++i) OCRPP_CUDA(cudaStreamWaitEvent(aux->st[i], aux->fork, 0));
     huge_k<<<kNumSMs, kHugeThreads, ex_smem_bytes(kHugeCap, kListCap), s>>>(p);   // long items first
     OCRPP_LAUNCHED();
-    big_k<<<kNumSMs * 2, kBigThreads, ex_smem_bytes(kBigCap, kListCap), s>>>(p);
+    big_k<<<kNumSMs * 2, kBigThreads, ex_smem_bytes(kBigCap, kListCap), aux->st[0]>>>(p);
     OCRPP_LAUNCHED();
-    prof.mark("ex_expand_big");
-    small_k<<<kNumSMs * 4, kSmallThreads, ex_smem_bytes(kSmallCap, kListCap), s>>>(p);
+    small_k<<<kNumSMs * 4, kSmallThreads, ex_smem_bytes(kSmallCap, kListCap), aux->st[1]>>>(p);
     OCRPP_LAUNCHED();
-    prof.mark("ex_expand_small");
-    tiny_k<<<kNumSMs * 9, kTinyThreads, ex_smem_bytes(kTinyCap, kTinyList), s>>>(p);
+    tiny_k<<<kNumSMs * 9, kTinyThreads, ex_smem_bytes(kTinyCap, kTinyList), aux->st[2]>>>(p);
     OCRPP_LAUNCHED();
+    for (int i = 0; i < 3; ++i) {
+      OCRPP_CUDA(cudaEventRecord(aux->join[i], aux->st[i]));
+      OCRPP_CUDA(cudaStreamWaitEvent(s, aux->join[i], 0));
+    }
   }
   prof.mark("ex_expand");
   ex_stats_kernel<T, 1><<<rgrid, kRunBlk, 0, s>>>(p);
