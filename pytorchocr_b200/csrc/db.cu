@@ -272,7 +272,7 @@ struct BitView {
 // kImgCtas CTAs per image: each scans the row counts (cheap) and converts its share of the rows.
 // ------------------------------------------------------------------------------------------------
 constexpr int kRunThreads = 512;
-constexpr int kImgCtas = 8;       // CTAs per image for the run-parallel kernels
+constexpr int kImgCtas = 8;       // minimum CTAs per image for the run-parallel kernels (more for small batches)
 
 __global__ void __launch_bounds__(kRunThreads) db_runs_kernel(DbParams p) {
   extern __shared__ int s_rowptr[];  // [H+1]
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kRunThreads) db_runs_kernel(DbParams p) {
     if (threadIdx.x == 0) p.nruns[n] = total;
   }
   const size_t ro = (size_t)n * p.R;
-  for (int y = blockIdx.x * nw + warp; y < p.H; y += kImgCtas * nw) {
+  for (int y = blockIdx.x * nw + warp; y < p.H; y += gridDim.x * nw) {
     const int rbase = s_rowptr[y];
     const int c = rc[y] & 0x7fffffff;
     const int first = (unsigned)rc[y] >> 31;
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256) db_slots_init_kernel(DbParams p) {
   const int n = blockIdx.y;
   const int nr = p.nruns[n];
   const size_t ro = (size_t)n * p.R;
-  for (int r = blockIdx.x * 256 + threadIdx.x; r < nr; r += kImgCtas * 256) {
+  for (int r = blockIdx.x * 256 + threadIdx.x; r < nr; r += gridDim.x * 256) {
     p.par[ro + r] = r;
     db_init_component(p, ro + r, 0);
   }
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(256) db_slots_init_kernel(DbParams p) {
 
 constexpr int kRunBlk = 256;
 
-#define FOR_EACH_RUN(r, nr) for (int r = blockIdx.x * kRunBlk + threadIdx.x; r < (nr); r += kImgCtas * kRunBlk)
+#define FOR_EACH_RUN(r, nr) for (int r = blockIdx.x * kRunBlk + threadIdx.x; r < (nr); r += gridDim.x * kRunBlk)
 
 // K3: link every run with the overlapping same-polarity runs of the row above
 // (foreground: 8-connectivity => overlap of [xs-1, xe+1]; background: 4-connectivity => [xs, xe]).
@@ -1181,10 +1181,11 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
     OCRPP_LAUNCHED();
     prof.mark("db_scan");
   }
-  db_runs_kernel<<<dim3(kImgCtas, N), kRunThreads, sizeof(int) * (H + 1), s>>>(p);
+  const int ictas = max(kImgCtas, min(64, (kNumSMs * 4 + N - 1) / N));   // fill the GPU at small batch sizes too
+  db_runs_kernel<<<dim3(ictas, N), kRunThreads, sizeof(int) * (H + 1), s>>>(p);
   OCRPP_LAUNCHED();
   prof.mark("db_runs");
-  dim3 rgrid(kImgCtas, N);
+  dim3 rgrid(ictas, N);
   const size_t ccl_smem = sizeof(int) * ((size_t)p.R + (p.R + 31) / 32 + 1);
   if (ccl_smem <= 200 * 1024) {
     static bool attr_set = false;   // opt in to > 48 KB of dynamic shared memory once

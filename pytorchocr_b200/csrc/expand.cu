@@ -57,6 +57,7 @@ struct ExParams {
   uint32_t* st;     // [N][H*W]
   uint32_t* bits;   // [N][2][H*Wd]
   int32_t* rowptr;  // [N][2][H+1]
+  int32_t* rowcnt;  // [N][2][H] run starts per row, written by ex_binarize_kernel
   uint16_t *run_xs, *run_xe, *run_y;  // [N][2][R]
   int32_t* par;     // [N][2][R]
   // text-root slots [N][R]
@@ -118,6 +119,8 @@ __global__ void __launch_bounds__(kBinWarps * 32) ex_binarize_kernel(ExParams p)
   uint32_t* tb = p.bits + ((size_t)(n * 2 + 0) * p.H + y) * p.Wd;
   uint32_t* sb = p.bits + ((size_t)(n * 2 + 1) * p.H + y) * p.Wd;
   const int K = p.K;
+  unsigned tprev = 0, sprev = 0;   // last word of the previous 128-pixel group (run starts need its top bit)
+  int tcnt = 0, scnt = 0;          // run starts of this row, counted by the lanes that own a word
   for (int x0 = 0; x0 < p.W; x0 += 128) {
     const int x = x0 + lane * 4;
     unsigned b[4] = {0u, 0u, 0u, 0u};
@@ -166,15 +169,32 @@ __global__ void __launch_bounds__(kBinWarps * 32) ex_binarize_kernel(ExParams p)
       sw |= __shfl_xor_sync(0xffffffffu, sw, o);
     }
     const int wi = (x0 >> 5) + (lane >> 3);
+    // word before mine: the previous owner lane's word, or the last word of the previous group
+    unsigned tp = __shfl_up_sync(0xffffffffu, tw, 8), sp = __shfl_up_sync(0xffffffffu, sw, 8);
+    if (lane < 8) {
+      tp = tprev;
+      sp = sprev;
+    }
     if ((lane & 7) == 0 && wi < p.Wd) {
       tb[wi] = tw;
       sb[wi] = sw;
+      tcnt += __popc(tw & ~((tw << 1) | (tp >> 31)));
+      scnt += __popc(sw & ~((sw << 1) | (sp >> 31)));
     }
+    tprev = __shfl_sync(0xffffffffu, tw, 24);
+    sprev = __shfl_sync(0xffffffffu, sw, 24);
+  }
+  tcnt = __reduce_add_sync(0xffffffffu, tcnt);
+  scnt = __reduce_add_sync(0xffffffffu, scnt);
+  if (lane == 0) {
+    p.rowcnt[(size_t)(n * 2 + 0) * p.H + y] = tcnt;
+    p.rowcnt[(size_t)(n * 2 + 1) * p.H + y] = scnt;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// E2: 1-bit mask -> table of foreground runs in raster order. One CTA per (image, mask).
+// E2: 1-bit mask -> table of foreground runs in raster order (row counts come from ex_binarize_kernel).
+// Several CTAs per (image, mask).
 // ------------------------------------------------------------------------------------------------
 constexpr int kRunThreads = 512;
 
@@ -183,50 +203,42 @@ __device__ __forceinline__ unsigned run_ends(unsigned w, unsigned next) { return
 
 __global__ void __launch_bounds__(kRunThreads) ex_runs_kernel(ExParams p) {
   extern __shared__ int s_rowcnt[];  // [H+1]
-  const int n = blockIdx.x, m = blockIdx.y;
+  const int n = blockIdx.y, m = blockIdx.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kRunThreads / 32;
   const uint32_t* bits = p.bits + (size_t)(n * 2 + m) * p.H * p.Wd;
+  const int32_t* rc = p.rowcnt + (size_t)(n * 2 + m) * p.H;
   int32_t* rowptr = p.rowptr + (size_t)(n * 2 + m) * (p.H + 1);
   const size_t ro = (size_t)(n * 2 + m) * p.R;
   const size_t so = (size_t)n * p.R;
-
-  for (int y = warp; y < p.H; y += nw) {
-    int c = 0;
-    for (int k = lane; k < p.Wd; k += 32) {
-      const unsigned w = bits[(size_t)y * p.Wd + k];
-      const unsigned pw = k > 0 ? bits[(size_t)y * p.Wd + k - 1] : 0u;
-      c += __popc(run_starts(w, pw));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0) s_rowcnt[y] = c;
-  }
-  __syncthreads();
+  // every CTA of the image scans the row counts (cheap); each converts its share of the rows
   const int chunk = (p.H + kRunThreads - 1) / kRunThreads;
   const int y0 = threadIdx.x * chunk, y1 = min(p.H, y0 + chunk);
   int local = 0;
-  for (int y = y0; y < y1; ++y) local += s_rowcnt[y];
+  for (int y = y0; y < y1; ++y) local += rc[y];
   int total;
   int base = block_exclusive_scan(local, &total);
   for (int y = y0; y < y1; ++y) {
-    const int c = s_rowcnt[y];
     s_rowcnt[y] = base;
-    base += c;
+    base += rc[y];
   }
   if (threadIdx.x == 0) s_rowcnt[p.H] = total;
   __syncthreads();
   if (total > p.R) {
-    if (threadIdx.x == 0) {
-      atomicOr(&p.imgflags[n], OCRPP_IMG_RUN_OVERFLOW);
-      p.nruns[n * 2 + m] = 0;
+    if (blockIdx.x == 0) {
+      if (threadIdx.x == 0) {
+        atomicOr(&p.imgflags[n], OCRPP_IMG_RUN_OVERFLOW);
+        p.nruns[n * 2 + m] = 0;
+      }
+      for (int y = threadIdx.x; y <= p.H; y += kRunThreads) rowptr[y] = 0;
     }
-    for (int y = threadIdx.x; y <= p.H; y += kRunThreads) rowptr[y] = 0;
     return;
   }
-  for (int y = threadIdx.x; y <= p.H; y += kRunThreads) rowptr[y] = s_rowcnt[y];
-  if (threadIdx.x == 0) p.nruns[n * 2 + m] = total;
+  if (blockIdx.x == 0) {
+    for (int y = threadIdx.x; y <= p.H; y += kRunThreads) rowptr[y] = s_rowcnt[y];
+    if (threadIdx.x == 0) p.nruns[n * 2 + m] = total;
+  }
 
-  for (int y = warp; y < p.H; y += nw) {
+  for (int y = blockIdx.x * nw + warp; y < p.H; y += gridDim.x * nw) {
     const int rbase = s_rowcnt[y];
     int carry_s = 0, carry_e = 0;
     for (int k0 = 0; k0 < p.Wd; k0 += 32) {
@@ -282,9 +294,9 @@ __global__ void __launch_bounds__(kRunThreads) ex_runs_kernel(ExParams p) {
   }
 }
 
-constexpr int kImgCtas = 8;
+constexpr int kImgCtas = 8;   // minimum CTAs per image of the run-parallel kernels (more for small batches)
 constexpr int kRunBlk = 256;
-#define EX_FOR_EACH_RUN(r, nr) for (int r = blockIdx.x * kRunBlk + threadIdx.x; r < (nr); r += kImgCtas * kRunBlk)
+#define EX_FOR_EACH_RUN(r, nr) for (int r = blockIdx.x * kRunBlk + threadIdx.x; r < (nr); r += gridDim.x * kRunBlk)
 
 // E3: 4-connectivity: link every run with the runs of the row above that overlap [xs, xe].
 __global__ void __launch_bounds__(kRunBlk) ex_link_kernel(ExParams p) {
@@ -425,7 +437,7 @@ __global__ void __launch_bounds__(kRunBlk) ex_paint_kernel(ExParams p, int m) {
   const size_t ro = (size_t)(n * 2 + m) * p.R, so = (size_t)n * p.R;
   uint32_t* st = p.st + (size_t)n * p.H * p.W;
   const int lane = threadIdx.x & 31, wpb = kRunBlk / 32;
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < nr; r += kImgCtas * wpb) {
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < nr; r += gridDim.x * wpb) {
     const int root = p.par[ro + r];
     uint32_t v;
     if (m == 0) {
@@ -872,7 +884,7 @@ __global__ void __launch_bounds__(kRunBlk) ex_stats_kernel(ExParams p) {
   const size_t ro = (size_t)(n * 2 + 0) * p.R, so = (size_t)n * p.R;
   const uint32_t* st = p.st + (size_t)n * p.H * p.W;
   const int lane = threadIdx.x & 31, wpb = kRunBlk / 32;
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < nr; r += kImgCtas * wpb) {
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < nr; r += gridDim.x * wpb) {
     if (!p.t_seen[so + p.par[ro + r]]) continue;
     const int y = p.run_y[ro + r], a = p.run_xs[ro + r], b = p.run_xe[ro + r];
     for (int xb = a; xb <= b; xb += 32) {
@@ -1123,7 +1135,7 @@ __global__ void __launch_bounds__(kRunBlk) ex_labels_kernel(ExParams p) {
   const uint32_t* st = p.st + (size_t)n * p.H * p.W;
   int32_t* lab = p.labels_dbg + (size_t)n * p.H * p.W;
   const int lane = threadIdx.x & 31, wpb = kRunBlk / 32;
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < nr; r += kImgCtas * wpb) {
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < nr; r += gridDim.x * wpb) {
     if (!p.t_seen[so + p.par[ro + r]]) continue;
     const size_t row = (size_t)p.run_y[ro + r] * p.W;
     for (int x = p.run_xs[ro + r] + lane; x <= (int)p.run_xe[ro + r]; x += 32) {
@@ -1147,6 +1159,7 @@ size_t ex_carve(ExParams& p, void* ws) {
   p.st = c.take<uint32_t>(N * HW);
   p.bits = c.take<uint32_t>(N * 2 * p.H * p.Wd);
   p.rowptr = c.take<int32_t>(N * 2 * (p.H + 1));
+  p.rowcnt = c.take<int32_t>(N * 2 * p.H);
   p.run_xs = c.take<uint16_t>(N * 2 * R);
   p.run_xe = c.take<uint16_t>(N * 2 * R);
   p.run_y = c.take<uint16_t>(N * 2 * R);
@@ -1243,10 +1256,11 @@ int ex_launch(ExParams& p, cudaStream_t s, bool vec) {
     OCRPP_LAUNCHED();
     prof.mark("ex_binarize");
   }
-  ex_runs_kernel<<<dim3(N, 2), kRunThreads, sizeof(int) * (p.H + 1), s>>>(p);
+  const int ictas = max(kImgCtas, min(64, (kNumSMs * 4 + N - 1) / N));   // fill the GPU at small batch sizes too
+  ex_runs_kernel<<<dim3(ictas, N, 2), kRunThreads, sizeof(int) * (p.H + 1), s>>>(p);
   OCRPP_LAUNCHED();
   prof.mark("ex_runs");
-  const dim3 rgrid2(kImgCtas, N, 2), rgrid(kImgCtas, N);
+  const dim3 rgrid2(ictas, N, 2), rgrid(ictas, N);
   ex_link_kernel<<<rgrid2, kRunBlk, 0, s>>>(p);
   OCRPP_LAUNCHED();
   prof.mark("ex_link");
