@@ -211,11 +211,16 @@ __device__ __forceinline__ void db_scan_group(const DbParams& p, const float* v,
   }
   carry += total;
   carry_bit = m[kEpl - 1] >> 31;
-  if (lane < kEpl) {
-    unsigned w = m[0];
-#pragma unroll
-    for (int k = 1; k < kEpl; ++k) w = lane == k ? m[k] : w;
-    out[(xg / PPG) * kEpl + lane] = w;
+  if (lane == 0) {   // rows of the mask are 32-byte aligned: one vector store per group
+    uint32_t* o = out + (xg / PPG) * kEpl;
+    if (kEpl == 4) {
+      *reinterpret_cast<uint4*>(o) = make_uint4(m[0], m[1 % kEpl], m[2 % kEpl], m[3 % kEpl]);
+    } else if (kEpl == 8) {
+      *reinterpret_cast<uint4*>(o) = make_uint4(m[0], m[1 % kEpl], m[2 % kEpl], m[3 % kEpl]);
+      *reinterpret_cast<uint4*>(o + 4) = make_uint4(m[4 % kEpl], m[5 % kEpl], m[6 % kEpl], m[7 % kEpl]);
+    } else {
+      o[0] = m[0];
+    }
   }
 }
 
@@ -237,17 +242,22 @@ __global__ void __launch_bounds__(kBinWarps * 32) db_scan_kernel(DbParams p) {
   int cnt = 1;                    // run 0 starts at x = 0
   unsigned first_bit = 0;
   if (lane == 0) sc[0] = 0ull;   // run 0: x = 0, nothing before it
-  for (int x0 = 0; x0 < p.W; x0 += PPG * U) {
+  // main loop: U full groups per iteration, all loads issued first, no per-group bounds checks
+  int x0 = 0;
+  for (; x0 + PPG * U <= p.W; x0 += PPG * U) {
     float v[U][kEpl];
 #pragma unroll
     for (int u = 0; u < U; ++u) RowLoader<T, kEpl>::load(row, x0 + u * PPG + lane * kEpl, p.W, v[u]);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int xg = x0 + u * PPG;          // first pixel of the group (warp-uniform)
-      if (xg >= p.W) break;
-      if (xg + PPG <= p.W) db_scan_group<kEpl, true>(p, v[u], xg, lane, sc, out, carry, carry_bit, cnt, first_bit, worst);
-      else db_scan_group<kEpl, false>(p, v[u], xg, lane, sc, out, carry, carry_bit, cnt, first_bit, worst);
-    }
+    for (int u = 0; u < U; ++u)
+      db_scan_group<kEpl, true>(p, v[u], x0 + u * PPG, lane, sc, out, carry, carry_bit, cnt, first_bit, worst);
+  }
+  // tail: the remaining (fewer than U) groups, the last of them possibly partial
+  for (; x0 < p.W; x0 += PPG) {
+    float v[kEpl];
+    RowLoader<T, kEpl>::load(row, x0 + lane * kEpl, p.W, v);
+    if (x0 + PPG <= p.W) db_scan_group<kEpl, true>(p, v, x0, lane, sc, out, carry, carry_bit, cnt, first_bit, worst);
+    else db_scan_group<kEpl, false>(p, v, x0, lane, sc, out, carry, carry_bit, cnt, first_bit, worst);
   }
   if (lane == 0) {
     p.srow_cnt[rowid] = cnt | (first_bit << 31);
@@ -1188,11 +1198,8 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
   dim3 rgrid(ictas, N);
   const size_t ccl_smem = sizeof(int) * ((size_t)p.R + (p.R + 31) / 32 + 1);
   if (ccl_smem <= 200 * 1024) {
-    static bool attr_set = false;   // opt in to > 48 KB of dynamic shared memory once
-    if (!attr_set) {
-      OCRPP_CUDA(cudaFuncSetAttribute(db_ccl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
-    }
+    // opt in to > 48 KB of dynamic shared memory (a per-device function attribute: set on every call)
+    OCRPP_CUDA(cudaFuncSetAttribute(db_ccl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     db_ccl_kernel<<<N, kCclThreads, ccl_smem, s>>>(p);
     OCRPP_LAUNCHED();
     prof.mark("db_ccl");

@@ -1280,17 +1280,14 @@ int ex_launch(ExParams& p, cudaStream_t s, bool vec) {
   OCRPP_LAUNCHED();
   prof.mark("ex_paint");
   {
-    static bool attr_set = false;   // opt in to > 48 KB of dynamic shared memory once per instantiation
     auto tiny_k = ex_expand_kernel<T, kTinyCap, kTinyList, kTinyThreads, 0>;
     auto small_k = ex_expand_kernel<T, kSmallCap, kListCap, kSmallThreads, 1>;
     auto big_k = ex_expand_kernel<T, kBigCap, kListCap, kBigThreads, 2>;
     auto huge_k = ex_expand_kernel<T, kHugeCap, kListCap, kHugeThreads, 3>;
-    if (!attr_set) {
-      OCRPP_CUDA(cudaFuncSetAttribute(huge_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem_bytes(kHugeCap, kListCap)));
-      OCRPP_CUDA(cudaFuncSetAttribute(small_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem_bytes(kSmallCap, kListCap)));
-      OCRPP_CUDA(cudaFuncSetAttribute(big_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem_bytes(kBigCap, kListCap)));
-      attr_set = true;
-    }
+    // opt in to > 48 KB of dynamic shared memory (a per-device function attribute: set on every call)
+    OCRPP_CUDA(cudaFuncSetAttribute(huge_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem_bytes(kHugeCap, kListCap)));
+    OCRPP_CUDA(cudaFuncSetAttribute(small_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem_bytes(kSmallCap, kListCap)));
+    OCRPP_CUDA(cudaFuncSetAttribute(big_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem_bytes(kBigCap, kListCap)));
     // The four tile classes are independent persistent kernels: fork them onto auxiliary streams so that
     // the tail of one (a few long items) overlaps the bulk of the next, and join before the statistics.
     ExAux* aux = ex_aux();
