@@ -22,6 +22,8 @@
 // probabilities >= 2^-9, order independent => deterministic). Algorithmic bytes per image:
 // H*W*sizeof(elem), the probability map, read once by db_scan_kernel.
 #include "common.cuh"
+
+#include <cstdlib>
 #include "dev_common.cuh"
 #include "dev_geom.cuh"
 #include "geometry.cuh"
@@ -39,7 +41,7 @@ struct DbParams {
   const void* maps;
   long long stride_n, stride_h;
   const int32_t* src_wh;
-  int N, H, W, Wd, R, maxc, cap, epl;
+  int N, H, W, Wd, R, maxc, cap, epl, n0;   // n0: first image of the sub-batch this launch covers
   float thresh, box_thresh, unclip_ratio;
   // per-image workspace (index with n * count)
   uint32_t* bits;        // [H*Wd] lane-major bit mask (see db_scan_kernel)
@@ -226,7 +228,7 @@ __device__ __forceinline__ void db_scan_group(const DbParams& p, const float* v,
 
 template <typename T, int kEpl>
 __global__ void __launch_bounds__(kBinWarps * 32) db_scan_kernel(DbParams p) {
-  const int n = blockIdx.y;
+  const int n = blockIdx.y + p.n0;
   const int y = blockIdx.x * kBinWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (y >= p.H) return;
@@ -286,7 +288,7 @@ constexpr int kImgCtas = 8;       // minimum CTAs per image for the run-parallel
 
 __global__ void __launch_bounds__(kRunThreads) db_runs_kernel(DbParams p) {
   extern __shared__ int s_rowptr[];  // [H+1]
-  const int n = blockIdx.y;
+  const int n = blockIdx.y + p.n0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kRunThreads / 32;
   const int32_t* rc = p.srow_cnt + (size_t)n * p.H;
   int32_t* rowptr = p.rowptr + (size_t)n * (p.H + 1);
@@ -352,7 +354,7 @@ __device__ __forceinline__ void db_init_component(const DbParams& p, size_t r, i
 
 // global-memory fallback of db_ccl_kernel, step 0: every run is its own set and owns fresh slots
 __global__ void __launch_bounds__(256) db_slots_init_kernel(DbParams p) {
-  const int n = blockIdx.y;
+  const int n = blockIdx.y + p.n0;
   const int nr = p.nruns[n];
   const size_t ro = (size_t)n * p.R;
   for (int r = blockIdx.x * 256 + threadIdx.x; r < nr; r += gridDim.x * 256) {
@@ -368,7 +370,7 @@ constexpr int kRunBlk = 256;
 // K3: link every run with the overlapping same-polarity runs of the row above
 // (foreground: 8-connectivity => overlap of [xs-1, xe+1]; background: 4-connectivity => [xs, xe]).
 __global__ void __launch_bounds__(kRunBlk) db_link_kernel(DbParams p) {
-  const int n = blockIdx.y;
+  const int n = blockIdx.y + p.n0;
   const int nr = p.nruns[n];
   const size_t ro = (size_t)n * p.R;
   const int32_t* rowptr = p.rowptr + (size_t)n * (p.H + 1);
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(kRunBlk) db_link_kernel(DbParams p) {
 
 // K4a: flatten; background runs touching the frame mark their region as OUT.
 __global__ void __launch_bounds__(kRunBlk) db_flatten_kernel(DbParams p) {
-  const int n = blockIdx.y;
+  const int n = blockIdx.y + p.n0;
   const int nr = p.nruns[n];
   const size_t ro = (size_t)n * p.R;
   const uint16_t *xs = p.run_xs + ro, *xe = p.run_xe + ro, *yf = p.run_yf + ro;
@@ -442,7 +444,7 @@ __device__ __forceinline__ void uf_union_s(int* par, int a, int b) {
 
 __global__ void __launch_bounds__(kCclThreads) db_ccl_kernel(DbParams p) {
   extern __shared__ int s_par[];  // [R] parents, then [R/32+1] words of per-run / per-root flags
-  const int n = blockIdx.x;
+  const int n = blockIdx.x + p.n0;
   const int nr = p.nruns[n];
   const size_t ro = (size_t)n * p.R;
   const int32_t* rowptr = p.rowptr + (size_t)n * (p.H + 1);
@@ -531,7 +533,7 @@ __global__ void __launch_bounds__(kCclThreads) db_ccl_kernel(DbParams p) {
 
 // K4b: per-component reductions from the per-run sums (no pixel is read again). One thread per run.
 __global__ void __launch_bounds__(kRunBlk) db_stats_kernel(DbParams p) {
-  const int n = blockIdx.y;
+  const int n = blockIdx.y + p.n0;
   const int nr = p.nruns[n];
   const size_t ro = (size_t)n * p.R;
   const uint16_t *xs = p.run_xs + ro, *xe = p.run_xe + ro, *yf = p.run_yf + ro;
@@ -573,7 +575,7 @@ __device__ __forceinline__ bool is_candidate_root(const DbParams& p, size_t ro, 
 
 // K5: parent links of the component tree + row-extent slot allocation, one thread per candidate root.
 __global__ void __launch_bounds__(kRunBlk) db_tree_kernel(DbParams p) {
-  const int n = blockIdx.y;
+  const int n = blockIdx.y + p.n0;
   const int nr = p.nruns[n];
   const size_t ro = (size_t)n * p.R;
   const int32_t* rowptr = p.rowptr + (size_t)n * (p.H + 1);
@@ -608,7 +610,7 @@ __global__ void __launch_bounds__(kRunBlk) db_tree_kernel(DbParams p) {
 
 // K6: every candidate adds its own (count, sum) to all its ancestors: fill = own + descendants.
 __global__ void __launch_bounds__(kRunBlk) db_fill_kernel(DbParams p) {
-  const int n = blockIdx.y;
+  const int n = blockIdx.y + p.n0;
   const int nr = p.nruns[n];
   const size_t ro = (size_t)n * p.R;
   FOR_EACH_RUN(r, nr) {
@@ -628,7 +630,7 @@ __global__ void __launch_bounds__(kRunBlk) db_fill_kernel(DbParams p) {
 // K7: row extents of every candidate's point set, stair pixels, hole rings. One thread per run.
 template <typename T>
 __global__ void __launch_bounds__(kRunBlk) db_extents_kernel(DbParams p) {
-  const int n = blockIdx.y;
+  const int n = blockIdx.y + p.n0;
   const int nr = p.nruns[n];
   const size_t ro = (size_t)n * p.R;
   const int32_t* rowptr = p.rowptr + (size_t)n * (p.H + 1);
@@ -733,7 +735,7 @@ __global__ void __launch_bounds__(kRunBlk) db_extents_kernel(DbParams p) {
 
 // K8: candidate ranking in cv2 order (reverse raster order of the first point), one CTA per image.
 __global__ void __launch_bounds__(kRunThreads) db_rank_kernel(DbParams p) {
-  const int n = blockIdx.x;
+  const int n = blockIdx.x + p.n0;
   const int nr = p.nruns[n];
   const size_t ro = (size_t)n * p.R;
   const int chunk = (nr + kRunThreads - 1) / kRunThreads;
@@ -768,7 +770,7 @@ __global__ void __launch_bounds__(kGeoWarps * 32) db_geometry_big_kernel(DbParam
   __shared__ P2i s_hull[kGeoWarps][2 * kSmallRows + 2];
   __shared__ P2i s_off[kGeoWarps][kOffCap];
   __shared__ P2i s_offh[kGeoWarps][kOffCap + 2];
-  const int n = blockIdx.y;
+  const int n = blockIdx.y + p.n0;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t ro = (size_t)n * p.R;
   const int nbig = min(p.nbig[n], p.maxc);
@@ -895,7 +897,7 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
   __shared__ int s_a[kGroups][2 * kFastRows];        // point set (row extents) / sorted unclip polygon
   __shared__ int s_b[kGroups][2 * kFastRows + 2];    // hull
   __shared__ P2i s_off[kGroups][kFastOff];           // raw unclip polygon
-  const int n = blockIdx.y;
+  const int n = blockIdx.y + p.n0;
   const int g = threadIdx.x / kGrp, gl = threadIdx.x % kGrp;
   const unsigned gmask = ((1u << kGrp) - 1u) << ((threadIdx.x & 31) / kGrp * kGrp);
   const int k = blockIdx.x * kGroups + g;
@@ -1017,7 +1019,7 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
 
 // K10: ordered compaction of the kept boxes, one CTA per image.
 __global__ void __launch_bounds__(kRunThreads) db_compact_kernel(DbParams p) {
-  const int n = blockIdx.x;
+  const int n = blockIdx.x + p.n0;
   const int nc = p.ncand[n];
   const size_t ko = (size_t)n * p.maxc;
   const int chunk = (nc + kRunThreads - 1) / kRunThreads;
@@ -1044,7 +1046,7 @@ __global__ void __launch_bounds__(kRunThreads) db_compact_kernel(DbParams p) {
 
 // debug: canonical 8-connected foreground label map (id = 1 + rank of the first raster pixel)
 __global__ void __launch_bounds__(kRunThreads) db_labels_kernel(DbParams p) {
-  const int n = blockIdx.x;
+  const int n = blockIdx.x + p.n0;
   const int nr = p.nruns[n];
   const size_t ro = (size_t)n * p.R;
   const int chunk = (nr + kRunThreads - 1) / kRunThreads;
@@ -1126,6 +1128,99 @@ int resolve_max_runs(int H, int W, int max_runs) {
   return max_runs;
 }
 
+// auxiliary stream / events of the current device (created once, never destroyed)
+constexpr int kDbAuxStreams = 3;
+struct DbAux {
+  cudaStream_t st[kDbAuxStreams];
+  cudaEvent_t fork, join[kDbAuxStreams];
+};
+
+DbAux* db_aux() {
+  static DbAux aux[64];
+  static bool ready[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!ready[dev]) {
+    for (int i = 0; i < kDbAuxStreams; ++i) {
+      if (cudaStreamCreateWithFlags(&aux[dev].st[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&aux[dev].join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&aux[dev].fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ready[dev] = true;
+  }
+  return &aux[dev];
+}
+
+// the whole chain for images [p.n0, p.n0 + N) on stream s
+int db_pipeline(DbParams p, int N, int dtype, cudaStream_t s, ProfileScope* prof) {
+  const int epl = dtype == OCRPP_F32 ? 4 : 8;
+  const bool vec = ((uintptr_t)p.maps % 16 == 0) && (p.stride_n % epl == 0) && (p.stride_h % epl == 0) && (p.W % epl == 0);
+  {
+    dim3 grid((p.H + kBinWarps - 1) / kBinWarps, N);
+    p.epl = vec ? epl : 1;
+    if (dtype == OCRPP_F32) {
+      if (vec) db_scan_kernel<float, 4><<<grid, kBinWarps * 32, 0, s>>>(p);
+      else db_scan_kernel<float, 1><<<grid, kBinWarps * 32, 0, s>>>(p);
+    } else {
+      if (vec) db_scan_kernel<__half, 8><<<grid, kBinWarps * 32, 0, s>>>(p);
+      else db_scan_kernel<__half, 1><<<grid, kBinWarps * 32, 0, s>>>(p);
+    }
+    OCRPP_LAUNCHED();
+    if (prof) prof->mark("db_scan");
+  }
+  const int ictas = max(kImgCtas, min(64, (kNumSMs * 4 + N - 1) / N));   // fill the GPU at small batch sizes too
+  db_runs_kernel<<<dim3(ictas, N), kRunThreads, sizeof(int) * (p.H + 1), s>>>(p);
+  OCRPP_LAUNCHED();
+  if (prof) prof->mark("db_runs");
+  dim3 rgrid(ictas, N);
+  const size_t ccl_smem = sizeof(int) * ((size_t)p.R + (p.R + 31) / 32 + 1);
+  if (ccl_smem <= 200 * 1024) {
+    // opt in to > 48 KB of dynamic shared memory (a per-device function attribute: set on every call)
+    OCRPP_CUDA(cudaFuncSetAttribute(db_ccl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    db_ccl_kernel<<<N, kCclThreads, ccl_smem, s>>>(p);
+    OCRPP_LAUNCHED();
+    if (prof) prof->mark("db_ccl");
+  } else {
+    db_slots_init_kernel<<<rgrid, 256, 0, s>>>(p);
+    OCRPP_LAUNCHED();
+    db_link_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
+    OCRPP_LAUNCHED();
+    db_flatten_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
+    OCRPP_LAUNCHED();
+    if (prof) prof->mark("db_ccl");
+  }
+  db_stats_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  if (prof) prof->mark("db_stats");
+  db_tree_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  if (prof) prof->mark("db_tree");
+  db_fill_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  if (prof) prof->mark("db_fill");
+  if (dtype == OCRPP_F32) db_extents_kernel<float><<<rgrid, kRunBlk, 0, s>>>(p);
+  else db_extents_kernel<__half><<<rgrid, kRunBlk, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  if (prof) prof->mark("db_extents");
+  db_rank_kernel<<<N, kRunThreads, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  if (prof) prof->mark("db_rank");
+  {
+    constexpr int kGroups = kGeoThreads / kGrp;
+    dim3 grid((p.maxc + kGroups - 1) / kGroups, N);
+    db_geometry_kernel<<<grid, kGeoThreads, 0, s>>>(p);
+    OCRPP_LAUNCHED();
+    if (prof) prof->mark("db_geometry");
+    db_geometry_big_kernel<<<dim3(2, N), kGeoWarps * 32, 0, s>>>(p);
+    OCRPP_LAUNCHED();
+    if (prof) prof->mark("db_geometry_big");
+  }
+  db_compact_kernel<<<N, kRunThreads, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  if (prof) prof->mark("db_compact");
+  return OCRPP_OK;
+}
+
 }  // namespace
 }  // namespace ocrpp
 
@@ -1173,74 +1268,33 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
   cudaStream_t s = (cudaStream_t)stream;
 
   OCRPP_CUDA(cudaMemsetAsync(p.nruns, 0, sizeof(int32_t) * 5 * N, s));
-  ProfileScope prof(s);
-  const size_t esz = dtype == OCRPP_F32 ? 4 : 2;
-  const int epl = dtype == OCRPP_F32 ? 4 : 8;
-  const bool vec = ((uintptr_t)maps_dev % 16 == 0) && (stride_n % epl == 0) && (stride_h % epl == 0) && (W % epl == 0);
-  (void)esz;
-  {
-    dim3 grid((H + kBinWarps - 1) / kBinWarps, N);
-    p.epl = vec ? epl : 1;
-    if (dtype == OCRPP_F32) {
-      if (vec) db_scan_kernel<float, 4><<<grid, kBinWarps * 32, 0, s>>>(p);
-      else db_scan_kernel<float, 1><<<grid, kBinWarps * 32, 0, s>>>(p);
-    } else {
-      if (vec) db_scan_kernel<__half, 8><<<grid, kBinWarps * 32, 0, s>>>(p);
-      else db_scan_kernel<__half, 1><<<grid, kBinWarps * 32, 0, s>>>(p);
+  // Large batches run as 2 or 4 independent sub-batch pipelines on separate streams: the bandwidth-bound
+  // scan of one sub-batch overlaps the ALU-bound geometry of another. (Not while per-phase profiling is
+  // on: the event marks describe one whole-batch chain.)
+  int nsplit = N >= 192 ? 4 : (N >= 64 ? 2 : 1);
+  if (const char* e = getenv("OCRPP_DB_SPLIT")) nsplit = atoi(e) < 1 ? 1 : (atoi(e) > 4 ? 4 : atoi(e));
+  DbAux* aux = (nsplit > 1 && nsplit <= N && !profile_on()) ? db_aux() : nullptr;
+  if (aux) {
+    OCRPP_CUDA(cudaEventRecord(aux->fork, s));
+    for (int i = 0; i < nsplit; ++i) {
+      cudaStream_t si = i == 0 ? s : aux->st[i - 1];
+      if (i > 0) OCRPP_CUDA(cudaStreamWaitEvent(si, aux->fork, 0));
+      const int lo = (int)((long long)N * i / nsplit), hi = (int)((long long)N * (i + 1) / nsplit);
+      p.n0 = lo;
+      const int rc = db_pipeline(p, hi - lo, dtype, si, nullptr);
+      if (rc != OCRPP_OK) return rc;
+      if (i > 0) {
+        OCRPP_CUDA(cudaEventRecord(aux->join[i - 1], si));
+        OCRPP_CUDA(cudaStreamWaitEvent(s, aux->join[i - 1], 0));
+      }
     }
-    OCRPP_LAUNCHED();
-    prof.mark("db_scan");
-  }
-  const int ictas = max(kImgCtas, min(64, (kNumSMs * 4 + N - 1) / N));   // fill the GPU at small batch sizes too
-  db_runs_kernel<<<dim3(ictas, N), kRunThreads, sizeof(int) * (H + 1), s>>>(p);
-  OCRPP_LAUNCHED();
-  prof.mark("db_runs");
-  dim3 rgrid(ictas, N);
-  const size_t ccl_smem = sizeof(int) * ((size_t)p.R + (p.R + 31) / 32 + 1);
-  if (ccl_smem <= 200 * 1024) {
-    // opt in to > 48 KB of dynamic shared memory (a per-device function attribute: set on every call)
-    OCRPP_CUDA(cudaFuncSetAttribute(db_ccl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    db_ccl_kernel<<<N, kCclThreads, ccl_smem, s>>>(p);
-    OCRPP_LAUNCHED();
-    prof.mark("db_ccl");
+    p.n0 = 0;
   } else {
-    db_slots_init_kernel<<<rgrid, 256, 0, s>>>(p);
-    OCRPP_LAUNCHED();
-    db_link_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
-    OCRPP_LAUNCHED();
-    db_flatten_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
-    OCRPP_LAUNCHED();
-    prof.mark("db_ccl");
+    ProfileScope prof(s);
+    p.n0 = 0;
+    const int rc = db_pipeline(p, N, dtype, s, &prof);
+    if (rc != OCRPP_OK) return rc;
   }
-  db_stats_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
-  OCRPP_LAUNCHED();
-  prof.mark("db_stats");
-  db_tree_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
-  OCRPP_LAUNCHED();
-  prof.mark("db_tree");
-  db_fill_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
-  OCRPP_LAUNCHED();
-  prof.mark("db_fill");
-  if (dtype == OCRPP_F32) db_extents_kernel<float><<<rgrid, kRunBlk, 0, s>>>(p);
-  else db_extents_kernel<__half><<<rgrid, kRunBlk, 0, s>>>(p);
-  OCRPP_LAUNCHED();
-  prof.mark("db_extents");
-  db_rank_kernel<<<N, kRunThreads, 0, s>>>(p);
-  OCRPP_LAUNCHED();
-  prof.mark("db_rank");
-  {
-    constexpr int kGroups = kGeoThreads / kGrp;
-    dim3 grid((max_candidates + kGroups - 1) / kGroups, N);
-    db_geometry_kernel<<<grid, kGeoThreads, 0, s>>>(p);
-    OCRPP_LAUNCHED();
-    prof.mark("db_geometry");
-    db_geometry_big_kernel<<<dim3(2, N), kGeoWarps * 32, 0, s>>>(p);
-    OCRPP_LAUNCHED();
-    prof.mark("db_geometry_big");
-  }
-  db_compact_kernel<<<N, kRunThreads, 0, s>>>(p);
-  OCRPP_LAUNCHED();
-  prof.mark("db_compact");
   if (labels_dbg_dev) {
     OCRPP_CUDA(cudaMemsetAsync(labels_dbg_dev, 0, sizeof(int32_t) * (size_t)N * H * W, s));
     db_labels_kernel<<<N, kRunThreads, 0, s>>>(p);
