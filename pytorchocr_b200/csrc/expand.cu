@@ -28,6 +28,8 @@
 // Algorithmic bytes per image: C*h*w*sizeof(elem), the head output, read once by ex_binarize_kernel
 // (plus channel 0 again at text pixels for the score mean, and embeddings at gated pixels only).
 #include "common.cuh"
+
+#include <cstdlib>
 #include "dev_common.cuh"
 #include "dev_geom.cuh"
 #include "geometry.cuh"
@@ -50,6 +52,7 @@ struct ExParams {
   long long stride_n, stride_c, stride_h;
   const double* shape;  // [N,4] src_h, src_w, ratio_h, ratio_w
   int N, C, K, h, w, fin, fout, H, W, Wd, R, E, maxc, mode, seed_bit;
+  int n0;  // first image of the sub-batch a launch covers (work lists / counters / arena are per sub-batch)
   float thresh, box_thresh, min_area_seed, min_area_box;
   long long arena_cap;
   // per-image maps
@@ -111,7 +114,7 @@ constexpr int kBigCap = 18432;    // big tiles (merged text regions): 2 CTAs of 
 
 template <typename T, bool kVec>
 __global__ void __launch_bounds__(kBinWarps * 32) ex_binarize_kernel(ExParams p) {
-  const int n = blockIdx.y;
+  const int n = blockIdx.y + p.n0;
   const int y = blockIdx.x * kBinWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (y >= p.H) return;
@@ -203,7 +206,7 @@ __device__ __forceinline__ unsigned run_ends(unsigned w, unsigned next) { return
 
 __global__ void __launch_bounds__(kRunThreads) ex_runs_kernel(ExParams p) {
   extern __shared__ int s_rowcnt[];  // [H+1]
-  const int n = blockIdx.y, m = blockIdx.z;
+  const int n = blockIdx.y + p.n0, m = blockIdx.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kRunThreads / 32;
   const uint32_t* bits = p.bits + (size_t)(n * 2 + m) * p.H * p.Wd;
   const int32_t* rc = p.rowcnt + (size_t)(n * 2 + m) * p.H;
@@ -300,7 +303,7 @@ constexpr int kRunBlk = 256;
 
 // E3: 4-connectivity: link every run with the runs of the row above that overlap [xs, xe].
 __global__ void __launch_bounds__(kRunBlk) ex_link_kernel(ExParams p) {
-  const int n = blockIdx.y, m = blockIdx.z;
+  const int n = blockIdx.y + p.n0, m = blockIdx.z;
   const int nr = p.nruns[n * 2 + m];
   const size_t ro = (size_t)(n * 2 + m) * p.R;
   const int32_t* rowptr = p.rowptr + (size_t)(n * 2 + m) * (p.H + 1);
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(kRunBlk) ex_link_kernel(ExParams p) {
 
 // E4: flatten + per-root reductions (text: area and bounding box; seed: area).
 __global__ void __launch_bounds__(kRunBlk) ex_flatten_kernel(ExParams p) {
-  const int n = blockIdx.y, m = blockIdx.z;
+  const int n = blockIdx.y + p.n0, m = blockIdx.z;
   const int nr = p.nruns[n * 2 + m];
   const size_t ro = (size_t)(n * 2 + m) * p.R, so = (size_t)n * p.R;
   const uint16_t *xs = p.run_xs + ro, *xe = p.run_xe + ro, *ry = p.run_y + ro;
@@ -355,7 +358,7 @@ __device__ __forceinline__ int ex_run_at(const int32_t* rowptr, const uint16_t* 
 // E5: seed components: cv2 label ids, min-area filter (pse.pyx:21-23, pa.pyx:33-37), enclosing text
 // component, work items, and (PAN) the per-text-component extreme kernel areas. One CTA per image.
 __global__ void __launch_bounds__(kRunThreads) ex_seed_kernel(ExParams p) {
-  const int n = blockIdx.x;
+  const int n = blockIdx.x + p.n0;
   const int nr = p.nruns[n * 2 + 1];
   const size_t to = (size_t)(n * 2 + 0) * p.R, ro = (size_t)(n * 2 + 1) * p.R, so = (size_t)n * p.R;
   const int32_t* t_rowptr = p.rowptr + (size_t)(n * 2 + 0) * (p.H + 1);
@@ -405,7 +408,7 @@ __global__ void __launch_bounds__(kRunThreads) ex_seed_kernel(ExParams p) {
 // < 2^20) and embedding sums of flagged kernels over their ORIGINAL pixels.
 template <typename T>
 __global__ void __launch_bounds__(kRunBlk) ex_pan_flag_kernel(ExParams p) {
-  const int n = blockIdx.y;
+  const int n = blockIdx.y + p.n0;
   const int nr = p.nruns[n * 2 + 1];
   const size_t ro = (size_t)(n * 2 + 1) * p.R, so = (size_t)n * p.R;
   EX_FOR_EACH_RUN(r, nr) {
@@ -432,7 +435,7 @@ __global__ void __launch_bounds__(kRunBlk) ex_pan_flag_kernel(ExParams p) {
 // neighbouring component reads them), then the surviving seed pixels -> their label (m == 1).
 // One warp per run.
 __global__ void __launch_bounds__(kRunBlk) ex_paint_kernel(ExParams p, int m) {
-  const int n = blockIdx.y;
+  const int n = blockIdx.y + p.n0;
   const int nr = p.nruns[n * 2 + m];
   const size_t ro = (size_t)(n * 2 + m) * p.R, so = (size_t)n * p.R;
   uint32_t* st = p.st + (size_t)n * p.H * p.W;
@@ -879,7 +882,7 @@ __global__ void __launch_bounds__(kExThreads) ex_expand_kernel(ExParams p) {
 // ------------------------------------------------------------------------------------------------
 template <typename T, int PASS>
 __global__ void __launch_bounds__(kRunBlk) ex_stats_kernel(ExParams p) {
-  const int n = blockIdx.y;
+  const int n = blockIdx.y + p.n0;
   const int nr = p.nruns[n * 2 + 0];
   const size_t ro = (size_t)(n * 2 + 0) * p.R, so = (size_t)n * p.R;
   const uint32_t* st = p.st + (size_t)n * p.H * p.W;
@@ -937,7 +940,7 @@ __global__ void __launch_bounds__(kRunBlk) ex_stats_kernel(ExParams p) {
 // E10: candidates = surviving labels in label order (generate_box iterates i = 1..max(label),
 // pse_postprocess.py:70); row-extent slots. One CTA per image.
 __global__ void __launch_bounds__(kRunThreads) ex_cand_kernel(ExParams p) {
-  const int n = blockIdx.x;
+  const int n = blockIdx.x + p.n0;
   const int nr = p.nruns[n * 2 + 1];
   const size_t ro = (size_t)(n * 2 + 1) * p.R, so = (size_t)n * p.R;
   const int chunk = (nr + kRunThreads - 1) / kRunThreads;
@@ -1003,7 +1006,7 @@ __global__ void __launch_bounds__(kGeoThreads) ex_geometry_fast_kernel(ExParams 
   constexpr int kGroups = kGeoThreads / kGrp;
   __shared__ int s_a[kGroups][2 * kFastRows];
   __shared__ int s_b[kGroups][2 * kFastRows + 2];
-  const int n = blockIdx.y;
+  const int n = blockIdx.y + p.n0;
   const int g = threadIdx.x / kGrp, gl = threadIdx.x % kGrp;
   const unsigned gmask = ((1u << kGrp) - 1u) << ((threadIdx.x & 31) / kGrp * kGrp);
   const int k = blockIdx.x * kGroups + g;
@@ -1051,7 +1054,7 @@ constexpr int kSmallRows = 64;
 __global__ void __launch_bounds__(kGeoWarps * 32) ex_geometry_kernel(ExParams p) {
   __shared__ P2i s_pts[kGeoWarps][4 * kSmallRows];
   __shared__ P2i s_hull[kGeoWarps][4 * kSmallRows + 2];
-  const int n = blockIdx.y;
+  const int n = blockIdx.y + p.n0;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t so = (size_t)n * p.R;
   const int nc = p.ncand[n];
@@ -1102,7 +1105,7 @@ __global__ void __launch_bounds__(kGeoWarps * 32) ex_geometry_kernel(ExParams p)
 
 // E12: ordered compaction of the kept boxes, one CTA per image.
 __global__ void __launch_bounds__(kRunThreads) ex_compact_kernel(ExParams p) {
-  const int n = blockIdx.x;
+  const int n = blockIdx.x + p.n0;
   const int nc = p.ncand[n];
   const size_t ko = (size_t)n * p.maxc;
   const int chunk = (nc + kRunThreads - 1) / kRunThreads;
@@ -1129,7 +1132,7 @@ __global__ void __launch_bounds__(kRunThreads) ex_compact_kernel(ExParams p) {
 
 // debug / parity: the label map pse()/pa() return (cv2 ids), at processing resolution
 __global__ void __launch_bounds__(kRunBlk) ex_labels_kernel(ExParams p) {
-  const int n = blockIdx.y;
+  const int n = blockIdx.y + p.n0;
   const int nr = p.nruns[n * 2 + 0];
   const size_t ro = (size_t)(n * 2 + 0) * p.R, so = (size_t)n * p.R;
   const uint32_t* st = p.st + (size_t)n * p.H * p.W;
@@ -1243,33 +1246,31 @@ ExAux* ex_aux() {
   return &aux[dev];
 }
 
+// the whole chain for images [p.n0, p.n0 + N) on stream s; `fork` = run the four tile-class kernels on
+// auxiliary streams (single-chain mode), otherwise back to back on s (another sub-batch fills the tails)
 template <typename T>
-int ex_launch(ExParams& p, cudaStream_t s, bool vec) {
-  OCRPP_CUDA(cudaMemsetAsync(p.g_nwork, 0, sizeof(int32_t) * 64, s));
-  OCRPP_CUDA(cudaMemsetAsync(p.nruns, 0, sizeof(int32_t) * 5 * p.N, s));
-  ProfileScope prof(s);
-  const int N = p.N;
+int ex_pipeline(ExParams p, int N, cudaStream_t s, bool vec, ProfileScope* prof, bool fork) {
   {
     dim3 grid((p.H + kBinWarps - 1) / kBinWarps, N);
     if (vec) ex_binarize_kernel<T, true><<<grid, kBinWarps * 32, 0, s>>>(p);
     else ex_binarize_kernel<T, false><<<grid, kBinWarps * 32, 0, s>>>(p);
     OCRPP_LAUNCHED();
-    prof.mark("ex_binarize");
+    if (prof) prof->mark("ex_binarize");
   }
   const int ictas = max(kImgCtas, min(64, (kNumSMs * 4 + N - 1) / N));   // fill the GPU at small batch sizes too
   ex_runs_kernel<<<dim3(ictas, N, 2), kRunThreads, sizeof(int) * (p.H + 1), s>>>(p);
   OCRPP_LAUNCHED();
-  prof.mark("ex_runs");
+  if (prof) prof->mark("ex_runs");
   const dim3 rgrid2(ictas, N, 2), rgrid(ictas, N);
   ex_link_kernel<<<rgrid2, kRunBlk, 0, s>>>(p);
   OCRPP_LAUNCHED();
-  prof.mark("ex_link");
+  if (prof) prof->mark("ex_link");
   ex_flatten_kernel<<<rgrid2, kRunBlk, 0, s>>>(p);
   OCRPP_LAUNCHED();
-  prof.mark("ex_flatten");
+  if (prof) prof->mark("ex_flatten");
   ex_seed_kernel<<<N, kRunThreads, 0, s>>>(p);
   OCRPP_LAUNCHED();
-  prof.mark("ex_seed");
+  if (prof) prof->mark("ex_seed");
   if (p.mode == kModePan) {
     ex_pan_flag_kernel<T><<<rgrid, kRunBlk, 0, s>>>(p);
     OCRPP_LAUNCHED();
@@ -1278,7 +1279,7 @@ int ex_launch(ExParams& p, cudaStream_t s, bool vec) {
   OCRPP_LAUNCHED();
   ex_paint_kernel<<<rgrid, kRunBlk, 0, s>>>(p, 1);
   OCRPP_LAUNCHED();
-  prof.mark("ex_paint");
+  if (prof) prof->mark("ex_paint");
   {
     auto tiny_k = ex_expand_kernel<T, kTinyCap, kTinyList, kTinyThreads, 0>;
     auto small_k = ex_expand_kernel<T, kSmallCap, kListCap, kSmallThreads, 1>;
@@ -1290,45 +1291,116 @@ int ex_launch(ExParams& p, cudaStream_t s, bool vec) {
     OCRPP_CUDA(cudaFuncSetAttribute(big_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem_bytes(kBigCap, kListCap)));
     // The four tile classes are independent persistent kernels: fork them onto auxiliary streams so that
     // the tail of one (a few long items) overlaps the bulk of the next, and join before the statistics.
-    ExAux* aux = ex_aux();
-    OCRPP_CHECK_ARG(aux != nullptr, "expand: cannot create auxiliary streams");
-    OCRPP_CUDA(cudaEventRecord(aux->fork, s));
-    for (int i = 0; i < 3; ++i) OCRPP_CUDA(cudaStreamWaitEvent(aux->st[i], aux->fork, 0));
+    ExAux* aux = fork ? ex_aux() : nullptr;
+    OCRPP_CHECK_ARG(!fork || aux != nullptr, "expand: cannot create auxiliary streams");
+    cudaStream_t s1 = s, s2 = s, s3 = s;
+    if (aux) {
+      OCRPP_CUDA(cudaEventRecord(aux->fork, s));
+      for (int i = 0; i < 3; ++i) OCRPP_CUDA(cudaStreamWaitEvent(aux->st[i], aux->fork, 0));
+      s1 = aux->st[0];
+      s2 = aux->st[1];
+      s3 = aux->st[2];
+    }
     huge_k<<<kNumSMs, kHugeThreads, ex_smem_bytes(kHugeCap, kListCap), s>>>(p);   // long items first
     OCRPP_LAUNCHED();
-    big_k<<<kNumSMs * 2, kBigThreads, ex_smem_bytes(kBigCap, kListCap), aux->st[0]>>>(p);
+    big_k<<<kNumSMs * 2, kBigThreads, ex_smem_bytes(kBigCap, kListCap), s1>>>(p);
     OCRPP_LAUNCHED();
-    small_k<<<kNumSMs * 4, kSmallThreads, ex_smem_bytes(kSmallCap, kListCap), aux->st[1]>>>(p);
+    small_k<<<kNumSMs * 4, kSmallThreads, ex_smem_bytes(kSmallCap, kListCap), s2>>>(p);
     OCRPP_LAUNCHED();
-    tiny_k<<<kNumSMs * 9, kTinyThreads, ex_smem_bytes(kTinyCap, kTinyList), aux->st[2]>>>(p);
+    tiny_k<<<kNumSMs * 9, kTinyThreads, ex_smem_bytes(kTinyCap, kTinyList), s3>>>(p);
     OCRPP_LAUNCHED();
-    for (int i = 0; i < 3; ++i) {
-      OCRPP_CUDA(cudaEventRecord(aux->join[i], aux->st[i]));
-      OCRPP_CUDA(cudaStreamWaitEvent(s, aux->join[i], 0));
-    }
+    if (aux)
+      for (int i = 0; i < 3; ++i) {
+        OCRPP_CUDA(cudaEventRecord(aux->join[i], aux->st[i]));
+        OCRPP_CUDA(cudaStreamWaitEvent(s, aux->join[i], 0));
+      }
   }
-  prof.mark("ex_expand");
+  if (prof) prof->mark("ex_expand");
   ex_stats_kernel<T, 1><<<rgrid, kRunBlk, 0, s>>>(p);
   OCRPP_LAUNCHED();
-  prof.mark("ex_stats");
+  if (prof) prof->mark("ex_stats");
   ex_cand_kernel<<<N, kRunThreads, 0, s>>>(p);
   OCRPP_LAUNCHED();
-  prof.mark("ex_cand");
+  if (prof) prof->mark("ex_cand");
   ex_stats_kernel<T, 2><<<rgrid, kRunBlk, 0, s>>>(p);
   OCRPP_LAUNCHED();
-  prof.mark("ex_extents");
+  if (prof) prof->mark("ex_extents");
   ex_geometry_fast_kernel<<<dim3((p.maxc + kGeoThreads / kGrp - 1) / (kGeoThreads / kGrp), N), kGeoThreads, 0, s>>>(p);
   OCRPP_LAUNCHED();
   ex_geometry_kernel<<<dim3(4, N), kGeoWarps * 32, 0, s>>>(p);
   OCRPP_LAUNCHED();
-  prof.mark("ex_geometry");
+  if (prof) prof->mark("ex_geometry");
   ex_compact_kernel<<<N, kRunThreads, 0, s>>>(p);
   OCRPP_LAUNCHED();
-  prof.mark("ex_compact");
+  if (prof) prof->mark("ex_compact");
   if (p.labels_dbg) {
-    OCRPP_CUDA(cudaMemsetAsync(p.labels_dbg, 0, sizeof(int32_t) * (size_t)N * p.H * p.W, s));
+    OCRPP_CUDA(cudaMemsetAsync(p.labels_dbg + (size_t)p.n0 * p.H * p.W, 0, sizeof(int32_t) * (size_t)N * p.H * p.W, s));
     ex_labels_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
     OCRPP_LAUNCHED();
+  }
+  return OCRPP_OK;
+}
+
+// per sub-batch i of nsplit: own work lists (a slice of each class region), counters and arena slice
+ExParams ex_sub_params(const ExParams& p, int i, int nsplit, int n0) {
+  ExParams q = p;
+  q.n0 = n0;
+  q.g_nwork = p.g_nwork + 16 * i;
+  q.g_next = q.g_nwork + 4;
+  q.g_arena_used = reinterpret_cast<unsigned long long*>(q.g_nwork + 8);
+  q.work = p.work + (size_t)n0 * p.R;
+  q.arena_cap = p.arena_cap / nsplit;
+  q.arena = p.arena + (size_t)q.arena_cap * i;
+  return q;
+}
+
+struct ExSplitAux {
+  cudaStream_t st[3];
+  cudaEvent_t fork, join[3];
+};
+
+ExSplitAux* ex_split_aux() {
+  static ExSplitAux aux[64];
+  static bool ready[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!ready[dev]) {
+    for (int i = 0; i < 3; ++i) {
+      if (cudaStreamCreateWithFlags(&aux[dev].st[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&aux[dev].join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&aux[dev].fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ready[dev] = true;
+  }
+  return &aux[dev];
+}
+
+template <typename T>
+int ex_launch(ExParams& p, cudaStream_t s, bool vec) {
+  OCRPP_CUDA(cudaMemsetAsync(p.g_nwork, 0, sizeof(int32_t) * 64, s));
+  OCRPP_CUDA(cudaMemsetAsync(p.nruns, 0, sizeof(int32_t) * 5 * p.N, s));
+  const int N = p.N;
+  // Large batches run as 2 or 4 independent sub-batch pipelines on separate streams, so that the
+  // bandwidth-bound binarisation of one overlaps the latency-bound expansion of another. (Not while
+  // per-phase profiling is on: the event marks describe one whole-batch chain.)
+  int nsplit = N >= 64 ? 4 : 1;   // measured: 2 sub-batches lose to the single chain with forked tile classes
+  if (const char* e = getenv("OCRPP_EX_SPLIT")) nsplit = atoi(e) < 1 ? 1 : (atoi(e) > 4 ? 4 : atoi(e));
+  ExSplitAux* aux = (nsplit > 1 && nsplit <= N && !profile_on()) ? ex_split_aux() : nullptr;
+  if (!aux) {
+    ProfileScope prof(s);
+    return ex_pipeline<T>(ex_sub_params(p, 0, 1, 0), N, s, vec, &prof, true);
+  }
+  OCRPP_CUDA(cudaEventRecord(aux->fork, s));
+  for (int i = 0; i < nsplit; ++i) {
+    cudaStream_t si = i == 0 ? s : aux->st[i - 1];
+    if (i > 0) OCRPP_CUDA(cudaStreamWaitEvent(si, aux->fork, 0));
+    const int lo = (int)((long long)N * i / nsplit), hi = (int)((long long)N * (i + 1) / nsplit);
+    const int rc = ex_pipeline<T>(ex_sub_params(p, i, nsplit, lo), hi - lo, si, vec, nullptr, false);
+    if (rc != OCRPP_OK) return rc;
+    if (i > 0) {
+      OCRPP_CUDA(cudaEventRecord(aux->join[i - 1], si));
+      OCRPP_CUDA(cudaStreamWaitEvent(s, aux->join[i - 1], 0));
+    }
   }
   return OCRPP_OK;
 }
