@@ -65,6 +65,7 @@ struct DbParams {
   int32_t* big;          // [maxc] candidates deferred to the generic geometry kernel
   int32_t* cand;         // [maxc]
   int32_t* res_keep;     // [maxc]
+  int32_t* hull_n;       // [maxc] vertices of the precomputed hull (db_hull_kernel)
   int16_t* res_box;      // [maxc*8]
   float* res_boxf;       // [maxc*8]
   float* res_score;      // [maxc]
@@ -892,15 +893,15 @@ constexpr int kFastRows = 64;                 // max rows of a candidate's point
 constexpr int kFastOff = 96;                  // max points of its unclip polygon
 
 
-__global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
-  constexpr int kGroups = kGeoThreads / kGrp;
-  __shared__ int s_a[kGroups][2 * kFastRows];        // point set (row extents) / sorted unclip polygon
-  __shared__ int s_b[kGroups][2 * kFastRows + 2];    // hull
-  __shared__ P2i s_off[kGroups][kFastOff];           // raw unclip polygon
+// K9a: candidate triage + convex hull of the row extents, ONE THREAD per candidate (the monotone chain is
+// sequential: with a thread per candidate a warp advances 32 hulls at once instead of 4). The hull is
+// written, packed, to the candidate's slice of the hull scratch; res_keep carries the verdict:
+// 0 dropped, 2 deferred to db_geometry_big_kernel, 3 hull ready (hull_n vertices).
+constexpr int kHullThreads = 64;
+
+__global__ void __launch_bounds__(kHullThreads) db_hull_kernel(DbParams p) {
   const int n = blockIdx.y + p.n0;
-  const int g = threadIdx.x / kGrp, gl = threadIdx.x % kGrp;
-  const unsigned gmask = ((1u << kGrp) - 1u) << ((threadIdx.x & 31) / kGrp * kGrp);
-  const int k = blockIdx.x * kGroups + g;
+  const int k = blockIdx.x * kHullThreads + threadIdx.x;
   if (k >= p.ncand[n]) return;
   const size_t ro = (size_t)n * p.R;
   const size_t ko = (size_t)n * p.maxc + k;
@@ -908,8 +909,8 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
   const int yf = p.run_yf[ro + c];
   const int fg = yf >> 15, y_first = yf & 0x7fff;
   const int ymax = p.ymax[ro + c];
-  if (gl == 0) p.res_keep[ko] = 0;
   const int area = p.area[ro + c];
+  p.res_keep[ko] = 0;
   if (fg) {  // "contour has <= 2 points" (db_postprocess.cpp:255-257)
     const int bw = p.xmax[ro + c] - p.xmin[ro + c] + 1, bh = ymax - y_first + 1;
     const bool diag = (bw == bh && bw == area) &&
@@ -918,14 +919,10 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
   }
   const int nrows = fg ? (ymax - y_first + 1) : (ymax - y_first + 3);
   const int off = p.rowoff[ro + c];
-  auto defer = [&]() {
-    if (gl == 0) {
-      const int slot = atomicAdd(&p.nbig[n], 1);
-      if (slot < p.maxc) p.big[(size_t)n * p.maxc + slot] = k;
-    }
-  };
   if (nrows > kFastRows || off < 0 || p.W >= 16384 || p.H >= 16384) {
-    defer();
+    const int slot = atomicAdd(&p.nbig[n], 1);
+    if (slot < p.maxc) p.big[(size_t)n * p.maxc + slot] = k;
+    p.res_keep[ko] = 2;
     return;
   }
   // BoxScore first: a low score drops the candidate whatever its rectangle is
@@ -937,16 +934,83 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
   const int y0 = fg ? y_first : y_first - 1;
   const int32_t* ext_l = p.ext_l + (size_t)n * p.E + off;
   const int32_t* ext_r = p.ext_r + (size_t)n * p.E + off;
+  int* gout = reinterpret_cast<int*>(p.hull + ((size_t)n * p.E + off) * 4);   // >= 8 * (nrows + 1) ints
+  int out[2 * kFastRows + 2];   // dynamically indexed => thread-local memory, which L1 caches write-back
+  // monotone chain over the points (ext_l[i], y0+i), (ext_r[i], y0+i), already sorted by (y, x);
+  // same result as hull_sorted32. The two top-of-stack points stay in registers.
+  const int npts = 2 * nrows;
+  auto pt = [&](int i) { return pk((i & 1) ? ext_r[i >> 1] : ext_l[i >> 1], y0 + (i >> 1)); };
+  int kk = 0, a = 0, b = 0;   // a = out[kk-2], b = out[kk-1]
+  int prev = 0;
+  for (int i = 0; i < npts; ++i) {
+    const int q = pt(i);
+    if (i > 0 && q == prev) continue;
+    prev = q;
+    while (kk >= 2 && cross32(a, b, q) <= 0) {
+      --kk;
+      b = a;
+      if (kk >= 2) a = out[kk - 2];
+    }
+    out[kk++] = q;
+    a = b;
+    b = q;
+  }
+  int hn = kk;
+  if (kk > 1) {
+    const int lo = kk + 1;
+    prev = pt(npts - 1);
+    for (int i = npts - 2; i >= 0; --i) {
+      const int q = pt(i);
+      if (q == prev) continue;
+      prev = q;
+      while (kk >= lo && cross32(a, b, q) <= 0) {
+        --kk;
+        b = a;
+        a = out[kk - 2];
+      }
+      out[kk++] = q;
+      a = b;
+      b = q;
+    }
+    hn = kk - 1;
+  }
+  for (int i = 0; i < hn; ++i) gout[i] = out[i];
+  p.hull_n[ko] = hn;
+  p.res_score[ko] = score;
+  p.res_keep[ko] = 3;
+}
+
+__global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
+  constexpr int kGroups = kGeoThreads / kGrp;
+  __shared__ int s_a[kGroups][2 * kFastRows];        // sorted unclip polygon
+  __shared__ int s_b[kGroups][2 * kFastRows + 2];    // hull
+  __shared__ P2i s_off[kGroups][kFastOff];           // raw unclip polygon
+  const int n = blockIdx.y + p.n0;
+  const int g = threadIdx.x / kGrp, gl = threadIdx.x % kGrp;
+  const unsigned gmask = ((1u << kGrp) - 1u) << ((threadIdx.x & 31) / kGrp * kGrp);
+  const int k = blockIdx.x * kGroups + g;
+  if (k >= p.ncand[n]) return;
+  const size_t ro = (size_t)n * p.R;
+  const size_t ko = (size_t)n * p.maxc + k;
+  if (p.res_keep[ko] != 3) return;   // dropped or deferred by db_hull_kernel
+  __syncwarp(gmask);
+  if (gl == 0) p.res_keep[ko] = 0;
+  const int c = p.cand[ko];
+  const float score = p.res_score[ko];
+  const int off = p.rowoff[ro + c];
+  auto defer = [&]() {
+    if (gl == 0) {
+      const int slot = atomicAdd(&p.nbig[n], 1);
+      if (slot < p.maxc) p.big[(size_t)n * p.maxc + slot] = k;
+    }
+  };
   int* A = s_a[g];
   int* B = s_b[g];
-  for (int i = gl; i < nrows; i += kGrp) {
-    A[2 * i] = pk(ext_l[i], y0 + i);
-    A[2 * i + 1] = pk(ext_r[i], y0 + i);
+  const int hn = p.hull_n[ko];
+  {
+    const int* hull = reinterpret_cast<const int*>(p.hull + ((size_t)n * p.E + off) * 4);
+    for (int i = gl; i < hn; i += kGrp) B[i] = hull[i];
   }
-  __syncwarp(gmask);
-  int hn = 0;
-  if (gl == 0) hn = hull_sorted32(A, 2 * nrows, B);
-  hn = __shfl_sync(gmask, hn, 0, kGrp);
   __syncwarp(gmask);
   geom::Rect rect;
   group_min_area_rect(B, hn, &rect, gl, gmask);
@@ -1107,6 +1171,7 @@ size_t carve(DbParams& p, void* ws) {
   p.big = c.take<int32_t>(N * p.maxc);
   p.cand = c.take<int32_t>(N * p.maxc);
   p.res_keep = c.take<int32_t>(N * p.maxc);
+  p.hull_n = c.take<int32_t>(N * p.maxc);
   p.res_box = c.take<int16_t>(N * p.maxc * 8);
   p.res_boxf = c.take<float>(N * p.maxc * 8);
   p.res_score = c.take<float>(N * p.maxc);
@@ -1208,6 +1273,9 @@ int db_pipeline(DbParams p, int N, int dtype, cudaStream_t s, ProfileScope* prof
   {
     constexpr int kGroups = kGeoThreads / kGrp;
     dim3 grid((p.maxc + kGroups - 1) / kGroups, N);
+    db_hull_kernel<<<dim3((p.maxc + kHullThreads - 1) / kHullThreads, N), kHullThreads, 0, s>>>(p);
+    OCRPP_LAUNCHED();
+    if (prof) prof->mark("db_hull");
     db_geometry_kernel<<<grid, kGeoThreads, 0, s>>>(p);
     OCRPP_LAUNCHED();
     if (prof) prof->mark("db_geometry");
