@@ -227,7 +227,7 @@ __device__ __forceinline__ void db_scan_group(const DbParams& p, const float* v,
   }
 }
 
-template <typename T, int kEpl>
+template <typename T, int kEpl, int kU = 4>
 __global__ void __launch_bounds__(kBinWarps * 32) db_scan_kernel(DbParams p) {
   const int n = blockIdx.y + p.n0;
   const int y = blockIdx.x * kBinWarps + (threadIdx.x >> 5);
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) db_scan_kernel(DbParams p) {
   const size_t rowid = (size_t)n * p.H + y;
   unsigned long long* sc = p.scum + rowid * (p.cap + 1);
   constexpr int PPG = 32 * kEpl;  // pixels per group
-  constexpr int U = kEpl == 1 ? 1 : (kEpl * sizeof(T) > 16 ? 2 : 4);
+  constexpr int U = kEpl == 1 ? 1 : kU;   // groups per main-loop iteration (all loads issued up front)
   unsigned worst = 0;
   unsigned long long carry = 0;   // sum of all pixels of the row before this group (warp-uniform)
   unsigned carry_bit = 0;         // bit of the pixel just before this group
@@ -1224,7 +1224,11 @@ int db_pipeline(DbParams p, int N, int dtype, cudaStream_t s, ProfileScope* prof
     dim3 grid((p.H + kBinWarps - 1) / kBinWarps, N);
     p.epl = vec ? epl : 1;
     if (dtype == OCRPP_F32) {
-      if (vec) db_scan_kernel<float, 4><<<grid, kBinWarps * 32, 0, s>>>(p);
+      // the tail loop (one group per iteration, its load latency exposed) costs ~15 % on short rows
+      const int ng = p.W % 128 == 0 ? p.W / 128 : 0;   // whole groups per row: pick U so that no tail loop is left
+      if (vec && ng > 0 && ng % 5 == 0) db_scan_kernel<float, 4, 5><<<grid, kBinWarps * 32, 0, s>>>(p);
+      else if (vec && ng > 0 && ng % 4 != 0 && ng % 3 == 0) db_scan_kernel<float, 4, 3><<<grid, kBinWarps * 32, 0, s>>>(p);
+      else if (vec) db_scan_kernel<float, 4><<<grid, kBinWarps * 32, 0, s>>>(p);
       else db_scan_kernel<float, 1><<<grid, kBinWarps * 32, 0, s>>>(p);
     } else {
       if (vec) db_scan_kernel<__half, 8><<<grid, kBinWarps * 32, 0, s>>>(p);
@@ -1340,7 +1344,8 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
   // scan of one sub-batch overlaps the ALU-bound geometry of another. (Not while per-phase profiling is
   // on: the event marks describe one whole-batch chain.)
   int nsplit = N >= 192 ? 4 : (N >= 64 ? 2 : 1);
-  if (const char* e = getenv("OCRPP_DB_SPLIT")) nsplit = atoi(e) < 1 ? 1 : (atoi(e) > 4 ? 4 : atoi(e));
+  static const int forced = [] { const char* e = getenv("OCRPP_DB_SPLIT"); return e ? atoi(e) : 0; }();   // tuning aid
+  if (forced > 0) nsplit = forced > 4 ? 4 : forced;
   DbAux* aux = (nsplit > 1 && nsplit <= N && !profile_on()) ? db_aux() : nullptr;
   if (aux) {
     OCRPP_CUDA(cudaEventRecord(aux->fork, s));

@@ -1384,7 +1384,8 @@ int ex_launch(ExParams& p, cudaStream_t s, bool vec) {
   // bandwidth-bound binarisation of one overlaps the latency-bound expansion of another. (Not while
   // per-phase profiling is on: the event marks describe one whole-batch chain.)
   int nsplit = N >= 64 ? 4 : 1;   // measured: 2 sub-batches lose to the single chain with forked tile classes
-  if (const char* e = getenv("OCRPP_EX_SPLIT")) nsplit = atoi(e) < 1 ? 1 : (atoi(e) > 4 ? 4 : atoi(e));
+  static const int forced = [] { const char* e = getenv("OCRPP_EX_SPLIT"); return e ? atoi(e) : 0; }();   // tuning aid
+  if (forced > 0) nsplit = forced > 4 ? 4 : forced;
   ExSplitAux* aux = (nsplit > 1 && nsplit <= N && !profile_on()) ? ex_split_aux() : nullptr;
   if (!aux) {
     ProfileScope prof(s);
