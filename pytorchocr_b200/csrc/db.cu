@@ -415,6 +415,7 @@ __global__ void __launch_bounds__(kRunBlk) db_flatten_kernel(DbParams p) {
 // flatten runs at shared-memory latency instead of L2 latency. Same result as db_link_kernel +
 // db_flatten_kernel (the root of a set is its smallest run index in both).
 constexpr int kCclThreads = 1024;
+constexpr int kCclSmemMax = 200 * 1024;   // dynamic shared memory the kernel is always launched with
 
 __device__ __forceinline__ int uf_find_s(volatile int* par, int x) {  // with path halving
   int q = par[x];
@@ -444,7 +445,9 @@ __device__ __forceinline__ void uf_union_s(int* par, int a, int b) {
 }
 
 __global__ void __launch_bounds__(kCclThreads) db_ccl_kernel(DbParams p) {
-  extern __shared__ int s_par[];  // [R] parents, then [R/32+1] words of per-run / per-root flags
+  extern __shared__ int s_par[];  // [R] parents, [R/32+1] words of per-run / per-root flags, then (when they
+                                  // fit) copies of the run table: the overlap searches below are chains of
+                                  // dependent loads, which cost ~30 cycles each from shared memory, ~600 from L2
   const int n = blockIdx.x + p.n0;
   const int nr = p.nruns[n];
   const size_t ro = (size_t)n * p.R;
@@ -453,6 +456,21 @@ __global__ void __launch_bounds__(kCclThreads) db_ccl_kernel(DbParams p) {
   unsigned* s_flag = reinterpret_cast<unsigned*>(s_par + p.R);
   const int nwords = (nr + 31) / 32;
   for (int w = threadIdx.x; w < nwords; w += kCclThreads) s_flag[w] = 0u;
+  {
+    uint16_t* stage = reinterpret_cast<uint16_t*>(s_flag + (p.R + 31) / 32 + 1);
+    const size_t used = sizeof(int) * ((size_t)p.R + (p.R + 31) / 32 + 1);
+    if (used + 6 * (size_t)nr + 16 <= (size_t)kCclSmemMax) {
+      uint16_t *sx = stage, *se = stage + nr, *sy = stage + 2 * (size_t)nr;
+      for (int r = threadIdx.x; r < nr; r += kCclThreads) {
+        sx[r] = xs[r];
+        se[r] = xe[r];
+        sy[r] = yf[r];
+      }
+      xs = sx;
+      xe = se;
+      yf = sy;
+    }
+  }
   __syncthreads();
   // pass 1: every run points at the FIRST overlapping run of the same polarity in the row above (a
   // smaller index), or at itself. No find, no atomic: most runs of a text map overlap exactly one run.
@@ -1243,10 +1261,10 @@ int db_pipeline(DbParams p, int N, int dtype, cudaStream_t s, ProfileScope* prof
   if (prof) prof->mark("db_runs");
   dim3 rgrid(ictas, N);
   const size_t ccl_smem = sizeof(int) * ((size_t)p.R + (p.R + 31) / 32 + 1);
-  if (ccl_smem <= 200 * 1024) {
+  if (ccl_smem <= (size_t)kCclSmemMax) {
     // opt in to > 48 KB of dynamic shared memory (a per-device function attribute: set on every call)
-    OCRPP_CUDA(cudaFuncSetAttribute(db_ccl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    db_ccl_kernel<<<N, kCclThreads, ccl_smem, s>>>(p);
+    OCRPP_CUDA(cudaFuncSetAttribute(db_ccl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCclSmemMax));
+    db_ccl_kernel<<<N, kCclThreads, kCclSmemMax, s>>>(p);
     OCRPP_LAUNCHED();
     if (prof) prof->mark("db_ccl");
   } else {
