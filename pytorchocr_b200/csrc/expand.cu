@@ -439,8 +439,10 @@ __global__ void __launch_bounds__(kRunBlk) ex_paint_kernel(ExParams p, int m) {
   const int nr = p.nruns[n * 2 + m];
   const size_t ro = (size_t)(n * 2 + m) * p.R, so = (size_t)n * p.R;
   uint32_t* st = p.st + (size_t)n * p.H * p.W;
-  const int lane = threadIdx.x & 31, wpb = kRunBlk / 32;
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < nr; r += gridDim.x * wpb) {
+  // 8 lanes per run (one 32-byte sector per store instruction): text runs are a few dozen pixels long and
+  // the kernel is bound by the latency of the per-run look-ups, so four runs per warp are in flight
+  const int gl = threadIdx.x & 7, gpb = kRunBlk / 8;
+  for (int r = blockIdx.x * gpb + (threadIdx.x >> 3); r < nr; r += gridDim.x * gpb) {
     const int root = p.par[ro + r];
     uint32_t v;
     if (m == 0) {
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(kRunBlk) ex_paint_kernel(ExParams p, int m) {
       v = kLabelBit | (p.s_flag[so + root] ? kGateBit : 0u) | (uint32_t)(root + 1);
     }
     const size_t row = (size_t)p.run_y[ro + r] * p.W;
-    for (int x = p.run_xs[ro + r] + lane; x <= (int)p.run_xe[ro + r]; x += 32) st[row + x] = v;
+    for (int x = p.run_xs[ro + r] + gl; x <= (int)p.run_xe[ro + r]; x += 8) st[row + x] = v;
   }
 }
 
