@@ -57,7 +57,8 @@ extern "C" {
 /* per-image status bits written to `status_out_dev` by the detection entry points */
 #define OCRPP_IMG_RUN_OVERFLOW 1        /* more runs than `max_runs` - result of that image is invalid; retry with a larger max_runs */
 #define OCRPP_IMG_CANDIDATES_TRUNCATED 2 /* more candidates than `max_candidates`; the reference keeps cv2's first 1000, we keep ours */
-#define OCRPP_IMG_VALUE_OUT_OF_RANGE 4   /* a map value was NaN/Inf or |v| > 1024: fixed-point score accumulation not valid */
+#define OCRPP_IMG_VALUE_OUT_OF_RANGE 4   /* DB: a map value was outside [0,1] (or NaN/Inf): not a probability map, the
+                                          * fixed-point score accumulation is not valid for it */
 
 OCRPP_API int ocrpp_abi_version(void);
 OCRPP_API const char* ocrpp_last_error(void);

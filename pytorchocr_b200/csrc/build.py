@@ -33,8 +33,7 @@ def build(force=False, verbose=False):
         if all(os.path.getmtime(p) <= t for p in _deps()):
             return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    extra = ["-DOCRPP_CHECKS"] if os.environ.get("OCRPP_CHECKS") == "1" else []  # device-side bounds checks (debug)
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", OUT]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", OUT]
     print("[build]", " ".join(cmd), flush=True)
     subprocess.check_call(cmd)
     return OUT

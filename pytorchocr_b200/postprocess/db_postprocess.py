@@ -137,7 +137,7 @@ class DBPostProcess(object):
                 host = buf["out_host"].numpy()
                 status = host[o_st:o_st + 4 * N].view(np.int32)
                 if (status & _lib.IMG_VALUE_OUT_OF_RANGE).any():
-                    raise _lib.OcrppError("DB probability map holds NaN/Inf or |value| > 1024: not a probability map")
+                    raise _lib.OcrppError("DB probability map holds a value outside [0, 1] (or NaN/Inf): not a probability map")
                 if (status & _lib.IMG_RUN_OVERFLOW).any():
                     if R >= worst:
                         raise _lib.OcrppError("DB post-process: internal capacity exceeded (image too large for the unclip buffer)")

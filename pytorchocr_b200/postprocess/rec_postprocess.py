@@ -161,6 +161,37 @@ class CTCLabelDecode(BaseRecLabelDecode):
             return text
         return text, self.decode(label)
 
+    def decode_batch(self, preds_list):
+        """Decodes many recogniser outputs with ONE library call: the reference's
+        pipeline runs the CTC decode once per text crop with B = 1 (R/deploy/pytorch/run_ocr.py:221-224),
+        which is launch-bound. `preds_list` holds per-crop tensors [T_i, 1, C] (or [T_i, C]) with
+        different T_i; they are packed into one [T_max, B, C] device tensor whose padding rows are pure
+        blank (class 0 = 1.0). Blank steps are dropped by the collapse and do not enter the confidence
+        mean, so every crop decodes exactly as `self(pred)[0]` would."""
+        torch = _lib.require_cuda()
+        if len(preds_list) == 0:
+            return []
+        items = []
+        for t in preds_list:
+            if isinstance(t, tuple):
+                t = t[-1]
+            if isinstance(t, np.ndarray):
+                t = torch.from_numpy(t)
+            t = t.detach()
+            if t.dim() == 3:
+                if t.shape[1] != 1:
+                    raise ValueError("decode_batch expects per-crop predictions [T, 1, C] or [T, C]")
+                t = t[:, 0]
+            items.append(t)
+        dev = next((t.device for t in items if t.is_cuda), torch.device("cuda", torch.cuda.current_device()))
+        C = items[0].shape[1]
+        Tmax = max(int(t.shape[0]) for t in items)
+        packed = torch.zeros((Tmax, len(items), C), dtype=torch.float32, device=dev)
+        packed[:, :, 0] = 1.0
+        for b, t in enumerate(items):
+            packed[:t.shape[0], b] = t.to(dev, dtype=torch.float32, non_blocking=True)
+        return self(packed)
+
 
 class DistillationCTCLabelDecode(CTCLabelDecode):
     """Reference :96-125 - dict of model outputs -> dict of decoded results."""

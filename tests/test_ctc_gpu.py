@@ -90,3 +90,21 @@ def test_ctc_fp16(dict_path):
     got = op(h.cuda())
     want = oracle(h.float())           # oracle sees the half values upcast
     _same(got, want)
+
+
+def test_decode_batch_matches_per_crop_decode(tmp_path):
+    """run_ocr.py decodes every crop with B = 1 (:221-224); decode_batch packs crops of different widths
+    into one call and must give the very same (text, confidence) pairs."""
+    import torch
+    from pytorchocr_b200.postprocess import build_post_process
+    d = synth.write_char_dict(str(tmp_path / "dict.txt"), 96)
+    op = build_post_process({"name": "CTCLabelDecode", "character_dict_path": d, "cuda_speedup": True})
+    crops = []
+    for i, T in enumerate([12, 33, 7, 80, 1, 25]):
+        probs, _ = synth.ctc_probs_numpy(40 + i, T, 1, 97)
+        crops.append(torch.from_numpy(probs).cuda())
+    one_by_one = [op(c)[0] for c in crops]
+    packed = op.decode_batch(crops)
+    assert [t for t, _ in packed] == [t for t, _ in one_by_one]
+    assert np.allclose([c for _, c in packed], [c for _, c in one_by_one], rtol=1e-6, equal_nan=True)
+    assert op.decode_batch([]) == []
