@@ -24,6 +24,7 @@
 #include "common.cuh"
 
 #include <cstdlib>
+#include <mutex>
 #include "dev_common.cuh"
 #include "dev_geom.cuh"
 #include "geometry.cuh"
@@ -1219,6 +1220,8 @@ struct DbAux {
 };
 
 DbAux* db_aux() {
+  static std::mutex mu;   // first use may come from several host threads
+  std::lock_guard<std::mutex> lock(mu);
   static DbAux aux[64];
   static bool ready[64] = {false};
   int dev = 0;
@@ -1366,6 +1369,8 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
   if (forced > 0) nsplit = forced > 4 ? 4 : forced;
   DbAux* aux = (nsplit > 1 && nsplit <= N && !profile_on()) ? db_aux() : nullptr;
   if (aux) {
+    static std::mutex enqueue_mu;   // the auxiliary streams/events are shared: one fork/join section at a time
+    std::lock_guard<std::mutex> lock(enqueue_mu);
     OCRPP_CUDA(cudaEventRecord(aux->fork, s));
     for (int i = 0; i < nsplit; ++i) {
       cudaStream_t si = i == 0 ? s : aux->st[i - 1];

@@ -30,6 +30,7 @@
 #include "common.cuh"
 
 #include <cstdlib>
+#include <mutex>
 #include "dev_common.cuh"
 #include "dev_geom.cuh"
 #include "geometry.cuh"
@@ -1233,6 +1234,8 @@ struct ExAux {
 };
 
 ExAux* ex_aux() {
+  static std::mutex mu;   // first use may come from several host threads
+  std::lock_guard<std::mutex> lock(mu);
   static ExAux aux[64];
   static bool ready[64] = {false};
   int dev = 0;
@@ -1296,7 +1299,10 @@ int ex_pipeline(ExParams p, int N, cudaStream_t s, bool vec, ProfileScope* prof,
     ExAux* aux = fork ? ex_aux() : nullptr;
     OCRPP_CHECK_ARG(!fork || aux != nullptr, "expand: cannot create auxiliary streams");
     cudaStream_t s1 = s, s2 = s, s3 = s;
+    static std::mutex enqueue_mu;   // the auxiliary streams/events are shared: one fork/join section at a time
+    std::unique_lock<std::mutex> lock(enqueue_mu, std::defer_lock);
     if (aux) {
+      lock.lock();
       OCRPP_CUDA(cudaEventRecord(aux->fork, s));
       for (int i = 0; i < 3; ++i) OCRPP_CUDA(cudaStreamWaitEvent(aux->st[i], aux->fork, 0));
       s1 = aux->st[0];
@@ -1362,6 +1368,8 @@ struct ExSplitAux {
 };
 
 ExSplitAux* ex_split_aux() {
+  static std::mutex mu;   // first use may come from several host threads
+  std::lock_guard<std::mutex> lock(mu);
   static ExSplitAux aux[64];
   static bool ready[64] = {false};
   int dev = 0;
@@ -1393,6 +1401,8 @@ int ex_launch(ExParams& p, cudaStream_t s, bool vec) {
     ProfileScope prof(s);
     return ex_pipeline<T>(ex_sub_params(p, 0, 1, 0), N, s, vec, &prof, true);
   }
+  static std::mutex enqueue_mu;   // the auxiliary streams/events are shared: one fork/join section at a time
+  std::lock_guard<std::mutex> lock(enqueue_mu);
   OCRPP_CUDA(cudaEventRecord(aux->fork, s));
   for (int i = 0; i < nsplit; ++i) {
     cudaStream_t si = i == 0 ? s : aux->st[i - 1];
