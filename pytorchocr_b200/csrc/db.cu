@@ -1044,14 +1044,10 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
 
   // UnClip (db_postprocess.cpp:34-64)
   const float distance = geom::unclip_distance(mx, my, p.unclip_ratio);
-  int m = 0;
-  if (gl == 0) {
-    P2i quad[4];
+  P2i quad[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) quad[q] = P2i{(int)mx[q], (int)my[q]};
-    m = geom::do_offset_quad(quad, (double)distance, s_off[g], kFastOff);
-  }
-  m = __shfl_sync(gmask, m, 0, kGrp);
+  for (int q = 0; q < 4; ++q) quad[q] = P2i{(int)mx[q], (int)my[q]};
+  const int m = group_do_offset_quad(quad, (double)distance, s_off[g], kFastOff, gl, gmask);
   if (m < 0) {
     defer();
     return;

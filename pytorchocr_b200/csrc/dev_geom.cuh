@@ -182,5 +182,112 @@ __device__ void group_min_area_rect(const int* h, int n, geom::Rect* r, int gl, 
   r->h = (double)(best.tmax - best.tmin) / len;
 }
 
+// ClipperOffset of one closed integer quad (geom::do_offset_quad) with ONE LANE PER CORNER: lanes 0..3 of
+// the group compute their corner's normals, angle and arc points at the same time and write them at their
+// rank; the result (points and order) is identical to the sequential routine. Inputs are group-uniform.
+// Anything off the common path (fewer than 4 distinct points, a near-straight corner that Clipper skips
+// without advancing k, near-zero delta) takes the sequential routine on lane 0. Returns the point count
+// on every lane (-1: cap too small).
+__device__ int group_do_offset_quad(const P2i* quad, double delta, P2i* out, int cap, int gl, unsigned gmask) {
+  const double kPi = 3.141592653589793238, kTwoPi = kPi * 2;
+  bool serial = false;
+  // AddPath duplicate stripping (clipper.cpp:3845-3864): the parallel path needs 4 distinct points
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = (i + 1) & 3;
+    serial |= quad[i].x == quad[j].x && quad[i].y == quad[j].y;
+  }
+  serial |= (delta > -1e-20 && delta < 1e-20) || !(delta > 0.0);
+  P2i c[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = quad[i];
+  {  // FixOrientations (clipper.cpp:3889-3903)
+    double a = 0;
+#pragma unroll
+    for (int i = 0, j = 3; i < 4; j = i, ++i) a += ((double)c[j].x + c[i].x) * ((double)c[j].y - c[i].y);
+    if (!(-a * 0.5 >= 0)) {
+      const P2i t0 = c[0], t1 = c[1];
+      c[0] = c[3];
+      c[1] = c[2];
+      c[2] = t1;
+      c[3] = t0;
+    }
+  }
+  const double ad = fabs(delta);
+  double y = 0.25;
+  if (0.25 > ad * 0.25) y = ad * 0.25;
+  double steps = kPi / acos(1 - y / ad);
+  if (steps > ad * kPi) steps = ad * kPi;
+  const double m_sin = sin(kTwoPi / steps), m_cos = cos(kTwoPi / steps);
+  const double steps_per_rad = steps / kTwoPi;
+  // lane j (< 4) owns corner j: normal of edge j -> j+1 and of edge k -> j with k = j - 1
+  const int j = gl & 3, k = (j + 3) & 3;
+  double njx, njy, nkx, nky;
+  {
+    const P2i p1 = c[j], p2 = c[(j + 1) & 3];
+    double dx = (double)(p2.x - p1.x), dy = (double)(p2.y - p1.y);
+    const double f = 1 * 1.0 / sqrt(dx * dx + dy * dy);
+    dx *= f;
+    dy *= f;
+    njx = dy;
+    njy = -dx;
+  }
+  // normal k from the lane that owns corner k (same group)
+  const int src = ((threadIdx.x & 31) & ~(kGrp - 1)) + k;
+  nkx = __shfl_sync(gmask, njx, src);
+  nky = __shfl_sync(gmask, njy, src);
+  double sin_a = nkx * njy - njx * nky;
+  const double cos_a = nkx * njx + njy * nky;
+  int kind = 1, ns = 0;  // 1: round join, 2: concave (3 points)
+  if (fabs(sin_a * delta) < 1.0) {
+    if (cos_a > 0) kind = 0;  // Clipper emits one point and does NOT advance k: sequential routine
+  } else if (sin_a > 1.0) sin_a = 1.0;
+  else if (sin_a < -1.0) sin_a = -1.0;
+  double ang = 0;
+  if (kind == 1) {
+    if (sin_a * delta < 0) kind = 2;
+    else {
+      ang = atan2(sin_a, nkx * njx + nky * njy);
+      long long n = geom::clipper_round(steps_per_rad * fabs(ang));
+      if (n < 1) n = 1;
+      ns = n > 100000 ? 100000 : (int)n;
+    }
+  }
+  serial |= (__ballot_sync(gmask, gl < 4 && kind == 0) & gmask) != 0;
+  if (serial) {
+    int m = 0;
+    if (gl == 0) m = geom::do_offset_quad(quad, delta, out, cap);
+    return __shfl_sync(gmask, m, (threadIdx.x & 31) & ~(kGrp - 1));
+  }
+  const int cnt = gl < 4 ? (kind == 2 ? 3 : ns + 1) : 0;
+  // exclusive prefix of the four counts (corner order)
+  int off = 0, total = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int cq = __shfl_sync(gmask, cnt, ((threadIdx.x & 31) & ~(kGrp - 1)) + q);
+    off += q < j ? cq : 0;
+    total += cq;
+  }
+  if (total > cap) return -1;
+  if (gl < 4) {
+    P2i* o = out + off;
+    if (kind == 2) {
+      o[0] = P2i{(int)geom::clipper_round(c[j].x + nkx * delta), (int)geom::clipper_round(c[j].y + nky * delta)};
+      o[1] = c[j];
+      o[2] = P2i{(int)geom::clipper_round(c[j].x + njx * delta), (int)geom::clipper_round(c[j].y + njy * delta)};
+    } else {
+      double X = nkx, Y = nky;
+      for (int i = 0; i < ns; ++i) {
+        o[i] = P2i{(int)geom::clipper_round(c[j].x + X * delta), (int)geom::clipper_round(c[j].y + Y * delta)};
+        const double X2 = X;
+        X = X * m_cos - m_sin * Y;
+        Y = X2 * m_sin + Y * m_cos;
+      }
+      o[ns] = P2i{(int)geom::clipper_round(c[j].x + njx * delta), (int)geom::clipper_round(c[j].y + njy * delta)};
+    }
+  }
+  return total;
+}
+
 }  // namespace
 }  // namespace ocrpp
