@@ -568,11 +568,13 @@ __global__ void __launch_bounds__(kRunBlk) db_stats_kernel(DbParams p) {
     atomicMin(&p.xmin[c], a);
     atomicMax(&p.xmax[c], b);
     atomicMax(&p.ymax[c], y);
-    if (fg) {
+    // diagonal extents feed the "<= 2 contour points" rule only, which needs bbox_w == bbox_h == area, i.e.
+    // one pixel per row: a run longer than one pixel rules it out, so only single-pixel runs report
+    if (fg && a == b) {
       atomicMin(&p.dmin[c], a - y);
-      atomicMax(&p.dmax[c], b - y);
+      atomicMax(&p.dmax[c], a - y);
       atomicMin(&p.smin[c], a + y);
-      atomicMax(&p.smax[c], b + y);
+      atomicMax(&p.smax[c], a + y);
     }
   }
 }
