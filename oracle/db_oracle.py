@@ -149,7 +149,6 @@ def boxes_from_bitmap(pred, bitmap, box_thresh, unclip_ratio, src_w, src_h,
                       use_padding_resize=False, return_details=False):
     """BoxesFromBitmap, db_postprocess.cpp:231-317. pred f32 [H,W]; bitmap uint8 [H,W].
     Returns list of 4x2 int lists (and, optionally, per-candidate details for parity tests)."""
-    assert not use_padding_resize, "use_padding_resize is SURVEY 8(f) rank 4 (unused in shipped configs)"
     min_size, max_candidates = 3, 1000
     pred = np.ascontiguousarray(pred, np.float32)
     bitmap = np.ascontiguousarray(bitmap, np.uint8)
@@ -187,9 +186,28 @@ def boxes_from_bitmap(pred, bitmap, box_thresh, unclip_ratio, src_w, src_h,
             d["status"] = "small2"
             continue
         out, out_f = [], []
+        if use_padding_resize:
+            # db_postprocess.cpp:293-302: inverse padding-resize affine map (get_affine_transform :111-135 with
+            # float32 points, cv::getAffineTransform in double) and transform_preds (:137-145, double product)
+            center = np.array([f(src_w / 2.0), f(src_h / 2.0)], np.float32)
+            img_maxsize = f(src_w if src_w > src_h else src_h)
+            square = f(height)
+            s_tri = np.zeros((3, 2), np.float32)
+            d_tri = np.zeros((3, 2), np.float32)
+            s_tri[0] = center
+            s_tri[1] = center + np.array([0, img_maxsize / 2.0], np.float32)
+            d_tri[0] = (square / 2.0, square / 2.0)
+            d_tri[1] = d_tri[0] + np.array([0, square / 2.0], np.float32)
+            d_tri[2] = (0, 0)
+            s_tri[2] = (0, center[1] - center[0]) if center[0] >= center[1] else (center[0] - center[1], 0)
+            warp = cv2.getAffineTransform(d_tri, s_tri).T          # 3x2, float64
         for j in range(4):
-            fx = f(f(cliparray[j][0] / f(width)) * f(src_w))
-            fy = f(f(cliparray[j][1] / f(height)) * f(src_h))
+            if use_padding_resize:
+                new_pt = np.array([[float(cliparray[j][0]), float(cliparray[j][1]), 1.0]], np.float64) @ warp
+                fx, fy = f(new_pt[0, 0]), f(new_pt[0, 1])
+            else:
+                fx = f(f(cliparray[j][0] / f(width)) * f(src_w))
+                fy = f(f(cliparray[j][1] / f(height)) * f(src_h))
             out_f.append((float(fx), float(fy)))
             out.append([int(min(max(roundf(fx), 0.0), float(src_w))),
                         int(min(max(roundf(fy), 0.0), float(src_h)))])

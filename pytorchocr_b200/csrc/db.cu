@@ -42,7 +42,7 @@ struct DbParams {
   const void* maps;
   long long stride_n, stride_h;
   const int32_t* src_wh;
-  int N, H, W, Wd, R, maxc, cap, epl, n0;   // n0: first image of the sub-batch this launch covers
+  int N, H, W, Wd, R, maxc, cap, epl, pad_resize, n0;   // n0: first image of the sub-batch this launch covers
   float thresh, box_thresh, unclip_ratio;
   // per-image workspace (index with n * count)
   uint32_t* bits;        // [H*Wd] lane-major bit mask (see db_scan_kernel)
@@ -891,8 +891,8 @@ __global__ void __launch_bounds__(kGeoWarps * 32) db_geometry_big_kernel(DbParam
   if (lane == 0) {
     const float sw = (float)p.src_wh[2 * n], sh = (float)p.src_wh[2 * n + 1];
     for (int q = 0; q < 4; ++q) {
-      const float fx = geom::fmul(geom::fdiv(mx[q], (float)p.W), sw);
-      const float fy = geom::fmul(geom::fdiv(my[q], (float)p.H), sh);
+      float fx, fy;
+      geom::db_rescale(mx[q], my[q], p.W, p.H, sw, sh, p.pad_resize, &fx, &fy);
       p.res_boxf[ko * 8 + 2 * q] = fx;
       p.res_boxf[ko * 8 + 2 * q + 1] = fy;
       p.res_box[ko * 8 + 2 * q] = (int16_t)(int)fminf(fmaxf(geom::roundf_half_away(fx), 0.f), sw);
@@ -1086,8 +1086,8 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
     const float sw = (float)p.src_wh[2 * n], sh = (float)p.src_wh[2 * n + 1];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float fx = geom::fmul(geom::fdiv(mx[q], (float)p.W), sw);
-      const float fy = geom::fmul(geom::fdiv(my[q], (float)p.H), sh);
+      float fx, fy;
+      geom::db_rescale(mx[q], my[q], p.W, p.H, sw, sh, p.pad_resize, &fx, &fy);
       p.res_boxf[ko * 8 + 2 * q] = fx;
       p.res_boxf[ko * 8 + 2 * q + 1] = fy;
       p.res_box[ko * 8 + 2 * q] = (int16_t)(int)fminf(fmaxf(geom::roundf_half_away(fx), 0.f), sw);
@@ -1330,7 +1330,8 @@ extern "C" size_t ocrpp_db_workspace_bytes(int N, int H, int W, int max_runs) {
 extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int H, int W,
                                     int64_t stride_n, int64_t stride_h, const int32_t* src_wh_dev,
                                     float thresh, float box_thresh, float unclip_ratio,
-                                    int max_candidates, int max_runs, int16_t* boxes_out_dev,
+                                    int max_candidates, int max_runs, int use_padding_resize,
+                                    int16_t* boxes_out_dev,
                                     float* scores_out_dev, int32_t* counts_out_dev,
                                     int32_t* status_out_dev, float* boxes_f_out_dev,
                                     int32_t* labels_dbg_dev, void* workspace_dev,
@@ -1351,6 +1352,7 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
   p.E = 4 * p.R + 4;
   p.maxc = max_candidates;
   p.thresh = thresh; p.box_thresh = box_thresh; p.unclip_ratio = unclip_ratio;
+  p.pad_resize = use_padding_resize ? 1 : 0;
   const size_t need = carve(p, workspace_dev);
   if (need > workspace_bytes)
     return set_error(OCRPP_ERR_WORKSPACE_TOO_SMALL, "db: workspace needs %zu bytes, got %zu", need, workspace_bytes);

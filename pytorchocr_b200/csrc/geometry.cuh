@@ -397,6 +397,28 @@ OCRPP_HD void sort_points_yx(P2i* p, int n) {
 
 OCRPP_HD float roundf_half_away(float v) { return roundf(v); }  // C roundf: half away from zero
 
+// Final coordinates of one unclipped corner (db_postprocess.cpp:291-311). Default: scale by src/map size in
+// float32. use_padding_resize: the inverse of the "pad to a square, then resize" affine map
+// (get_affine_transform(center, max(src_w, src_h), map_height, inv=1) + transform_preds, :111-145,293-302):
+// cv::getAffineTransform on those three point pairs is, in exact arithmetic, the similarity
+//   x' = s*x + max(cx - cy, 0) - ... i.e.  x' = s*x + (cx >= cy ? 0 : cx - cy),  y' = s*y + (cx >= cy ? cy - cx : 0)
+// with s = max(src_w, src_h) / map_height and (cx, cy) = (src_w/2, src_h/2); it is evaluated in double like the
+// reference's matrix product and cast to float32 (cv::Point2f) before roundf.
+OCRPP_HD void db_rescale(float mx, float my, int W, int H, float sw, float sh, int use_padding_resize,
+                         float* fx, float* fy) {
+  if (!use_padding_resize) {
+    *fx = fmul(fdiv(mx, (float)W), sw);
+    *fy = fmul(fdiv(my, (float)H), sh);
+    return;
+  }
+  const double cx = (double)(float)((double)sw / 2.0), cy = (double)(float)((double)sh / 2.0);
+  const double m = sw > sh ? (double)sw : (double)sh;
+  const double s = m / (double)H;
+  const double tx = cx >= cy ? 0.0 : cx - cy, ty = cx >= cy ? cy - cx : 0.0;
+  *fx = (float)(s * (double)mx + tx);
+  *fy = (float)(s * (double)my + ty);
+}
+
 // np.round (half to even) on a double, as used by PSE/PAN generate_box (pse_postprocess.py:100-101)
 OCRPP_HD double round_half_even(double v) {
   return nearbyint(v);

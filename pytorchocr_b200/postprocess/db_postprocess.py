@@ -90,7 +90,7 @@ class DBPostProcess(object):
             return int(self.max_runs)
         return max(4096, (H * W) // 32)
 
-    def run_device(self, pred, shape_list, boxes_f=False, labels=False):
+    def run_device(self, pred, shape_list, boxes_f=False, labels=False, use_padding_resize=False):
         """Enqueues the kernels and returns host views (boxes[N,cap,4,2] i16, scores[N,cap] f32,
         counts[N], status[N], extras dict). Blocks until the results are on the host."""
         torch = _lib.require_cuda()
@@ -130,7 +130,7 @@ class DBPostProcess(object):
                     t.data_ptr(), _lib.F32 if t.dtype == torch.float32 else _lib.F16, N, H, W,
                     t.stride(0), t.stride(2), buf["wh_dev"].data_ptr(),
                     float(self.thresh), float(self.box_thresh), float(self.unclip_ratio), cap, R,
-                    base + o_box, base + o_sc, base + o_cnt, base + o_st, bf_ptr, lab_ptr,
+                    1 if use_padding_resize else 0, base + o_box, base + o_sc, base + o_cnt, base + o_st, bf_ptr, lab_ptr,
                     buf["ws"].data_ptr(), buf["ws_bytes"], stream.cuda_stream))
                 buf["out_host"].copy_(out, non_blocking=True)
                 stream.synchronize()
@@ -154,9 +154,8 @@ class DBPostProcess(object):
         return boxes, scores, counts, status, extras
 
     def __call__(self, outs_dict, shape_list, use_padding_resize=False):
-        if use_padding_resize:
-            raise NotImplementedError("use_padding_resize is unused in the shipped configs (SURVEY.md 8(f) rank 4)")
-        boxes, scores, counts, _, _ = self.run_device(outs_dict["maps"], shape_list)
+        boxes, scores, counts, _, _ = self.run_device(outs_dict["maps"], shape_list,
+                                                      use_padding_resize=use_padding_resize)
         res_batch = []
         for n in range(boxes.shape[0]):
             k = int(counts[n])

@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     missing = [s for s in _header_symbols() if not hasattr(L, s)]
     assert not missing, missing
     L.ocrpp_abi_version.restype = ctypes.c_int
-    assert L.ocrpp_abi_version() == 1
+    assert L.ocrpp_abi_version() == 2
     # sm_100a code is really in the binary
     out = subprocess.check_output(["/usr/local/cuda/bin/cuobjdump", "-lelf", path]).decode()
     assert "sm_100a" in out

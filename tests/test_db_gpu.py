@@ -149,3 +149,26 @@ def test_db_run_capacity_retry_and_bad_values():
     bad[0, 0, 3, 3] = np.nan
     with pytest.raises(_lib.OcrppError):
         _op()({"maps": torch.from_numpy(bad).cuda()}, np.array([[H, W, 1.0, 1.0]]))
+
+
+@pytest.mark.parametrize("src_hw", [(480, 640), (900, 600), (512, 512)])
+def test_db_use_padding_resize(src_hw):
+    """db_postprocess.cpp:293-302: boxes mapped back through the inverse padding-resize affine transform."""
+    import torch
+    H = W = 256                                   # padded square map
+    maps = synth.db_batch(2, seed=11, H=H, W=W)
+    src_h, src_w = src_hw
+    sl = np.array([[src_h, src_w, 1.0, 1.0]] * 2, np.float64)
+    op = _op()
+    got = op({"maps": torch.from_numpy(maps).cuda()}, sl, use_padding_resize=True)
+    want = DBPostProcessOracle(**CFG)({"maps": maps}, sl, use_padding_resize=True)
+    plain = op({"maps": torch.from_numpy(maps).cuda()}, sl)
+    n_diff = 0
+    for g, w, q in zip(got, want, plain):
+        a = np.array(sorted(map(tuple, g["points"].reshape(-1, 8).tolist())))
+        b = np.array(sorted(map(tuple, w["points"].reshape(-1, 8).tolist())))
+        assert a.shape == b.shape and len(a) > 0
+        diff = np.abs(a - b).max(1)
+        assert (diff > 0).sum() <= 1 and diff.max() <= 1       # <= 1 box on a rounding discontinuity
+        n_diff += int(not np.array_equal(g["points"], q["points"]))
+    assert n_diff > 0 or src_h == src_w                       # the flag changes the mapping unless the source is square
