@@ -249,7 +249,7 @@ class DbWorkload(DetWorkload):
         base = buf["out_dev"].data_ptr()
         _lib.check(L.ocrpp_db_postprocess(
             m.data_ptr(), _lib.F32, self.batch, H, W, m.stride(0), m.stride(2), buf["wh_dev"].data_ptr(),
-            DB_CFG["thresh"], DB_CFG["box_thresh"], DB_CFG["unclip_ratio"], self.key[5], self.key[4], 0,
+            DB_CFG["thresh"], DB_CFG["box_thresh"], DB_CFG["unclip_ratio"], self.key[5], self.key[4], 0, 0,
             base + o_box, base + o_sc, base + o_cnt, base + o_st, None, None,
             buf["ws"].data_ptr(), buf["ws_bytes"], stream.cuda_stream))
         buf["out_host"].copy_(buf["out_dev"], non_blocking=True)

@@ -101,6 +101,9 @@ OCRPP_API int ocrpp_ctc_greedy(const void* probs_dev, int dtype, int T, int B, i
  *   max_candidates: output capacity per image (reference constant: 1000).
  *   max_runs: capacity of the per-image run table (foreground + background runs);
  *             0 selects the worst case H*(W+1).
+ *   use_dilation: extract the boxes from the 2x2 dilation of the thresholded map (db_postprocess.py:52-55,
+ *             cv2.dilate with a [[1,1],[1,1]] kernel) instead of the thresholded map itself; BoxScore still
+ *             averages the probabilities under the (dilated) region. Costs a second pass over the maps.
  *   use_padding_resize: map the boxes back through the inverse "pad to square + resize" affine transform
  *             (db_postprocess.cpp:293-302) instead of the plain src/map scaling (:303-311).
  * outputs (device):
@@ -117,7 +120,7 @@ OCRPP_API size_t ocrpp_db_workspace_bytes(int N, int H, int W, int max_runs);
 OCRPP_API int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int H, int W,
                          int64_t stride_n, int64_t stride_h, const int32_t* src_wh_dev,
                          float thresh, float box_thresh, float unclip_ratio,
-                         int max_candidates, int max_runs, int use_padding_resize,
+                         int max_candidates, int max_runs, int use_dilation, int use_padding_resize,
                          int16_t* boxes_out_dev, float* scores_out_dev, int32_t* counts_out_dev,
                          int32_t* status_out_dev, float* boxes_f_out_dev, int32_t* labels_dbg_dev,
                          void* workspace_dev, size_t workspace_bytes, void* stream);

@@ -46,6 +46,8 @@ struct DbParams {
   float thresh, box_thresh, unclip_ratio;
   // per-image workspace (index with n * count)
   uint32_t* bits;        // [H*Wd] lane-major bit mask (see db_scan_kernel)
+  uint32_t* rawbits;     // [H*Wd] raw threshold bits (use_dilation only)
+  int dilate;
   unsigned long long* scum;  // [H*(cap+1)] per-row run starts: x << 48 | cumulative row sum before x (2^-23 units)
   int32_t* srow_cnt;     // [H] runs in the row | first pixel bit << 31
   long long* run_sum;    // [R] pixel sum of every run (32.32 fixed point)
@@ -122,12 +124,17 @@ struct RowLoader<T, 1> {  // unaligned / odd-width fallback: one pixel per lane
   }
 };
 
-// one group of 32*kEpl pixels; kFull = every pixel of the group is inside the row
-template <int kEpl, bool kFull>
+// one group of 32*kEpl pixels; kFull = every pixel of the group is inside the row.
+// kDilate: the mask is not `f > thresh` but its 2x2 dilation (use_dilation, db_postprocess.py:52-55:
+// cv2.dilate with a [[1,1],[1,1]] kernel = OR over (x-1..x, y-1..y)), assembled from the raw threshold
+// bits of rows y and y-1 that db_rawbits_kernel wrote (same lane-major layout); dil[0]/dil[1] carry the
+// last raw bit of the previous group of row y / y-1.
+template <int kEpl, bool kFull, bool kDilate>
 __device__ __forceinline__ void db_scan_group(const DbParams& p, const float* v, int xg, int lane,
                                               unsigned long long* sc, uint32_t* out,
                                               unsigned long long& carry, unsigned& carry_bit, int& cnt,
-                                              unsigned& first_bit, unsigned& worst) {
+                                              unsigned& first_bit, unsigned& worst,
+                                              const uint32_t* raw_y, const uint32_t* raw_u, unsigned* dil) {
   constexpr int PPG = 32 * kEpl;
   const int x = xg + lane * kEpl;
   unsigned m[kEpl];    // ballot of pixel k of every lane
@@ -137,7 +144,7 @@ __device__ __forceinline__ void db_scan_group(const DbParams& p, const float* v,
   for (int k = 0; k < kEpl; ++k) {
     const float f = v[k];
     const bool valid = kFull || x + k < p.W;
-    m[k] = __ballot_sync(0xffffffffu, valid && f > p.thresh);
+    if (!kDilate) m[k] = __ballot_sync(0xffffffffu, valid && f > p.thresh);
     // f in [0,1]: the mantissa of f + 1.0f is round(f * 2^23); anything else (negative, > 1, NaN, Inf)
     // gives u > 2^23 and is reported through `worst`
     unsigned u = __float_as_uint(f + 1.0f) - 0x3f800000u;
@@ -145,6 +152,27 @@ __device__ __forceinline__ void db_scan_group(const DbParams& p, const float* v,
     worst = max(worst, u);
     run += u;
     pre[k] = run;
+  }
+  if (kDilate) {
+    const int w0 = (xg / PPG) * kEpl;
+    unsigned ry[kEpl], ru[kEpl];
+#pragma unroll
+    for (int k = 0; k < kEpl; ++k) {
+      ry[k] = raw_y[w0 + k];
+      ru[k] = raw_u ? raw_u[w0 + k] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kEpl; ++k) {   // pixel x-1: word k-1 at the same lane, or word kEpl-1 one lane down
+      const unsigned py = k == 0 ? ((ry[kEpl - 1] << 1) | dil[0]) : ry[k - 1];
+      const unsigned pu = k == 0 ? ((ru[kEpl - 1] << 1) | dil[1]) : ru[k - 1];
+      m[k] = ry[k] | py | ru[k] | pu;
+      if (!kFull) {
+        const int nvalid = (p.W - xg - k + kEpl - 1) / kEpl;
+        m[k] &= nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+      }
+    }
+    dil[0] = ry[kEpl - 1] >> 31;
+    dil[1] = ru[kEpl - 1] >> 31;
   }
   const unsigned total = __reduce_add_sync(0xffffffffu, run);  // <= 32 * kEpl * 2^23 <= 2^31
   if (xg == 0) first_bit = m[0] & 1u;
@@ -228,7 +256,7 @@ __device__ __forceinline__ void db_scan_group(const DbParams& p, const float* v,
   }
 }
 
-template <typename T, int kEpl, int kU = 4>
+template <typename T, int kEpl, int kU = 4, bool kDilate = false>
 __global__ void __launch_bounds__(kBinWarps * 32) db_scan_kernel(DbParams p) {
   const int n = blockIdx.y + p.n0;
   const int y = blockIdx.x * kBinWarps + (threadIdx.x >> 5);
@@ -246,6 +274,9 @@ __global__ void __launch_bounds__(kBinWarps * 32) db_scan_kernel(DbParams p) {
   int cnt = 1;                    // run 0 starts at x = 0
   unsigned first_bit = 0;
   if (lane == 0) sc[0] = 0ull;   // run 0: x = 0, nothing before it
+  const uint32_t* raw_y = kDilate ? p.rawbits + ((size_t)n * p.H + y) * p.Wd : nullptr;
+  const uint32_t* raw_u = (kDilate && y > 0) ? raw_y - p.Wd : nullptr;
+  unsigned dil[2] = {0u, 0u};
   // main loop: U full groups per iteration, all loads issued first, no per-group bounds checks
   int x0 = 0;
   for (; x0 + PPG * U <= p.W; x0 += PPG * U) {
@@ -254,20 +285,45 @@ __global__ void __launch_bounds__(kBinWarps * 32) db_scan_kernel(DbParams p) {
     for (int u = 0; u < U; ++u) RowLoader<T, kEpl>::load(row, x0 + u * PPG + lane * kEpl, p.W, v[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      db_scan_group<kEpl, true>(p, v[u], x0 + u * PPG, lane, sc, out, carry, carry_bit, cnt, first_bit, worst);
+      db_scan_group<kEpl, true, kDilate>(p, v[u], x0 + u * PPG, lane, sc, out, carry, carry_bit, cnt, first_bit, worst,
+                                         raw_y, raw_u, dil);
   }
   // tail: the remaining (fewer than U) groups, the last of them possibly partial
   for (; x0 < p.W; x0 += PPG) {
     float v[kEpl];
     RowLoader<T, kEpl>::load(row, x0 + lane * kEpl, p.W, v);
-    if (x0 + PPG <= p.W) db_scan_group<kEpl, true>(p, v, x0, lane, sc, out, carry, carry_bit, cnt, first_bit, worst);
-    else db_scan_group<kEpl, false>(p, v, x0, lane, sc, out, carry, carry_bit, cnt, first_bit, worst);
+    if (x0 + PPG <= p.W)
+      db_scan_group<kEpl, true, kDilate>(p, v, x0, lane, sc, out, carry, carry_bit, cnt, first_bit, worst, raw_y, raw_u, dil);
+    else
+      db_scan_group<kEpl, false, kDilate>(p, v, x0, lane, sc, out, carry, carry_bit, cnt, first_bit, worst, raw_y, raw_u, dil);
   }
   if (lane == 0) {
     p.srow_cnt[rowid] = cnt | (first_bit << 31);
     if (cnt <= p.cap) sc[cnt] = carry;
   }
   if (__any_sync(0xffffffffu, worst > 0x800000u) && lane == 0) atomicOr(&p.imgflags[n], OCRPP_IMG_VALUE_OUT_OF_RANGE);
+}
+
+// use_dilation, pass 1: raw threshold bits of every row in the lane-major layout (the dilated mask of row y
+// needs rows y-1 and y, so the scan kernel cannot threshold on the fly)
+template <typename T, int kEpl>
+__global__ void __launch_bounds__(kBinWarps * 32) db_rawbits_kernel(DbParams p) {
+  const int n = blockIdx.y + p.n0;
+  const int y = blockIdx.x * kBinWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (y >= p.H) return;
+  const T* row = reinterpret_cast<const T*>(p.maps) + n * p.stride_n + y * p.stride_h;
+  uint32_t* out = p.rawbits + ((size_t)n * p.H + y) * p.Wd;
+  constexpr int PPG = 32 * kEpl;
+  for (int x0 = 0; x0 < p.W; x0 += PPG) {
+    float v[kEpl];
+    RowLoader<T, kEpl>::load(row, x0 + lane * kEpl, p.W, v);
+#pragma unroll
+    for (int k = 0; k < kEpl; ++k) {
+      const unsigned w = __ballot_sync(0xffffffffu, x0 + lane * kEpl + k < p.W && v[k] > p.thresh);
+      if (lane == k) out[(x0 / PPG) * kEpl + k] = w;
+    }
+  }
 }
 
 // pixel (x,y) of the lane-major bit mask written by db_scan_kernel
@@ -1153,6 +1209,7 @@ size_t carve(DbParams& p, void* ws) {
   Carver c{(char*)ws, 0};
   const size_t N = p.N, R = p.R, E = p.E;
   p.bits = c.take<uint32_t>(N * p.H * p.Wd);
+  p.rawbits = c.take<uint32_t>(N * p.H * p.Wd);
   p.scum = c.take<unsigned long long>(N * p.H * (p.cap + 1));
   p.srow_cnt = c.take<int32_t>(N * p.H);
   p.run_sum = c.take<long long>(N * R);
@@ -1242,7 +1299,23 @@ int db_pipeline(DbParams p, int N, int dtype, cudaStream_t s, ProfileScope* prof
   {
     dim3 grid((p.H + kBinWarps - 1) / kBinWarps, N);
     p.epl = vec ? epl : 1;
-    if (dtype == OCRPP_F32) {
+    if (p.dilate) {
+      if (dtype == OCRPP_F32) {
+        if (vec) db_rawbits_kernel<float, 4><<<grid, kBinWarps * 32, 0, s>>>(p);
+        else db_rawbits_kernel<float, 1><<<grid, kBinWarps * 32, 0, s>>>(p);
+      } else {
+        if (vec) db_rawbits_kernel<__half, 8><<<grid, kBinWarps * 32, 0, s>>>(p);
+        else db_rawbits_kernel<__half, 1><<<grid, kBinWarps * 32, 0, s>>>(p);
+      }
+      OCRPP_LAUNCHED();
+      if (dtype == OCRPP_F32) {
+        if (vec) db_scan_kernel<float, 4, 4, true><<<grid, kBinWarps * 32, 0, s>>>(p);
+        else db_scan_kernel<float, 1, 4, true><<<grid, kBinWarps * 32, 0, s>>>(p);
+      } else {
+        if (vec) db_scan_kernel<__half, 8, 4, true><<<grid, kBinWarps * 32, 0, s>>>(p);
+        else db_scan_kernel<__half, 1, 4, true><<<grid, kBinWarps * 32, 0, s>>>(p);
+      }
+    } else if (dtype == OCRPP_F32) {
       // the tail loop (one group per iteration, its load latency exposed) costs ~15 % on short rows
       const int ng = p.W % 128 == 0 ? p.W / 128 : 0;   // whole groups per row: pick U so that no tail loop is left
       if (vec && ng > 0 && ng % 5 == 0) db_scan_kernel<float, 4, 5><<<grid, kBinWarps * 32, 0, s>>>(p);
@@ -1330,7 +1403,7 @@ extern "C" size_t ocrpp_db_workspace_bytes(int N, int H, int W, int max_runs) {
 extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int H, int W,
                                     int64_t stride_n, int64_t stride_h, const int32_t* src_wh_dev,
                                     float thresh, float box_thresh, float unclip_ratio,
-                                    int max_candidates, int max_runs, int use_padding_resize,
+                                    int max_candidates, int max_runs, int use_dilation, int use_padding_resize,
                                     int16_t* boxes_out_dev,
                                     float* scores_out_dev, int32_t* counts_out_dev,
                                     int32_t* status_out_dev, float* boxes_f_out_dev,
@@ -1353,6 +1426,7 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
   p.maxc = max_candidates;
   p.thresh = thresh; p.box_thresh = box_thresh; p.unclip_ratio = unclip_ratio;
   p.pad_resize = use_padding_resize ? 1 : 0;
+  p.dilate = use_dilation ? 1 : 0;
   const size_t need = carve(p, workspace_dev);
   if (need > workspace_bytes)
     return set_error(OCRPP_ERR_WORKSPACE_TOO_SMALL, "db: workspace needs %zu bytes, got %zu", need, workspace_bytes);

@@ -26,8 +26,7 @@ class DBPostProcess(object):
         # The C++ path the CUDA path replaces ignores score_mode (always scores the contour polygon),
         # hard-codes min_size = 3 and max_candidates = 1000 and cannot emit polygons
         # (db_postprocess.cpp:238-239,270); options outside it are SURVEY 8(f) items.
-        if use_dilation:
-            raise NotImplementedError("use_dilation is not on the configured path (SURVEY.md 8(f) rank 4)")
+        self.use_dilation = bool(use_dilation)   # db_postprocess.py:22: dilation_kernel = [[1,1],[1,1]]
         if out_polygon:
             raise NotImplementedError("out_polygon needs cpp_speedup False in the reference; not on the CUDA path")
         self.thresh = thresh
@@ -130,7 +129,7 @@ class DBPostProcess(object):
                     t.data_ptr(), _lib.F32 if t.dtype == torch.float32 else _lib.F16, N, H, W,
                     t.stride(0), t.stride(2), buf["wh_dev"].data_ptr(),
                     float(self.thresh), float(self.box_thresh), float(self.unclip_ratio), cap, R,
-                    1 if use_padding_resize else 0, base + o_box, base + o_sc, base + o_cnt, base + o_st, bf_ptr, lab_ptr,
+                    1 if self.use_dilation else 0, 1 if use_padding_resize else 0, base + o_box, base + o_sc, base + o_cnt, base + o_st, bf_ptr, lab_ptr,
                     buf["ws"].data_ptr(), buf["ws_bytes"], stream.cuda_stream))
                 buf["out_host"].copy_(out, non_blocking=True)
                 stream.synchronize()

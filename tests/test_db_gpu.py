@@ -37,7 +37,10 @@ def _check(maps, shape_list, op=None, oracle_maps=None, loose=0.02, **kw):
     for n in range(len(want)):
         k = int(counts[n])
         merge(tot, compare_image(boxes[n, :k], ex["boxes_f"][n, :k], scores[n, :k], want[n]["details"]))
-        fg, _ = ndi.label(ref_in[n, 0] > ocfg["thresh"], structure=np.ones((3, 3)))
+        seg = ref_in[n, 0] > ocfg["thresh"]
+        if ocfg.get("use_dilation"):
+            seg = cv2.dilate(seg.astype(np.uint8), np.array([[1, 1], [1, 1]], np.uint8)) > 0
+        fg, _ = ndi.label(seg, structure=np.ones((3, 3)))
         assert np.array_equal(canonical_labels(fg), ex["labels"][n]), "label map differs"
     n_boxes = max(1, tot.get("n_oracle", 0))
     off = tot.get("n_oracle", 0) - tot.get("exact", 0) + tot.get("unmatched_gpu", 0)
@@ -172,3 +175,28 @@ def test_db_use_padding_resize(src_hw):
         assert (diff > 0).sum() <= 1 and diff.max() <= 1       # <= 1 box on a rounding discontinuity
         n_diff += int(not np.array_equal(g["points"], q["points"]))
     assert n_diff > 0 or src_h == src_w                       # the flag changes the mapping unless the source is square
+
+
+@pytest.mark.parametrize("H,W,dtype", [(192, 320, "f32"), (97, 131, "f32"), (256, 1280, "f32"), (33, 1000, "f16"),
+                                       (160, 256, "f16")])
+def test_db_use_dilation(H, W, dtype):
+    """db_postprocess.py:52-55: contours come from cv2.dilate(segmentation, [[1,1],[1,1]])."""
+    import torch
+    maps = synth.db_batch(3, seed=synth.BASE_SEED + 5 * H, H=H, W=W)
+    sl = np.array([[H, W, 1.0, 1.0], [H * 2, W * 2, 2.0, 2.0], [H // 2 + 7, W // 2 + 3, 0.5, 0.5]], np.float64)
+    if dtype == "f16":
+        dev = torch.from_numpy(maps).cuda().half()
+        _check(dev, sl, oracle_maps=dev.float().cpu().numpy(), use_dilation=True, loose=0.05)
+    else:
+        # dilated blobs have longer axis-parallel hull edges, so more mini-boxes land within cv2's float32
+        # noise of an integer corner (the "truncation" class of db_compare.py) than in the undilated tests
+        _check(maps, sl, use_dilation=True, loose=0.05)
+
+
+def test_db_use_dilation_blob_field():
+    """Dilation merges diagonal / one-pixel-gap neighbours: adversarial topology through the dilated scan."""
+    rng = np.random.default_rng(4)
+    H, W = 120, 152
+    f = ndi.gaussian_filter(rng.standard_normal((2, 1, H, W)), (0, 0, 1.2, 1.2))
+    maps = (1.0 / (1.0 + np.exp(-6.0 * f / f.std()))).astype(np.float32)
+    _check(maps, np.array([[H, W, 1.0, 1.0]] * 2), use_dilation=True, loose=0.35)
