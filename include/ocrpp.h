@@ -57,6 +57,8 @@ extern "C" {
 /* per-image status bits written to `status_out_dev` by the detection entry points */
 #define OCRPP_IMG_RUN_OVERFLOW 1        /* more runs than `max_runs` - result of that image is invalid; retry with a larger max_runs */
 #define OCRPP_IMG_CANDIDATES_TRUNCATED 2 /* more candidates than `max_candidates`; the reference keeps cv2's first 1000, we keep ours */
+#define OCRPP_IMG_BOX_DEGENERATE 8       /* crop: empty bounding rectangle, corner outside the page or collinear corners; its crop is empty */
+#define OCRPP_IMG_CROPS_TRUNCATED 16     /* crop: the arena is too small; offsets/dims are complete, crops past the capacity are not written */
 #define OCRPP_IMG_VALUE_OUT_OF_RANGE 4   /* DB: a map value was outside [0,1] (or NaN/Inf): not a probability map, the
                                           * fixed-point score accumulation is not valid for it */
 
@@ -179,6 +181,33 @@ OCRPP_API int ocrpp_pan_postprocess(const void* maps_dev, int dtype, int N, int 
                           int16_t* boxes_out_dev, float* scores_out_dev, int32_t* counts_out_dev,
                           int32_t* status_out_dev, float* boxes_f_out_dev, int32_t* labels_dbg_dev,
                           void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Text-line crops of detected boxes for a batch of pages: the step between the detection operators and
+ * the recogniser. Replaces sort_boxes (R/pytocr/utils/utility.py:32-50), get_part_img (:53-78:
+ * bounding-rectangle crop, cv2.getPerspectiveTransform, cv2.warpPerspective with INTER_LINEAR and
+ * BORDER_REPLICATE) and the rot90 rule of its caller (R/deploy/pytorch/run_ocr.py:188-191), with cv2's
+ * 8-bit arithmetic reproduced bit for bit (oracle/crop_oracle.py).
+ *   img_dev:   uint8 pages, page n pixel (y,x) channel c at img_dev[n*stride_n + y*stride_row + x*C + c]
+ *              (byte strides; C = 1, 3 or 4; H, W <= 32767).
+ *   boxes_dev: int16 [N,max_boxes,4,2] corners (x,y) - the layout ocrpp_db/pse/pan_postprocess write -
+ *              and counts_dev int32 [N] (NULL: max_boxes boxes on every page); max_boxes <= 8192.
+ *   sort_boxes:  reorder every page's boxes as the reference's sort_boxes does before cropping.
+ *   rotate_tall: store crops with rows >= 1.5 * cols rotated counter-clockwise (np.rot90(crop, 1)).
+ * outputs (device), entry e = n*max_boxes + r for the r-th box of page n in output order:
+ *   crops_out_dev    uint8 arena of crops_capacity_bytes; crop e is the dense [rows,cols,C] array at byte
+ *                    offsets_out_dev[e] (entries are packed back to back: offsets[e+1]-offsets[e] = its size)
+ *   offsets_out_dev  int64 [N*max_boxes+1]   (the last entry = bytes needed for all crops)
+ *   dims_out_dev     int32 [N*max_boxes,2]   rows, cols as stored (0,0 past the count / degenerate box)
+ *   order_out_dev    int32 [N*max_boxes]     index of the box in the page's input list (-1 past the count)
+ *   status_out_dev   int32 [N]               OCRPP_IMG_BOX_DEGENERATE / OCRPP_IMG_CROPS_TRUNCATED
+ * ------------------------------------------------------------------------------------------- */
+OCRPP_API size_t ocrpp_crop_workspace_bytes(int N, int max_boxes);
+OCRPP_API int ocrpp_crop_boxes(const uint8_t* img_dev, int N, int H, int W, int C, int64_t stride_n, int64_t stride_row,
+                     const int16_t* boxes_dev, const int32_t* counts_dev, int max_boxes, int sort_boxes,
+                     int rotate_tall, uint8_t* crops_out_dev, size_t crops_capacity_bytes,
+                     int64_t* offsets_out_dev, int32_t* dims_out_dev, int32_t* order_out_dev,
+                     int32_t* status_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

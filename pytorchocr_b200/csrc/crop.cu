@@ -1,0 +1,413 @@
+// Text-line crops of detected boxes: the step between the detection path and the
+// recogniser. Replaces, for a whole batch of pages in three launches,
+//   sort_boxes      R/pytocr/utils/utility.py:32-50   (top-to-bottom / left-to-right order)
+//   get_part_img    R/pytocr/utils/utility.py:53-78   (bounding-rect crop, getPerspectiveTransform,
+//                                                      warpPerspective INTER_LINEAR + BORDER_REPLICATE)
+//   the rot90 rule  R/deploy/pytorch/run_ocr.py:188-191 (crops at least 1.5x taller than wide are turned
+//                                                      counter-clockwise)
+// The arithmetic is cv2's for 8-bit images, restated in oracle/crop_oracle.py and pinned there bit for bit:
+// float64 LU solve of the 8x8 system, cofactor inverse, per-pixel fixed-point (5 fractional bits) source
+// coordinates evaluated in cv2's block order, int16 bilinear weights, (sum + 2^14) >> 15. Every float64
+// operation uses the _rn intrinsics so that nvcc cannot contract a*b+c into an FMA (cv2's x86 code has none).
+#include "common.cuh"
+#include "dev_common.cuh"
+
+namespace ocrpp {
+namespace {
+
+constexpr int kPlanThreads = 256;
+constexpr int kWarpThreads = 256;
+constexpr int kChunkPx = 2048;   // destination pixels per work item of the warp kernel
+
+struct CropParams {
+  const uint8_t* img;
+  int N, H, W, C;
+  long long stride_n, stride_row;   // bytes
+  const int16_t* boxes;             // [N,cap,4,2]
+  const int32_t* counts;            // [N] or null (= cap boxes on every page)
+  int cap, sort, rotate_tall;
+  uint8_t* out;
+  unsigned long long capacity;
+  long long* offsets;               // [N*cap+1] byte offset of crop (page n, sorted position r) in `out`
+  int32_t* dims;                    // [N*cap,2] rows, cols as stored (after the rot90 rule)
+  int32_t* order;                   // [N*cap] index into the page's boxes of sorted position r (-1 past the count)
+  int32_t* status;                  // [N]
+  // workspace
+  double* minv;                     // [N*cap,9] inverse transform (destination -> crop-rect coordinates)
+  int4* rect;                       // [N*cap] left, top, clipped source width, height
+  int2* wh;                         // [N*cap] destination w, h before the rot90 rule (w = 0: nothing to do)
+  unsigned long long* local_off;    // [N*cap] byte offset inside the page's share of the arena
+  int32_t* chunk_local;             // [N*cap] exclusive prefix of work items inside the page
+  unsigned long long* page_bytes;   // [N]
+  int32_t* page_chunks;             // [N]
+  int32_t* page_chunk_base;         // [N+1]
+};
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+
+// cv2.getPerspectiveTransform(src, dst) followed by cv2.invert: the matrix warpPerspective iterates with.
+// Returns false for a singular system (collinear corners): cv2 4.13 then falls back to an SVD null-space
+// solution whose pixels mean nothing; such a box is reported as degenerate instead.
+__device__ bool crop_transform(const float* sx, const float* sy, const float* dx, const float* dy, double* out) {
+  double A[8][8], b[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double x = sx[i], y = sy[i], u = dx[i], v = dy[i];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) A[i][c] = A[i + 4][c] = 0.0;
+    A[i][0] = A[i + 4][3] = x;
+    A[i][1] = A[i + 4][4] = y;
+    A[i][2] = A[i + 4][5] = 1.0;
+    A[i][6] = dmul(-x, u);
+    A[i][7] = dmul(-y, u);
+    A[i + 4][6] = dmul(-x, v);
+    A[i + 4][7] = dmul(-y, v);
+    b[i] = u;
+    b[i + 4] = v;
+  }
+  for (int i = 0; i < 8; ++i) {
+    int k = i;
+    for (int j = i + 1; j < 8; ++j)
+      if (fabs(A[j][i]) > fabs(A[k][i])) k = j;
+    if (fabs(A[k][i]) < 2.220446049250313e-16 * 100) return false;
+    if (k != i) {
+      for (int c = i; c < 8; ++c) {
+        const double t = A[i][c];
+        A[i][c] = A[k][c];
+        A[k][c] = t;
+      }
+      const double t = b[i];
+      b[i] = b[k];
+      b[k] = t;
+    }
+    const double d = ddiv(-1.0, A[i][i]);
+    for (int j = i + 1; j < 8; ++j) {
+      const double alpha = dmul(A[j][i], d);
+      for (int c = i + 1; c < 8; ++c) A[j][c] = dadd(A[j][c], dmul(alpha, A[i][c]));
+      b[j] = dadd(b[j], dmul(alpha, b[i]));
+    }
+  }
+  for (int i = 7; i >= 0; --i) {
+    double s = b[i];
+    for (int c = i + 1; c < 8; ++c) s = dsub(s, dmul(A[i][c], b[c]));
+    b[i] = ddiv(s, A[i][i]);
+  }
+  double S[9];
+  for (int i = 0; i < 8; ++i) S[i] = b[i];
+  S[8] = 1.0;
+  const double c00 = dsub(dmul(S[4], S[8]), dmul(S[5], S[7]));
+  const double c01 = dsub(dmul(S[3], S[8]), dmul(S[5], S[6]));
+  const double c02 = dsub(dmul(S[3], S[7]), dmul(S[4], S[6]));
+  const double det = dadd(dsub(dmul(S[0], c00), dmul(S[1], c01)), dmul(S[2], c02));
+  if (det == 0.0) return false;
+  const double d = ddiv(1.0, det);
+  out[0] = dmul(c00, d);
+  out[1] = dmul(dsub(dmul(S[2], S[7]), dmul(S[1], S[8])), d);
+  out[2] = dmul(dsub(dmul(S[1], S[5]), dmul(S[2], S[4])), d);
+  out[3] = dmul(dsub(dmul(S[5], S[6]), dmul(S[3], S[8])), d);
+  out[4] = dmul(dsub(dmul(S[0], S[8]), dmul(S[2], S[6])), d);
+  out[5] = dmul(dsub(dmul(S[2], S[3]), dmul(S[0], S[5])), d);
+  out[6] = dmul(c02, d);
+  out[7] = dmul(dsub(dmul(S[1], S[6]), dmul(S[0], S[7])), d);
+  out[8] = dmul(dsub(dmul(S[0], S[4]), dmul(S[1], S[3])), d);
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: one CTA per page: sort_boxes order, crop geometry + transform of every box, offsets inside the page
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPlanThreads) crop_plan_kernel(CropParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  int cnt = p.counts ? p.counts[n] : p.cap;
+  cnt = max(0, min(cnt, p.cap));
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);   // [cap]; later: byte prefix
+  int* ord = reinterpret_cast<int*>(keys + p.cap);                               // [cap]
+  int* fy = ord + p.cap;                                                         // [cap] first-corner y; later: chunk prefix
+  int* fx = fy + p.cap;                                                          // [cap] first-corner x
+  int* npx = fx + p.cap;                                                         // [cap] destination pixels
+  const int16_t* boxes = p.boxes + (size_t)n * p.cap * 8;
+  const size_t g0 = (size_t)n * p.cap;
+
+  // stable sort by (y, x) of the first corner == rank by (y, x, input index)
+  for (int i = tid; i < cnt; i += kPlanThreads) {
+    const unsigned y = (unsigned)(boxes[i * 8 + 1] + 32768), x = (unsigned)(boxes[i * 8] + 32768);
+    keys[i] = p.sort ? (((unsigned long long)((y << 16) | x) << 32) | (unsigned)i) : (unsigned long long)i;
+  }
+  __syncthreads();
+  for (int i = tid; i < cnt; i += kPlanThreads) {
+    const unsigned long long k = keys[i];
+    int r = 0;
+    for (int j = 0; j < cnt; ++j) r += keys[j] < k;
+    ord[r] = i;
+    fy[r] = boxes[i * 8 + 1];
+    fx[r] = boxes[i * 8];
+  }
+  __syncthreads();
+  if (p.sort && tid == 0 && cnt > 1) {
+    // the reference's single adjacent-swap pass: the box carried forward is compared with the next one
+    int c = ord[0], cy = fy[0], cx = fx[0];
+    for (int i = 0; i + 1 < cnt; ++i) {
+      const int ni = ord[i + 1], ny = fy[i + 1], nx = fx[i + 1];
+      if (abs(ny - cy) < 10 && nx < cx) {
+        ord[i] = ni;
+      } else {
+        ord[i] = c;
+        c = ni;
+        cy = ny;
+        cx = nx;
+      }
+    }
+    ord[cnt - 1] = c;
+  }
+  __syncthreads();
+
+  int flags = 0;
+  for (int r = tid; r < cnt; r += kPlanThreads) {
+    const int b = ord[r];
+    int xs[4], ys[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      xs[k] = boxes[b * 8 + 2 * k];
+      ys[k] = boxes[b * 8 + 2 * k + 1];
+    }
+    const int left = min(min(xs[0], xs[1]), min(xs[2], xs[3])), right = max(max(xs[0], xs[1]), max(xs[2], xs[3]));
+    const int top = min(min(ys[0], ys[1]), min(ys[2], ys[3])), bottom = max(max(ys[0], ys[1]), max(ys[2], ys[3]));
+    const int w = right - left, h = bottom - top;
+    // the reference slices img[top:bottom, left:right]: an empty slice makes cv2 raise; negative corners
+    // would wrap around in numpy - both are reported instead of reproduced
+    bool ok = w >= 1 && h >= 1 && left >= 0 && top >= 0 && left < p.W && top < p.H;
+    if (ok) {
+      float sx[4], sy[4], dx[4], dy[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        sx[k] = (float)(xs[k] - left);
+        sy[k] = (float)(ys[k] - top);
+      }
+      dx[0] = 0.f; dy[0] = 0.f;
+      dx[1] = (float)(w - 1); dy[1] = 0.f;
+      dx[2] = (float)(w - 1); dy[2] = (float)(h - 1);
+      dx[3] = 0.f; dy[3] = (float)(h - 1);
+      double m[9];
+      ok = crop_transform(sx, sy, dx, dy, m);
+      if (ok) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) p.minv[(g0 + r) * 9 + k] = m[k];
+      }
+    }
+    if (!ok) flags |= OCRPP_IMG_BOX_DEGENERATE;
+    p.rect[g0 + r] = make_int4(left, top, min(right, p.W) - left, min(bottom, p.H) - top);
+    p.wh[g0 + r] = ok ? make_int2(w, h) : make_int2(0, 0);
+    npx[r] = ok ? w * h : 0;
+    const bool rot = p.rotate_tall && ok && 2 * h >= 3 * w;   // h >= 1.5 * w
+    p.dims[(g0 + r) * 2] = ok ? (rot ? w : h) : 0;
+    p.dims[(g0 + r) * 2 + 1] = ok ? (rot ? h : w) : 0;
+    p.order[g0 + r] = b;
+  }
+  for (int r = cnt + tid; r < p.cap; r += kPlanThreads) {
+    p.dims[(g0 + r) * 2] = p.dims[(g0 + r) * 2 + 1] = 0;
+    p.order[g0 + r] = -1;
+    p.wh[g0 + r] = make_int2(0, 0);
+  }
+  if (flags) atomicOr(&p.status[n], flags);
+  __syncthreads();
+  if (tid == 0) {   // prefix over at most `cap` entries; 64-bit byte counts
+    unsigned long long bytes = 0;
+    int chunks = 0;
+    for (int r = 0; r < cnt; ++r) {
+      const int px = npx[r];
+      keys[r] = bytes;
+      fy[r] = chunks;
+      bytes += (unsigned long long)px * p.C;
+      chunks += (px + kChunkPx - 1) / kChunkPx;
+    }
+    p.page_bytes[n] = bytes;
+    p.page_chunks[n] = chunks;
+  }
+  __syncthreads();
+  for (int r = tid; r < cnt; r += kPlanThreads) {
+    p.local_off[g0 + r] = keys[r];
+    p.chunk_local[g0 + r] = fy[r];
+  }
+}
+
+// K2: page bases (every CTA sums the totals of the pages before its own) -> global offsets / work-item bases
+__global__ void __launch_bounds__(kPlanThreads) crop_offsets_kernel(CropParams p) {
+  __shared__ unsigned long long s_b[kPlanThreads];
+  __shared__ int s_c[kPlanThreads];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  unsigned long long b = 0;
+  int c = 0;
+  for (int m = tid; m < n; m += kPlanThreads) {
+    b += p.page_bytes[m];
+    c += p.page_chunks[m];
+  }
+  s_b[tid] = b;
+  s_c[tid] = c;
+  __syncthreads();
+  for (int o = kPlanThreads / 2; o > 0; o >>= 1) {
+    if (tid < o) {
+      s_b[tid] += s_b[tid + o];
+      s_c[tid] += s_c[tid + o];
+    }
+    __syncthreads();
+  }
+  const unsigned long long base = s_b[0];
+  const int cbase = s_c[0];
+  int cnt = p.counts ? p.counts[n] : p.cap;
+  cnt = max(0, min(cnt, p.cap));
+  const unsigned long long total = p.page_bytes[n];
+  const size_t g0 = (size_t)n * p.cap;
+  for (int r = tid; r < p.cap; r += kPlanThreads)
+    p.offsets[g0 + r] = (long long)(base + (r < cnt ? p.local_off[g0 + r] : total));
+  if (tid == 0) {
+    p.page_chunk_base[n] = cbase;
+    if (base + total > p.capacity) atomicOr(&p.status[n], OCRPP_IMG_CROPS_TRUNCATED);
+    if (n == p.N - 1) {
+      p.offsets[(size_t)p.N * p.cap] = (long long)(base + total);
+      p.page_chunk_base[p.N] = cbase + p.page_chunks[n];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: persistent CTAs over work items (= up to kChunkPx destination pixels of one crop), thread per pixel
+// ------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(kWarpThreads) crop_warp_kernel(CropParams p) {
+  const int total = p.page_chunk_base[p.N];
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    // page of the item, then the crop inside the page (both by bisection; uniform over the CTA)
+    int lo = 0, hi = p.N - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (p.page_chunk_base[mid] <= item) lo = mid; else hi = mid - 1;
+    }
+    const int n = lo;
+    const int local = item - p.page_chunk_base[n];
+    int cnt = p.counts ? p.counts[n] : p.cap;
+    cnt = max(0, min(cnt, p.cap));
+    const size_t g0 = (size_t)n * p.cap;
+    lo = 0;
+    hi = cnt - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (p.chunk_local[g0 + mid] <= local) lo = mid; else hi = mid - 1;
+    }
+    const size_t g = g0 + lo;
+    const int2 wh = p.wh[g];
+    const int w = wh.x, h = wh.y;
+    const long long off = p.offsets[g];
+    if (w == 0 || (unsigned long long)off + (unsigned long long)w * h * C > p.capacity) continue;
+    const int4 rc = p.rect[g];
+    const double* M = p.minv + g * 9;
+    const double m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5], m6 = M[6], m7 = M[7], m8 = M[8];
+    const bool rot = p.rotate_tall && 2 * h >= 3 * w;
+    const int bh = min(16, h), bw = min(1024 / bh, w);   // cv2's block width: X0/Y0/W0 restart at every block
+    const uint8_t* src = p.img + n * p.stride_n + (long long)rc.y * p.stride_row + (long long)rc.x * C;
+    uint8_t* dst = p.out + off;
+    const int px0 = (local - p.chunk_local[g]) * kChunkPx, px1 = min(w * h, px0 + kChunkPx);
+    for (int q = px0 + threadIdx.x; q < px1; q += kWarpThreads) {
+      const int y = q / w, x = q - y * w;
+      const int xb = (x / bw) * bw;
+      const double dxb = (double)xb, dy = (double)y, dx1 = (double)(x - xb);
+      const double X0 = dadd(dadd(dmul(m0, dxb), dmul(m1, dy)), m2);
+      const double Y0 = dadd(dadd(dmul(m3, dxb), dmul(m4, dy)), m5);
+      const double W0 = dadd(dadd(dmul(m6, dxb), dmul(m7, dy)), m8);
+      double Wv = dadd(W0, dmul(m6, dx1));
+      Wv = Wv != 0.0 ? ddiv(32.0, Wv) : 0.0;
+      const double fX = fmax(-2147483648.0, fmin(2147483647.0, dmul(dadd(X0, dmul(m0, dx1)), Wv)));
+      const double fY = fmax(-2147483648.0, fmin(2147483647.0, dmul(dadd(Y0, dmul(m3, dx1)), Wv)));
+      const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
+      const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+      const int ax = X & 31, ay = Y & 31;
+      // int16 weights round((1-fy)(1-fx) * 2^15) etc.; the only value that saturates is 1.0 -> 32767
+      const int w00 = min(32767, 32 * (32 - ay) * (32 - ax)), w01 = 32 * (32 - ay) * ax;
+      const int w10 = 32 * ay * (32 - ax), w11 = 32 * ay * ax;
+      const int x0 = max(0, min(rc.z - 1, sx)), x1 = max(0, min(rc.z - 1, sx + 1));
+      const int y0 = max(0, min(rc.w - 1, sy)), y1 = max(0, min(rc.w - 1, sy + 1));
+      const uint8_t* r0 = src + (long long)y0 * p.stride_row;
+      const uint8_t* r1 = src + (long long)y1 * p.stride_row;
+      uint8_t* o = dst + (rot ? ((long long)(w - 1 - x) * h + y) : (long long)q) * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int v = r0[x0 * C + c] * w00 + r0[x1 * C + c] * w01 + r1[x0 * C + c] * w10 + r1[x1 * C + c] * w11;
+        o[c] = (uint8_t)max(0, min(255, (v + (1 << 14)) >> 15));
+      }
+    }
+  }
+}
+
+size_t crop_carve(CropParams& p, void* ws) {
+  Carver c{static_cast<char*>(ws), 0};
+  const size_t K = (size_t)p.N * p.cap;
+  p.minv = c.take<double>(K * 9);
+  p.rect = c.take<int4>(K);
+  p.wh = c.take<int2>(K);
+  p.local_off = c.take<unsigned long long>(K);
+  p.chunk_local = c.take<int32_t>(K);
+  p.page_bytes = c.take<unsigned long long>(p.N);
+  p.page_chunks = c.take<int32_t>(p.N);
+  p.page_chunk_base = c.take<int32_t>(p.N + 1);
+  return align_up(c.off, 256);
+}
+
+}  // namespace
+}  // namespace ocrpp
+
+using namespace ocrpp;
+
+extern "C" size_t ocrpp_crop_workspace_bytes(int N, int max_boxes) {
+  if (N <= 0 || max_boxes <= 0) return 0;
+  CropParams p{};
+  p.N = N;
+  p.cap = max_boxes;
+  return crop_carve(p, nullptr);
+}
+
+extern "C" int ocrpp_crop_boxes(const uint8_t* img_dev, int N, int H, int W, int C, int64_t stride_n, int64_t stride_row,
+                                const int16_t* boxes_dev, const int32_t* counts_dev, int max_boxes, int sort_boxes,
+                                int rotate_tall, uint8_t* crops_out_dev, size_t crops_capacity_bytes,
+                                int64_t* offsets_out_dev, int32_t* dims_out_dev, int32_t* order_out_dev,
+                                int32_t* status_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  OCRPP_CHECK_ARG(img_dev && boxes_dev && offsets_out_dev && dims_out_dev && order_out_dev && status_out_dev,
+                  "ocrpp_crop_boxes: null pointer");
+  OCRPP_CHECK_ARG(crops_out_dev || crops_capacity_bytes == 0, "ocrpp_crop_boxes: null crop arena");
+  OCRPP_CHECK_ARG(N > 0 && H > 0 && W > 0 && H <= 32767 && W <= 32767, "ocrpp_crop_boxes: bad shape N=%d H=%d W=%d", N, H, W);
+  OCRPP_CHECK_ARG(C == 1 || C == 3 || C == 4, "ocrpp_crop_boxes: channels must be 1, 3 or 4 (got %d)", C);
+  OCRPP_CHECK_ARG(max_boxes > 0 && max_boxes <= 8192, "ocrpp_crop_boxes: max_boxes must be in [1, 8192] (got %d)", max_boxes);
+  OCRPP_CHECK_ARG(stride_row >= (int64_t)W * C && (N == 1 || stride_n >= stride_row * H), "ocrpp_crop_boxes: bad strides");
+  CropParams p{};
+  p.img = img_dev;
+  p.N = N; p.H = H; p.W = W; p.C = C;
+  p.stride_n = stride_n; p.stride_row = stride_row;
+  p.boxes = boxes_dev; p.counts = counts_dev;
+  p.cap = max_boxes; p.sort = sort_boxes ? 1 : 0; p.rotate_tall = rotate_tall ? 1 : 0;
+  p.out = crops_out_dev; p.capacity = crops_capacity_bytes;
+  p.offsets = reinterpret_cast<long long*>(offsets_out_dev);
+  p.dims = dims_out_dev; p.order = order_out_dev; p.status = status_out_dev;
+  const size_t need = crop_carve(p, workspace_dev);
+  if (workspace_bytes < need || !workspace_dev)
+    return set_error(OCRPP_ERR_WORKSPACE_TOO_SMALL, "ocrpp_crop_boxes: workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ProfileScope prof(s);
+  OCRPP_CUDA(cudaMemsetAsync(status_out_dev, 0, sizeof(int32_t) * N, s));
+  const size_t smem = (size_t)max_boxes * 24;
+  if (smem > 48 * 1024)
+    OCRPP_CUDA(cudaFuncSetAttribute(crop_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  crop_plan_kernel<<<N, kPlanThreads, smem, s>>>(p);
+  OCRPP_LAUNCHED();
+  crop_offsets_kernel<<<N, kPlanThreads, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  prof.mark("crop_plan");
+  const int grid = kNumSMs * 8;
+  if (C == 1) crop_warp_kernel<1><<<grid, kWarpThreads, 0, s>>>(p);
+  else if (C == 3) crop_warp_kernel<3><<<grid, kWarpThreads, 0, s>>>(p);
+  else crop_warp_kernel<4><<<grid, kWarpThreads, 0, s>>>(p);
+  OCRPP_LAUNCHED();
+  prof.mark("crop_warp");
+  return OCRPP_OK;
+}

@@ -329,3 +329,36 @@ def ctc_probs_torch(seed, T, B, C, device, chunk=512):
         out[:, b0:b1] = torch.softmax(logits, dim=2)
         del logits
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# pages + detected boxes for the text-line crop step
+# ------------------------------------------------------------------------------------------------
+def page_image(seed, H=736, W=1280, C=3):
+    """uint8 page with structure at every scale (so that a wrong tap or weight changes the result)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W]
+    base = 127 + 80 * np.sin(xx[..., None] * (0.05 + 0.03 * np.arange(C)) + yy[..., None] * 0.07)
+    img = base + rng.integers(-47, 48, (H, W, C))
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def page_boxes(seed, n=200, H=736, W=1280, tall_frac=0.1, skew=2.0, scale=1.0):
+    """int16 [n,4,2] text-line quads as a detector emits them (TL,TR,BR,BL, inside the page): rotated
+    rectangles, a share of them tall (rot90 rule), corners jittered by `skew` px so that the transform is a
+    true perspective map; clustered first-corner rows exercise the swap pass of sort_boxes."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((n, 4, 2), np.int16)
+    rows = rng.integers(20, H - 20, max(1, n // 6))
+    for i in range(n):
+        hw, hh = rng.uniform(15, 60) * scale, rng.uniform(5, 14) * scale
+        if rng.random() < tall_frac:
+            hw, hh = hh, hw * 0.8
+        a = rng.uniform(-0.35, 0.35) if rng.random() < 0.8 else 0.0
+        cx = rng.uniform(hw + hh + 4, W - hw - hh - 4)
+        cy = float(np.clip(rows[rng.integers(len(rows))] + rng.uniform(-6, 6), hw + hh + 4, H - hw - hh - 4))
+        c, s_ = np.cos(a), np.sin(a)
+        q = np.array([[-hw, -hh], [hw, -hh], [hw, hh], [-hw, hh]])
+        q = q @ np.array([[c, s_], [-s_, c]]) + [cx, cy] + rng.uniform(-skew, skew, (4, 2))
+        out[i] = np.clip(np.round(q), 0, [W, H]).astype(np.int16)
+    return out

@@ -1,6 +1,7 @@
 """Generates tests/golden/*.npz by running the REFERENCE ITSELF in the authoring container.
 
     python tests/golden/make_golden.py          (needs /root/reference and oracle/_ref built)
+    python tests/golden/make_golden.py crops    (reference_crops.npz only: sort_boxes / get_part_img)
 
 What runs unmodified from /root/reference (imported in place, nothing is copied):
   * pytocr.postprocess.pse_postprocess.PSEPostProcess    (whole operator incl. generate_box)
@@ -167,5 +168,33 @@ def main():
           {k: v.shape for k, v in out.items() if "points" in k})
 
 
+def main_crops():
+    """tests/golden/reference_crops.npz: the reference's own sort_boxes / get_part_img (imported in place from
+    /root/reference/pytocr/utils/utility.py) on one small synthetic page."""
+    import importlib.util
+    from pytorchocr_b200 import synth
+    spec = importlib.util.spec_from_file_location("ref_utility", os.path.join(REF, "pytocr", "utils", "utility.py"))
+    U = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(U)
+    H, W = 200, 320
+    img = synth.page_image(31, H, W)
+    boxes = synth.page_boxes(32, n=24, H=H, W=W, tall_frac=0.2)
+    sorted_boxes = U.sort_boxes(boxes)
+    crops = []
+    for b in sorted_boxes:
+        part = U.get_part_img(img, b)
+        if part.shape[0] >= 1.5 * part.shape[1]:          # run_ocr.py:190-191
+            part = np.rot90(part, 1)
+        crops.append(np.ascontiguousarray(part))
+    out = dict(img=img, boxes=boxes, sorted_boxes=np.asarray(sorted_boxes, np.int16),
+               dims=np.array([c.shape[:2] for c in crops], np.int32),
+               pixels=np.concatenate([c.reshape(-1) for c in crops]))
+    np.savez_compressed(os.path.join(HERE, "reference_crops.npz"), **out)
+    print("wrote reference_crops.npz", out["dims"].tolist())
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "crops":
+        main_crops()
+    else:
+        main()
