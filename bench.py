@@ -31,6 +31,7 @@ DB_CFG = dict(thresh=0.3, box_thresh=0.5, max_candidates=1000, unclip_ratio=1.7,
 PSE_CFG = dict(thresh=0, box_thresh=0.85, min_area=16, scale=1)                          # det_r50_pse.yml:56-62
 PAN_CFG = dict(thresh=0, box_thresh=0.85, min_area=16, min_kernel_area=2.6, scale=1)     # det_r18_pan.yml:62-69 at full res
 CTC_T, CTC_C = 80, 6623
+CROP_BOXES = 200
 
 
 # ----------------------------------------------------------------------------------------------
@@ -91,6 +92,23 @@ def _cpu_ctc(args):
     t0 = time.perf_counter()
     r = op(x)
     return time.perf_counter() - t0, len(r)
+
+
+def _gen_page(seed):
+    from pytorchocr_b200 import synth
+    return synth.page_image(seed, H, W), synth.page_boxes(seed + 100000, n=CROP_BOXES, H=H, W=W)
+
+
+def _cpu_crop(page):
+    import cv2
+    cv2.setNumThreads(1)
+    from oracle import crop_oracle as co
+    img, boxes = page
+    t0 = time.perf_counter()
+    n = 0
+    for b in co.sort_boxes(boxes):          # run_ocr.py:181-191: sort, crop, rot90 rule
+        n += co.crop_for_rec(img, b).size
+    return time.perf_counter() - t0, n
 
 
 def _timed_pool(pool, fn, items, cores):
@@ -400,7 +418,90 @@ class CtcWorkload(Workload):
                 "e2e_region": "%d-line chunks: pinned host probabilities -> python strings" % self.host_chunk.shape[1]}
 
 
-WORKLOADS = {"db": DbWorkload, "pse": PseWorkload, "pan": PanWorkload, "ctc": CtcWorkload}
+class CropWorkload(Workload):
+    """the text-line crops between the detector and the recogniser."""
+    name = "crop"
+    unit = "images/s"
+    metric = "text-line crop pages/sec @736x1280 (200 boxes per page)"
+    default_batch = 64
+    dtype = "u8"
+    stream_kernel = "crop_warp_kernel"
+    stream_phase = 1
+    workload = ("sort_boxes + get_part_img + rot90 rule for 200 detected boxes on each of 64 synthetic 736x1280x3 uint8 "
+                "pages per GPU (the step after BASELINE.json configs[1]'s detector path)")
+
+    def alg_bytes_per_unit(self):
+        # every crop pixel written once and the source pixels under it read once
+        return 2 * self.crop_bytes // self.batch
+
+    def host_prepare(self, pool, want_cpu):
+        seeds = [SEED + self.rank * 1000 + i for i in range(self.batch)]
+        self.pages = pool.map(_gen_page, seeds, chunksize=2)
+        if not want_cpu:
+            return None
+        sample = self.pages[:max(16, self.cores)] * 4
+        out, dt = _timed_pool(pool, _cpu_crop, sample, self.cores)
+        inner = sum(o[0] for o in out)
+        return {"value": len(sample) / (inner / self.cores), "unit": self.unit, "cores": self.cores, "kind": "port",
+                "sample": "%d pages of this step (4 passes), multiprocessing.Pool(%d), cv2.setNumThreads(1), crop time "
+                          "only (%.2f s summed); oracle/crop_oracle.py = the reference's own sequence of cv2 calls "
+                          "(utility.py:32-78)" % (len(sample), self.cores, inner)}
+
+    def device_prepare(self, dev):
+        import torch
+        from pytorchocr_b200.part_img import PartImageCropper
+        self.torch, self.dev = torch, dev
+        self.op = PartImageCropper()
+        self.host_imgs = torch.from_numpy(np.stack([p[0] for p in self.pages])).pin_memory()
+        self.host_boxes = torch.from_numpy(np.stack([p[1] for p in self.pages])).pin_memory()
+        self.imgs = self.host_imgs.to(dev)
+        self.boxes = self.host_boxes.to(dev)
+        self.counts = torch.full((self.batch,), CROP_BOXES, dtype=torch.int32, device=dev)
+        arena, offsets, dims, order, status = self.op.run_device(self.imgs, self.boxes, self.counts)
+        assert not status.any(), status
+        self.crop_bytes = int(offsets[-1])
+        self.n_boxes = self.batch * CROP_BOXES
+        self.buf = next(iter(self.op._bufs.values()))
+        K = self.batch * CROP_BOXES
+        self.meta_host = torch.empty(self.buf["meta"].numel(), dtype=torch.int32, pin_memory=True)
+        self.crops_host = torch.empty(self.crop_bytes, dtype=torch.uint8, pin_memory=True)
+        self.K = K
+
+    def device_step(self, L, stream):
+        from pytorchocr_b200 import _lib
+        b, K = self.buf, self.K
+        base = b["meta"].data_ptr()
+        o_dims = base + 8 * (K + 1)
+        _lib.check(L.ocrpp_crop_boxes(self.imgs.data_ptr(), self.batch, H, W, 3, self.imgs.stride(0), self.imgs.stride(1),
+                                      self.boxes.data_ptr(), self.counts.data_ptr(), CROP_BOXES, 1, 1,
+                                      b["arena"].data_ptr(), b["arena"].numel(), base, o_dims, o_dims + 8 * K,
+                                      o_dims + 12 * K, b["ws"].data_ptr(), b["ws"].numel(), stream.cuda_stream))
+        self.meta_host.copy_(b["meta"], non_blocking=True)      # offsets / dims / order / status; the crops stay in HBM
+
+    def e2e_step(self):
+        imgs = self.host_imgs.to(self.dev, non_blocking=True)
+        boxes = self.host_boxes.to(self.dev, non_blocking=True)
+        arena, offsets, dims, order, status = self.op.run_device(imgs, boxes, self.counts)
+        self.crops_host.copy_(arena[:self.crop_bytes], non_blocking=True)     # the crops themselves come back
+        self.torch.cuda.current_stream().synchronize()
+        return offsets
+
+    def h2d_bytes(self):
+        return int(self.host_imgs.numel() + self.host_boxes.numel() * 2)
+
+    def d2h_bytes(self):
+        return int(self.crop_bytes + self.meta_host.numel() * 4)
+
+    def config(self):
+        return {"batch_per_gpu": self.batch, "H": H, "W": W, "boxes_per_page": CROP_BOXES,
+                "crop_bytes_per_step": self.crop_bytes,
+                "l2": "pages (%.0f MB per GPU) larger than the 126 MB L2; no flush needed" % (self.batch * H * W * 3 / 1e6),
+                "timed_region": "device pages + device boxes -> crops in a device arena (where the recogniser reads "
+                                "them), offsets/dims/order in pinned host memory",
+                "e2e_region": "pinned host pages + boxes -> crops in pinned host memory"}
+
+
+WORKLOADS = {"db": DbWorkload, "pse": PseWorkload, "pan": PanWorkload, "ctc": CtcWorkload, "crop": CropWorkload}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -424,6 +525,11 @@ def run_reference(args):
             items = [SEED + i for i in range(sample)]
             fn, units = (_cpu_pse if args.workload == "pse" else _cpu_pan), sample
             what = "%d maps" % sample
+        elif args.workload == "crop":
+            sample = max(16, cores)
+            items = pool.map(_gen_page, [SEED + i for i in range(sample)], chunksize=2) * 8
+            fn, units = _cpu_crop, sample * 8
+            what = "%d pages" % (sample * 8)
         else:
             import tempfile
             from pytorchocr_b200 import synth
@@ -447,10 +553,13 @@ def run_reference(args):
         "config": {"workload": wl.workload + "; each step = a bounded sample (%s) on the host cores" % what,
                    "H": H, "W": W},
         "cpu_baseline": {"value": rate, "unit": wl.unit, "cores": cores, "kind": "port",
-                         "sample": "%s x %d steps, multiprocessing.Pool(%d), cv2.setNumThreads(1); the oracle port of "
-                                   "the reference's CPU path (oracle/): db_postprocess.cpp needs OpenCV C++ and cannot be "
-                                   "built here, pse.pyx/pa.pyx are restated in C and pinned against the compiled reference"
-                                   % (what, args.steps, cores)},
+                         "sample": "%s x %d steps, multiprocessing.Pool(%d), cv2.setNumThreads(1); %s"
+                                   % (what, args.steps, cores,
+                                      "oracle/crop_oracle.py: the reference's own sequence of cv2 calls (utility.py:32-78)"
+                                      if args.workload == "crop" else
+                                      "the oracle port of the reference's CPU path (oracle/): db_postprocess.cpp needs "
+                                      "OpenCV C++ and cannot be built here, pse.pyx/pa.pyx are restated in C and pinned "
+                                      "against the compiled reference")},
         "e2e": {"value": rate, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -548,7 +657,8 @@ def run_ours(args):
         peak_src = ("MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks
                     else "fallback 6.65 TB/s (B200_PROFILING.md)")
         alg_bytes = wl.batch * wl.alg_bytes_per_unit()
-        k1_ms = phases[0][1] / max(1, calls) if phases else None
+        sp = getattr(wl, "stream_phase", 0)
+        k1_ms = phases[sp][1] / max(1, calls) if len(phases) > sp else None
         achieved = alg_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms else None
         traffic = None
         try:
