@@ -160,6 +160,9 @@ def boxes_from_bitmap(pred, bitmap, box_thresh, unclip_ratio, src_w, src_h,
     for ci in range(num_contours):
         contour = contours[ci].reshape(-1, 2)
         d = {"contour_first": (int(contour[0][0]), int(contour[0][1])), "npts": len(contour), "status": "ok"}
+        if return_details:   # what the parity tests need to enumerate exact equal-area ties (tests/db_compare.py)
+            d["contour"] = contour.copy()
+            d["unclip_ratio"], d["scale"] = unclip_ratio, (width, height, src_w, src_h)
         details.append(d)
         if len(contour) <= 2:
             d["status"] = "le2pts"

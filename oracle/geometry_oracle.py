@@ -52,6 +52,52 @@ def _unit_normal(p1, p2):
     return (dy, -dx)
 
 
+def tied_min_area_rects(points, rel=1e-9, corners=False):
+    """All edge-aligned minimum-area rectangles of an integer point set, as cv2 RotatedRect tuples
+    ((cx, cy), (w, h), angle_deg), one per hull-edge direction (mod 90 degrees) whose rectangle area equals the
+    minimum (exact integer projections, so `equal` is decided exactly). cv2.minAreaRect returns ONE of them,
+    chosen by float32 noise in its rotating calipers; the parity tests accept any. `rel` widens
+    "equal" to near-ties below cv2's float32 resolution; corners=True returns the exact float64 corner arrays
+    [4,2] instead (no float32 boxPoints noise)."""
+    import cv2
+    pts = np.asarray(points, np.int64).reshape(-1, 2)
+    h = cv2.convexHull(pts.astype(np.int32)).reshape(-1, 2).astype(np.int64)
+    m = len(h)
+    if m < 3:
+        return []
+    cands = []
+    for i in range(m):
+        d = h[(i + 1) % m] - h[i]
+        l2 = int(d @ d)
+        if l2 == 0:
+            continue
+        s = (h - h[i]) @ d
+        t = (h - h[i]) @ np.array([-d[1], d[0]])
+        num = int(s.max() - s.min()) * int(t.max() - t.min())          # area * l2, exact
+        cands.append((num, l2, i, d, s, t))
+    best = min(c[0] / c[1] for c in cands)
+    out, seen = [], []
+    for num, l2, i, d, s, t in cands:
+        if num / l2 > best * (1 + rel) + 1e-12:
+            continue
+        ang = np.degrees(np.arctan2(float(d[1]), float(d[0]))) % 90.0
+        if any(min(abs(ang - a), 90 - abs(ang - a)) < 1e-7 for a in seen):
+            continue
+        seen.append(ang)
+        ln = np.sqrt(l2)
+        u = d / ln
+        v = np.array([-d[1], d[0]]) / ln
+        sc, tc = (s.max() + s.min()) / 2.0 / ln, (t.max() + t.min()) / 2.0 / ln
+        if corners:
+            s0, s1, t0, t1 = s.min() / ln, s.max() / ln, t.min() / ln, t.max() / ln
+            out.append(np.array([h[i] + u * a + v * b for a, b in ((s0, t0), (s1, t0), (s1, t1), (s0, t1))]))
+            continue
+        c = h[i] + u * sc + v * tc
+        out.append(((float(c[0]), float(c[1])), (float((s.max() - s.min()) / ln), float((t.max() - t.min()) / ln)),
+                    float(np.degrees(np.arctan2(float(d[1]), float(d[0]))))))
+    return out
+
+
 def do_offset(path, delta, arc_tolerance=0.25):
     """Raw m_destPoly of DoOffset for one etClosedPolygon/jtRound path (list of int (x,y)).
     Returns a list of int (x,y); empty when AddPath rejects the path."""

@@ -78,7 +78,7 @@ def generate_box(score, label, shape, min_area, box_thresh, return_details=False
         scores.append(score_i)
         if return_details:
             details.append({"label": i, "area": int(pix.size), "score": float(score_i),
-                            "rect": rect, "box_f": pre,
+                            "rect": rect, "box_f": pre, "hull": cv2.convexHull(points.astype(np.int32)).reshape(-1, 2),
                             "box_scaled": np.stack([pre[:, 0] / ratio_w, pre[:, 1] / ratio_h], 1)})
     boxes = np.array(boxes, dtype=np.int16)
     if return_details:

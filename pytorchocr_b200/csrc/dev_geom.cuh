@@ -236,8 +236,9 @@ __device__ int group_do_offset_quad(const P2i* quad, double delta, P2i* out, int
   const int src = ((threadIdx.x & 31) & ~(kGrp - 1)) + k;
   nkx = __shfl_sync(gmask, njx, src);
   nky = __shfl_sync(gmask, njy, src);
-  double sin_a = nkx * njy - njx * nky;
-  const double cos_a = nkx * njx + njy * nky;
+  // products and sums rounded one by one, as in the reference's x86 build (see geom::dmul)
+  double sin_a = geom::dsub(geom::dmul(nkx, njy), geom::dmul(njx, nky));
+  const double cos_a = geom::dadd(geom::dmul(nkx, njx), geom::dmul(njy, nky));
   int kind = 1, ns = 0;  // 1: round join, 2: concave (3 points)
   if (fabs(sin_a * delta) < 1.0) {
     if (cos_a > 0) kind = 0;  // Clipper emits one point and does NOT advance k: sequential routine
@@ -247,8 +248,8 @@ __device__ int group_do_offset_quad(const P2i* quad, double delta, P2i* out, int
   if (kind == 1) {
     if (sin_a * delta < 0) kind = 2;
     else {
-      ang = atan2(sin_a, nkx * njx + nky * njy);
-      long long n = geom::clipper_round(steps_per_rad * fabs(ang));
+      ang = atan2(sin_a, geom::dadd(geom::dmul(nkx, njx), geom::dmul(nky, njy)));
+      long long n = geom::clipper_round(geom::dmul(steps_per_rad, fabs(ang)));
       if (n < 1) n = 1;
       ns = n > 100000 ? 100000 : (int)n;
     }
@@ -269,21 +270,22 @@ __device__ int group_do_offset_quad(const P2i* quad, double delta, P2i* out, int
     total += cq;
   }
   if (total > cap) return -1;
+  auto ofs = [delta](int cc, double nn) { return (int)geom::clipper_round(geom::dadd((double)cc, geom::dmul(nn, delta))); };
   if (gl < 4) {
     P2i* o = out + off;
     if (kind == 2) {
-      o[0] = P2i{(int)geom::clipper_round(c[j].x + nkx * delta), (int)geom::clipper_round(c[j].y + nky * delta)};
+      o[0] = P2i{ofs(c[j].x, nkx), ofs(c[j].y, nky)};
       o[1] = c[j];
-      o[2] = P2i{(int)geom::clipper_round(c[j].x + njx * delta), (int)geom::clipper_round(c[j].y + njy * delta)};
+      o[2] = P2i{ofs(c[j].x, njx), ofs(c[j].y, njy)};
     } else {
       double X = nkx, Y = nky;
       for (int i = 0; i < ns; ++i) {
-        o[i] = P2i{(int)geom::clipper_round(c[j].x + X * delta), (int)geom::clipper_round(c[j].y + Y * delta)};
+        o[i] = P2i{ofs(c[j].x, X), ofs(c[j].y, Y)};
         const double X2 = X;
-        X = X * m_cos - m_sin * Y;
-        Y = X2 * m_sin + Y * m_cos;
+        X = geom::dsub(geom::dmul(X, m_cos), geom::dmul(m_sin, Y));
+        Y = geom::dadd(geom::dmul(X2, m_sin), geom::dmul(Y, m_cos));
       }
-      o[ns] = P2i{(int)geom::clipper_round(c[j].x + njx * delta), (int)geom::clipper_round(c[j].y + njy * delta)};
+      o[ns] = P2i{ofs(c[j].x, njx), ofs(c[j].y, njy)};
     }
   }
   return total;

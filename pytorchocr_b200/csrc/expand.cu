@@ -205,6 +205,14 @@ constexpr int kRunThreads = 512;
 __device__ __forceinline__ unsigned run_starts(unsigned w, unsigned prev) { return w & ~((w << 1) | (prev >> 31)); }
 __device__ __forceinline__ unsigned run_ends(unsigned w, unsigned next) { return w & ~((w >> 1) | (next << 31)); }
 
+// run count of mask m of image n for every kernel AFTER ex_runs_kernel: when either mask overflowed the run
+// table, the other one's table is complete but the tables no longer describe the same image (a seed's text
+// run is looked up in a table that was never written), so the image is treated as empty from here on - it is
+// reported through OCRPP_IMG_RUN_OVERFLOW and its outputs are dropped anyway
+__device__ __forceinline__ int ex_nruns(const ExParams& p, int n, int m) {
+  return (p.imgflags[n] & OCRPP_IMG_RUN_OVERFLOW) ? 0 : p.nruns[n * 2 + m];
+}
+
 __global__ void __launch_bounds__(kRunThreads) ex_runs_kernel(ExParams p) {
   extern __shared__ int s_rowcnt[];  // [H+1]
   const int n = blockIdx.y + p.n0, m = blockIdx.z;
@@ -305,7 +313,7 @@ constexpr int kRunBlk = 256;
 // E3: 4-connectivity: link every run with the runs of the row above that overlap [xs, xe].
 __global__ void __launch_bounds__(kRunBlk) ex_link_kernel(ExParams p) {
   const int n = blockIdx.y + p.n0, m = blockIdx.z;
-  const int nr = p.nruns[n * 2 + m];
+  const int nr = ex_nruns(p, n, m);
   const size_t ro = (size_t)(n * 2 + m) * p.R;
   const int32_t* rowptr = p.rowptr + (size_t)(n * 2 + m) * (p.H + 1);
   const uint16_t *xs = p.run_xs + ro, *xe = p.run_xe + ro, *ry = p.run_y + ro;
@@ -327,7 +335,7 @@ __global__ void __launch_bounds__(kRunBlk) ex_link_kernel(ExParams p) {
 // E4: flatten + per-root reductions (text: area and bounding box; seed: area).
 __global__ void __launch_bounds__(kRunBlk) ex_flatten_kernel(ExParams p) {
   const int n = blockIdx.y + p.n0, m = blockIdx.z;
-  const int nr = p.nruns[n * 2 + m];
+  const int nr = ex_nruns(p, n, m);
   const size_t ro = (size_t)(n * 2 + m) * p.R, so = (size_t)n * p.R;
   const uint16_t *xs = p.run_xs + ro, *xe = p.run_xe + ro, *ry = p.run_y + ro;
   int32_t* par = p.par + ro;
@@ -360,7 +368,7 @@ __device__ __forceinline__ int ex_run_at(const int32_t* rowptr, const uint16_t* 
 // component, work items, and (PAN) the per-text-component extreme kernel areas. One CTA per image.
 __global__ void __launch_bounds__(kRunThreads) ex_seed_kernel(ExParams p) {
   const int n = blockIdx.x + p.n0;
-  const int nr = p.nruns[n * 2 + 1];
+  const int nr = ex_nruns(p, n, 1);
   const size_t to = (size_t)(n * 2 + 0) * p.R, ro = (size_t)(n * 2 + 1) * p.R, so = (size_t)n * p.R;
   const int32_t* t_rowptr = p.rowptr + (size_t)(n * 2 + 0) * (p.H + 1);
   const int chunk = (nr + kRunThreads - 1) / kRunThreads;
@@ -394,7 +402,7 @@ __global__ void __launch_bounds__(kRunThreads) ex_seed_kernel(ExParams p) {
   // directly and only components with two or more kernels become work items of ex_expand_kernel.
   // PSE has no such shortcut: a pixel that claimed a neighbour is not revisited at later levels
   // (pse.pyx:47,58-60), so which text pixels stay unlabelled depends on the pop order even for one seed.
-  const int nt = p.nruns[n * 2 + 0];
+  const int nt = ex_nruns(p, n, 0);
   const int min_seeds = p.mode == kModePan ? 2 : 1;
   for (int r = threadIdx.x; r < nt; r += kRunThreads) {
     if (p.par[to + r] != r || p.t_nseed[so + r] < min_seeds) continue;
@@ -410,7 +418,7 @@ __global__ void __launch_bounds__(kRunThreads) ex_seed_kernel(ExParams p) {
 template <typename T>
 __global__ void __launch_bounds__(kRunBlk) ex_pan_flag_kernel(ExParams p) {
   const int n = blockIdx.y + p.n0;
-  const int nr = p.nruns[n * 2 + 1];
+  const int nr = ex_nruns(p, n, 1);
   const size_t ro = (size_t)(n * 2 + 1) * p.R, so = (size_t)n * p.R;
   EX_FOR_EACH_RUN(r, nr) {
     const int root = p.par[ro + r];
@@ -437,7 +445,7 @@ __global__ void __launch_bounds__(kRunBlk) ex_pan_flag_kernel(ExParams p) {
 // One warp per run.
 __global__ void __launch_bounds__(kRunBlk) ex_paint_kernel(ExParams p, int m) {
   const int n = blockIdx.y + p.n0;
-  const int nr = p.nruns[n * 2 + m];
+  const int nr = ex_nruns(p, n, m);
   const size_t ro = (size_t)(n * 2 + m) * p.R, so = (size_t)n * p.R;
   uint32_t* st = p.st + (size_t)n * p.H * p.W;
   // 8 lanes per run (one 32-byte sector per store instruction): text runs are a few dozen pixels long and
@@ -886,7 +894,7 @@ __global__ void __launch_bounds__(kExThreads) ex_expand_kernel(ExParams p) {
 template <typename T, int PASS>
 __global__ void __launch_bounds__(kRunBlk) ex_stats_kernel(ExParams p) {
   const int n = blockIdx.y + p.n0;
-  const int nr = p.nruns[n * 2 + 0];
+  const int nr = ex_nruns(p, n, 0);
   const size_t ro = (size_t)(n * 2 + 0) * p.R, so = (size_t)n * p.R;
   const uint32_t* st = p.st + (size_t)n * p.H * p.W;
   const int lane = threadIdx.x & 31, wpb = kRunBlk / 32;
@@ -944,7 +952,7 @@ __global__ void __launch_bounds__(kRunBlk) ex_stats_kernel(ExParams p) {
 // pse_postprocess.py:70); row-extent slots. One CTA per image.
 __global__ void __launch_bounds__(kRunThreads) ex_cand_kernel(ExParams p) {
   const int n = blockIdx.x + p.n0;
-  const int nr = p.nruns[n * 2 + 1];
+  const int nr = ex_nruns(p, n, 1);
   const size_t ro = (size_t)(n * 2 + 1) * p.R, so = (size_t)n * p.R;
   const int chunk = (nr + kRunThreads - 1) / kRunThreads;
   const int lo = min(nr, (int)threadIdx.x * chunk), hi = min(nr, lo + chunk);
@@ -1136,7 +1144,7 @@ __global__ void __launch_bounds__(kRunThreads) ex_compact_kernel(ExParams p) {
 // debug / parity: the label map pse()/pa() return (cv2 ids), at processing resolution
 __global__ void __launch_bounds__(kRunBlk) ex_labels_kernel(ExParams p) {
   const int n = blockIdx.y + p.n0;
-  const int nr = p.nruns[n * 2 + 0];
+  const int nr = ex_nruns(p, n, 0);
   const size_t ro = (size_t)(n * 2 + 0) * p.R, so = (size_t)n * p.R;
   const uint32_t* st = p.st + (size_t)n * p.H * p.W;
   int32_t* lab = p.labels_dbg + (size_t)n * p.H * p.W;

@@ -73,6 +73,33 @@ OCRPP_HD float fdiv(float a, float b) {
   return r;
 #endif
 }
+// float64 likewise: the reference's Clipper is plain x86-64 code (every product and sum rounded on its own). A
+// contracted a*b+c*d leaves a residual of one rounding error, which is enough to flip Clipper's `cosA > 0` test
+// for an exactly right-angled corner (found by tests/stress_gpu.py on a thin 45-degree box).
+OCRPP_HD double dmul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(a, b);
+#else
+  volatile double r = a * b;
+  return r;
+#endif
+}
+OCRPP_HD double dadd(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(a, b);
+#else
+  volatile double r = a + b;
+  return r;
+#endif
+}
+OCRPP_HD double dsub(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dsub_rn(a, b);
+#else
+  volatile double r = a - b;
+  return r;
+#endif
+}
 OCRPP_HD float fsqrt(float a) {
 #if defined(__CUDA_ARCH__)
   return __fsqrt_rn(a);
@@ -342,6 +369,7 @@ OCRPP_HD int do_offset_quad(const P2i* quad, double delta, P2i* out, int cap) {
   }
   int m = 0;
   int k = n - 1;
+#define OCRPP_OFS(C, N) clipper_round(dadd((double)(C), dmul((N), delta)))
 #define OCRPP_EMIT(X, Y)                                  \
   do {                                                    \
     if (m >= cap) return -1;                              \
@@ -350,35 +378,36 @@ OCRPP_HD int do_offset_quad(const P2i* quad, double delta, P2i* out, int cap) {
     ++m;                                                  \
   } while (0)
   for (int j = 0; j < n; ++j) {  // OffsetPoint :4160-4201
-    double sin_a = nx[k] * ny[j] - nx[j] * ny[k];
+    double sin_a = dsub(dmul(nx[k], ny[j]), dmul(nx[j], ny[k]));
     if (fabs(sin_a * delta) < 1.0) {
-      const double cos_a = nx[k] * nx[j] + ny[j] * ny[k];
+      const double cos_a = dadd(dmul(nx[k], nx[j]), dmul(ny[j], ny[k]));
       if (cos_a > 0) {
-        OCRPP_EMIT(clipper_round(c[j].x + nx[k] * delta), clipper_round(c[j].y + ny[k] * delta));
+        OCRPP_EMIT(OCRPP_OFS(c[j].x, nx[k]), OCRPP_OFS(c[j].y, ny[k]));
         continue;  // returns before `k = j` (:4172)
       }
     } else if (sin_a > 1.0) sin_a = 1.0;
     else if (sin_a < -1.0) sin_a = -1.0;
     if (sin_a * delta < 0) {
-      OCRPP_EMIT(clipper_round(c[j].x + nx[k] * delta), clipper_round(c[j].y + ny[k] * delta));
+      OCRPP_EMIT(OCRPP_OFS(c[j].x, nx[k]), OCRPP_OFS(c[j].y, ny[k]));
       OCRPP_EMIT(c[j].x, c[j].y);
-      OCRPP_EMIT(clipper_round(c[j].x + nx[j] * delta), clipper_round(c[j].y + ny[j] * delta));
+      OCRPP_EMIT(OCRPP_OFS(c[j].x, nx[j]), OCRPP_OFS(c[j].y, ny[j]));
     } else {  // DoRound :4225-4244
-      const double a = atan2(sin_a, nx[k] * nx[j] + ny[k] * ny[j]);
-      long long ns = clipper_round(steps_per_rad * fabs(a));
+      const double a = atan2(sin_a, dadd(dmul(nx[k], nx[j]), dmul(ny[k], ny[j])));
+      long long ns = clipper_round(dmul(steps_per_rad, fabs(a)));
       if (ns < 1) ns = 1;
       double X = nx[k], Y = ny[k];
       for (long long i = 0; i < ns; ++i) {
-        OCRPP_EMIT(clipper_round(c[j].x + X * delta), clipper_round(c[j].y + Y * delta));
+        OCRPP_EMIT(OCRPP_OFS(c[j].x, X), OCRPP_OFS(c[j].y, Y));
         const double X2 = X;
-        X = X * m_cos - m_sin * Y;
-        Y = X2 * m_sin + Y * m_cos;
+        X = dsub(dmul(X, m_cos), dmul(m_sin, Y));
+        Y = dadd(dmul(X2, m_sin), dmul(Y, m_cos));
       }
-      OCRPP_EMIT(clipper_round(c[j].x + nx[j] * delta), clipper_round(c[j].y + ny[j] * delta));
+      OCRPP_EMIT(OCRPP_OFS(c[j].x, nx[j]), OCRPP_OFS(c[j].y, ny[j]));
     }
     k = j;
   }
 #undef OCRPP_EMIT
+#undef OCRPP_OFS
   return m;
 }
 

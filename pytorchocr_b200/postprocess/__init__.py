@@ -8,6 +8,7 @@ reference) the reference's own classes run (see INTEGRATION.md for the two-line 
 """
 import copy
 
+from .cls_postprocess import ClsPostProcess
 from .rec_postprocess import CTCLabelDecode, DistillationCTCLabelDecode
 
 __all__ = ["build_post_process"]
@@ -15,6 +16,7 @@ __all__ = ["build_post_process"]
 _REGISTRY = {
     "CTCLabelDecode": CTCLabelDecode,
     "DistillationCTCLabelDecode": DistillationCTCLabelDecode,
+    "ClsPostProcess": ClsPostProcess,
 }
 
 try:  # detection operators (registered as they are built)

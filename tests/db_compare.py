@@ -46,17 +46,62 @@ def _set_dist(a, b):
 def classify(d):
     """Which discontinuities of the reference algorithm the oracle box `d` sits on."""
     cls = set()
+    if "mini" not in d:
+        return cls
     mini = np.asarray(d["mini"], np.float64)
     if np.abs(mini - np.round(mini)).min() < 2e-3:
         cls.add("truncation")
-    for quad in (mini, np.asarray(d["clip"], np.float64)):
+    for quad in (mini,) + ((np.asarray(d["clip"], np.float64),) if "clip" in d else ()):
         if np.min(np.diff(np.sort(quad[:, 0]))) < 1e-3:
             cls.add("ordering")
-    dist = float(d["distance"])
-    base = G.do_offset(d["quad"], dist)
-    if any(G.do_offset(d["quad"], dist * (1 + e)) != base for e in (-1e-4, 1e-4)):
-        cls.add("rounding")
+    if "distance" in d:
+        dist = float(d["distance"])
+        base = G.do_offset(d["quad"], dist)
+        if any(G.do_offset(d["quad"], dist * (1 + e)) != base for e in (-1e-4, 1e-4)):
+            cls.add("rounding")
     return cls
+
+
+def on_discontinuity(d):
+    """True when the oracle's own data shows candidate `d` (any status) on one of the reference's discontinuities:
+    a class of classify() or an exact equal-area tie of its contour's minimal rectangles. On such a candidate
+    cv2's float32 noise decides the outcome (which rectangle, which truncation), and with it everything downstream
+    - the box may move by several pixels, or appear / disappear through the size filters."""
+    if classify(d):
+        return True
+    return "contour" in d and len(d["contour"]) >= 3 and len(G.tied_min_area_rects(d["contour"], rel=2e-6)) > 1
+
+
+def tie_alternatives(d):
+    """Outputs (pre-rounding corners) the reference algorithm produces when cv2.minAreaRect resolves an exact
+    equal-area tie the other way, at the contour's rectangle and/or at the rectangle of the offset polygon. Built
+    with the oracle's own steps (get_mini_boxes, unclip, scaling) from every tied rectangle."""
+    from oracle import db_oracle as O
+    if "contour" not in d:
+        return []
+    f = np.float32
+    width, height, src_w, src_h = d["scale"]
+    outs = []
+
+    def mini_box(c):
+        """GetMiniBoxes (db_postprocess.cpp:159-192) on exact corners: sort by x, then TL,TR,BR,BL"""
+        a = sorted(np.asarray(c, np.float32).tolist(), key=lambda q: q[0])
+        i2, i3 = (a[3], a[2]) if a[3][1] <= a[2][1] else (a[2], a[3])
+        i1, i4 = (a[1], a[0]) if a[1][1] <= a[0][1] else (a[0], a[1])
+        return np.array([i1, i2, i3, i4], np.float32)
+
+    # rel = 2e-6: cv2's float32 rotating calipers cannot tell rectangles whose areas differ by less than that
+    firsts = G.tied_min_area_rects(d["contour"], rel=2e-6, corners=True)
+    for c1 in firsts:
+        mini = mini_box(c1)
+        rect2, _, _, soln = O.unclip(mini, d["unclip_ratio"])
+        pts = [p for path in soln for p in path]
+        seconds = G.tied_min_area_rects(pts, rel=2e-6, corners=True) if len(pts) >= 3 else []
+        for c2 in seconds:
+            clip = mini_box(c2)
+            outs.append(np.array([[float(f(f(clip[j][0] / f(width)) * f(src_w))),
+                                   float(f(f(clip[j][1] / f(height)) * f(src_h)))] for j in range(4)]))
+    return outs if len(outs) > 1 else []
 
 
 def compare_image(boxes, boxes_f, scores, details, tol_px=1e-3, tol_score=1e-5):
@@ -71,16 +116,23 @@ def compare_image(boxes, boxes_f, scores, details, tol_px=1e-3, tol_score=1e-5):
         return stats
     of = np.array([d["out_f"] for d in ok], np.float64)           # [K,4,2]
     gf = np.asarray(boxes_f, np.float64)
-    # corner-order independent distance between boxes
-    dist = np.array([[_set_dist(of[i], gf[j]) for j in range(len(gf))] for i in range(len(of))])
-    used = set()
+    # corner-order independent distance between boxes, for the MATCHING in map pixels (a box that moved by one
+    # map pixel on one of the reference's discontinuities moves by src/map pixels in the output)
+    norm = np.ones(2)
+    if "scale" in ok[0]:
+        width, height, src_w, src_h = ok[0]["scale"]
+        norm = np.array([min(1.0, width / float(src_w)), min(1.0, height / float(src_h))])
+    dist = np.array([[_set_dist(of[i] * norm, gf[j] * norm) for j in range(len(gf))] for i in range(len(of))])
+    used, done = set(), set()
     for i in np.argsort(dist.min(1)):
         cand = [(dist[i, j], j) for j in range(len(gf)) if j not in used]
         if not cand or min(cand)[0] > 2.5:
             stats["unmatched_oracle"] += 1
             continue
-        dd, j = min(cand)
+        j = min(cand)[1]
+        dd = _set_dist(of[i], gf[j])
         used.add(j)
+        done.add(int(i))
         d = ok[i]
         assert abs(scores[j] - d["score"]) <= tol_score * abs(d["score"]) + 1e-7, (scores[j], d["score"])
         ordered = np.abs(of[i] - gf[j]).max()
@@ -95,13 +147,50 @@ def compare_image(boxes, boxes_f, scores, details, tol_px=1e-3, tol_score=1e-5):
             stats["ordering"] += 1
         elif cls & {"truncation", "rounding"}:
             stats["truncation" if "truncation" in cls else "rounding"] += 1
+        elif any(_set_dist(a, gf[j]) < 5e-3 for a in tie_alternatives(d)):
+            # verified equal-area tie: the GPU box is exactly what the reference computes from another of the
+            # tied minimal rectangles
+            stats["tie"] += 1
         else:
             # different rectangle of the same area around the same points: equal-area tie
             def area(b):
                 return np.linalg.norm(b[1] - b[0]) * np.linalg.norm(b[2] - b[1])
             assert abs(area(of[i]) - area(gf[j])) <= 2e-3 * area(of[i]) + 0.6, ("box mismatch", dd, d["out_f"], gf[j].tolist(), d["mini"])
             stats["tie"] += 1
-    stats["unmatched_gpu"] = len(gf) - len(used)
+    # an oracle box without a GPU box within 2.5 px: a verified equal-area tie can move the box further than that
+    if stats["unmatched_oracle"]:
+        for i in range(len(of)):
+            if i in done:
+                continue
+            for a in tie_alternatives(ok[i]):
+                hit = [j for j in range(len(gf)) if j not in used and _set_dist(a, gf[j]) < 5e-3]
+                if hit:
+                    used.add(hit[0])
+                    stats["tie"] += 1
+                    stats["unmatched_oracle"] -= 1
+                    assert abs(scores[hit[0]] - ok[i]["score"]) <= tol_score * abs(ok[i]["score"]) + 1e-7
+                    break
+    # what is still unmatched: "explained" when it sits on a discontinuity the oracle's data proves
+    stats["explained"] = 0
+    for i in range(len(of)):
+        if i not in done and stats["unmatched_oracle"] > 0 and on_discontinuity(ok[i]):
+            done.add(i)
+            stats["unmatched_oracle"] -= 1
+            stats["explained"] += 1
+    stats["unmatched_gpu"] = 0
+    for j in range(len(gf)):
+        if j in used:
+            continue
+        c = gf[j].mean(0)                                                  # box centre in map pixels
+        if "scale" in ok[0]:
+            c = c * np.array([width / float(src_w), height / float(src_h)])
+        near = [d for d in details if "contour" in d and
+                d["contour"][:, 0].min() - 3 <= c[0] <= d["contour"][:, 0].max() + 3 and
+                d["contour"][:, 1].min() - 3 <= c[1] <= d["contour"][:, 1].max() + 3]
+        if any(on_discontinuity(d) for d in near):
+            stats["explained"] += 1
+        else:
+            stats["unmatched_gpu"] += 1
     return stats
 
 

@@ -9,6 +9,8 @@ ties on x+y / y-x) is counted, not failed, and bounded by the caller."""
 import cv2
 import numpy as np
 
+from oracle import geometry_oracle as G
+
 
 def _set_dist(a, b):
     d = np.abs(np.asarray(a)[:, None, :] - np.asarray(b)[None, :, :]).max(-1)
@@ -41,6 +43,10 @@ def compare_image(boxes, boxes_f, scores, want, shape, tol_px=1e-3, tol_score=1e
             # same rectangle; order_points_clockwise met a tie (45-degree diamond) that cv2's float32
             # noise resolved differently, so the two boxes repeat different corners of it
             stats["ordering"] += 1
+        elif any(_subset_dist(gf, cv2.boxPoints(r).astype(np.float64) / ratio) < 5e-3
+                 for r in G.tied_min_area_rects(d["hull"], rel=2e-6)):
+            # verified equal-area tie: the GPU box is made of corners of another minimal rectangle of the label
+            stats["tie"] += 1
         elif min(d["rect"][1]) < 3.0 or d["area"] < 64:
             # tiny / degenerate label (a few pixels, 1-px lines, small triangles): several edge-aligned
             # rectangles have exactly the same area and order_points_clockwise may repeat a corner of a

@@ -1,0 +1,137 @@
+"""Randomised parity stress on a GPU box (not collected by pytest; run by hand):
+
+    python tests/stress_gpu.py [--seconds 120] [--seed 0]
+
+Loops over random sizes / seeds / thresholds of the adversarial generators of the GPU parity tests (blob fields with
+merged masks, non-nested kernels, gate scenes, random pages) and checks every result against the oracle with the
+same comparators the tests use. Prints one line per failure and a summary; exit code 1 if anything failed."""
+import argparse
+import os
+import sys
+import time
+import traceback
+
+import cv2
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+import pytest  # noqa: E402
+import test_crop_gpu as tc  # noqa: E402
+import test_db_gpu as tdb  # noqa: E402
+import test_pan_gpu as tpan  # noqa: E402
+import test_pse_gpu as tpse  # noqa: E402
+from pytorchocr_b200 import synth  # noqa: E402
+
+
+def case_db(rng):
+    H, W = int(rng.integers(24, 260)), int(rng.integers(24, 400))
+    sig = float(rng.choice([0.45, 0.6, 1.0, 1.5, 2.5, 4.0]))
+    p = np.stack([cv2.GaussianBlur(rng.random((H, W)).astype(np.float32), (0, 0), sig) for _ in range(2)])
+    lo, hi = np.quantile(p, 0.02), np.quantile(p, 0.98)
+    p = np.clip((p - lo) / (hi - lo), 0, 1).astype(np.float32)
+    q = float(np.quantile(p, rng.uniform(0.3, 0.7)))
+    kw = dict(thresh=q, box_thresh=q + 0.02, max_unmatched=0)
+    if rng.random() < 0.3:
+        kw["use_dilation"] = True
+    sl = np.array([[H, W, 1.0, 1.0], [int(H * 1.7), int(W * 0.8), 1.7, 0.8]])
+    tdb._check(p[:, None], sl, **kw)
+    return "db %dx%d sig=%.2f %s" % (H, W, sig, "dil" if "use_dilation" in kw else "")
+
+
+def case_db_synth(rng):
+    H, W = int(rng.integers(64, 400)), int(rng.integers(64, 700))
+    maps = synth.db_batch(2, seed=int(rng.integers(1 << 30)), H=H, W=W)
+    tdb._check(maps, np.array([[H, W, 1.0, 1.0]] * 2), max_unmatched=0)
+    return "db_synth %dx%d" % (H, W)
+
+
+def case_pse(rng):
+    K = int(rng.integers(2, 8))
+    H, W = int(rng.integers(24, 200)), int(rng.integers(24, 260))
+    blur = float(rng.choice([0.4, 0.6, 1.0, 1.5, 2.0, 3.0, 5.0]))
+    nested = bool(rng.integers(2))
+    maps = np.stack([tpse._blob_fields(rng, K, H, W, blur, nested) for _ in range(2)])
+    ma = int(rng.choice([0, 5, 16]))
+    tpse._check(maps, tpse._shape(2, H, W), maps_at_processing_res=True, min_area=ma, box_thresh=0.5, loose=0.4)
+    return "pse K=%d %dx%d blur=%.1f nested=%d min_area=%d" % (K, H, W, blur, nested, ma)
+
+
+def case_pse_synth(rng):
+    H, W = int(rng.integers(96, 420)), int(rng.integers(128, 640))
+    maps = np.stack([synth.pse_maps(int(rng.integers(1 << 30)), H, W) for _ in range(2)])
+    tpse._check(maps, tpse._shape(2, H, W), maps_at_processing_res=True, loose=0.06)
+    return "pse_synth %dx%d" % (H, W)
+
+
+def case_pan(rng):
+    H, W = int(rng.integers(24, 200)), int(rng.integers(24, 260))
+    base = cv2.GaussianBlur(rng.random((H, W)).astype(np.float32), (0, 0), float(rng.choice([1.0, 2.0, 4.0])))
+    text = base > np.quantile(base, rng.uniform(0.2, 0.6))
+    kern = (rng.random((H, W)) > rng.uniform(0.4, 0.9)) & text
+    inst = rng.integers(0, 4, (H, W))
+    centres = np.array([[0, 0, 0, 0], [6, 0, 0, 0], [0, 6, 0, 0], [0, 0, 6, 0]], np.float32)
+    maps = np.empty((1, 6, H, W), np.float32)
+    maps[0, 0] = np.where(text, 3.0, -3.0)
+    maps[0, 1] = np.where(kern, 3.0, -3.0)
+    maps[0, 2:] = centres[inst].transpose(2, 0, 1) + rng.normal(0, 0.25, (4, H, W))
+    mka = float(rng.choice([0.0, 2.6]))
+    tpan._check(maps, tpan._shape(1, H, W), scale=1, maps_at_processing_res=True, min_kernel_area=mka, min_area=2,
+                box_thresh=0.5, loose=0.6)
+    return "pan %dx%d mka=%.1f" % (H, W, mka)
+
+
+def case_pan_synth(rng):
+    H, W = int(rng.integers(96, 420)), int(rng.integers(128, 640))
+    maps = np.stack([synth.pan_maps(int(rng.integers(1 << 30)), H, W) for _ in range(2)])
+    tpan._check(maps, tpan._shape(2, H, W), scale=1, maps_at_processing_res=True, loose=0.06)
+    return "pan_synth %dx%d" % (H, W)
+
+
+def case_crop(rng):
+    H, W = int(rng.integers(120, 500)), int(rng.integers(160, 700))
+    img = synth.page_image(int(rng.integers(1 << 30)), H, W)
+    boxes = synth.page_boxes(int(rng.integers(1 << 30)), n=int(rng.integers(1, 120)), H=H, W=W,
+                             tall_frac=float(rng.uniform(0, 0.5)), skew=float(rng.uniform(0, 4)), scale=0.7)
+    gb, gc = tc._cropper()(img, boxes)
+    tc._check_page(img, boxes, gb, gc)
+    return "crop %dx%d n=%d" % (H, W, len(boxes))
+
+
+CASES = [case_db, case_db_synth, case_pse, case_pse_synth, case_pan, case_pan_synth, case_crop]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=120)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--verbose", action="store_true", help="print every case before it runs (to find a crashing one)")
+    ap.add_argument("--first", type=int, default=0, help="first iteration number")
+    args = ap.parse_args()
+    cases = [c for c in CASES if not args.only or args.only in c.__name__]
+    n, fails = {}, []
+    t0, it = time.time(), args.first
+    while time.time() - t0 < args.seconds:
+        case = cases[it % len(cases)]
+        seed = args.seed * 1000003 + it
+        it += 1
+        rng = np.random.default_rng(seed)
+        if args.verbose:
+            print("run", case.__name__, "it", it - 1, "seed", seed, flush=True)
+        try:
+            case(rng)
+            n[case.__name__] = n.get(case.__name__, 0) + 1
+        except (AssertionError, pytest.fail.Exception, Exception) as e:  # noqa: B014
+            fails.append((case.__name__, seed, repr(e)[:300]))
+            print("FAIL", case.__name__, "seed", seed, repr(e)[:300], flush=True)
+            if not isinstance(e, (AssertionError, pytest.fail.Exception)):
+                traceback.print_exc()
+    print("passed:", n, "failed:", len(fails))
+    return 1 if fails else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

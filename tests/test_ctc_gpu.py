@@ -108,3 +108,28 @@ def test_decode_batch_matches_per_crop_decode(tmp_path):
     assert [t for t, _ in packed] == [t for t, _ in one_by_one]
     assert np.allclose([c for _, c in packed], [c for _, c in one_by_one], rtol=1e-6, equal_nan=True)
     assert op.decode_batch([]) == []
+
+
+@pytest.mark.parametrize("B,C,dtype", [(1, 2, "f32"), (37, 2, "f32"), (256, 4, "f16"), (5, 2, "numpy")])
+def test_cls_postprocess_matches_reference_semantics(B, C, dtype):
+    """R/pytocr/postprocess/cls_postprocess.py:11-20: (label_list[argmax], preds[i, argmax]), first maximum wins."""
+    import torch
+    from pytorchocr_b200.postprocess import build_post_process
+    rng = np.random.default_rng(B)
+    preds = rng.random((B, C)).astype(np.float32)
+    preds[::3] = preds[::3, :1]                           # ties: every class equal -> index 0
+    labels = ["0", "180", "90", "270"][:C]
+    op = build_post_process({"name": "ClsPostProcess", "label_list": labels, "cuda_speedup": True})
+    if dtype == "numpy":
+        x, ref = preds, preds
+    else:
+        x = torch.from_numpy(preds).cuda()
+        x = x.half() if dtype == "f16" else x
+        ref = x.float().cpu().numpy()
+    got = op(x)
+    idx = ref.argmax(axis=1)
+    want = [(labels[k], ref[i, k]) for i, k in enumerate(idx)]
+    assert [g[0] for g in got] == [w[0] for w in want]
+    assert np.array_equal(np.array([g[1] for g in got], np.float32), np.array([w[1] for w in want], np.float32))
+    out, lab = op(x, label=[1, 0])
+    assert lab == [(labels[1], 1.0), (labels[0], 1.0)] and len(out) == B

@@ -129,3 +129,19 @@ def test_pse_capacity_retry():
     maps = np.where(rng.random((1, 3, H, W)) > 0.4, 3.0, -3.0).astype(np.float32)   # ~H*W/4 runs
     _check(maps, _shape(1, H, W), maps_at_processing_res=True, max_runs=32, max_boxes=2, min_area=2,
            box_thresh=0.5, loose=0.5)
+
+
+def test_pse_text_run_table_overflows_alone():
+    """Only the TEXT mask overflows the run table (striped text, a few compact kernels) and the workspace holds
+    stale data: the first pass must bail out cleanly (found by tests/stress_gpu.py: the seed lookup walked a text
+    table that had not been written) and the retry must match the oracle."""
+    import torch
+    H, W = 64, 128
+    maps = np.full((2, 3, H, W), -3.0, np.float32)
+    maps[:, 0, :, ::2] = 3.0                       # text: 64 one-pixel runs per row = 4096 runs
+    maps[:, 0, 20:30, 40:80] = 3.0
+    maps[:, 1:, 22:28, 44:60] = 3.0                # one kernel blob inside a solid text block
+    maps[:, 1:, 10:14, 8] = 3.0                    # and a 1-px-wide kernel on a stripe
+    junk = torch.full((64 << 20,), 0x7f7f7f7f, dtype=torch.int32, device="cuda")   # poison the allocator's pool
+    del junk
+    _check(maps, _shape(2, H, W), maps_at_processing_res=True, max_runs=1024, min_area=2, box_thresh=0.5, loose=0.5)
