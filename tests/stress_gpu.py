@@ -100,7 +100,46 @@ def case_crop(rng):
     return "crop %dx%d n=%d" % (H, W, len(boxes))
 
 
-CASES = [case_db, case_db_synth, case_pse, case_pse_synth, case_pan, case_pan_synth, case_crop]
+_CTC = {}
+
+
+def case_ctc(rng):
+    import tempfile
+    import torch
+    import test_ctc_gpu as tctc
+    T, B, C = int(rng.integers(1, 140)), int(rng.integers(1, 300)), int(rng.choice([2, 37, 97, 513, 6623, 6624]))
+    if "ops" not in _CTC:
+        _CTC["ops"] = tctc._ops(synth.write_char_dict(os.path.join(tempfile.mkdtemp(), "d.txt"), 6623))
+    op, oracle, _ = _CTC["ops"]
+    probs, _ = synth.ctc_probs_numpy(int(rng.integers(1 << 30)), T, B, C)
+    mode = int(rng.integers(3))
+    x = torch.from_numpy(probs).cuda()
+    if mode == 1:                                   # fp16 input: the oracle sees the same rounded values
+        x = x.half()
+        ref = x.float().cpu()
+    elif mode == 2:                                 # strided view (class and line padding)
+        big = torch.zeros((T, B + 3, C + 5), device="cuda")
+        big[:, 1:B + 1, 2:C + 2] = x
+        x = big[:, 1:B + 1, 2:C + 2]
+        ref = torch.from_numpy(probs)
+    else:
+        ref = torch.from_numpy(probs)
+    tctc._same(op(x), oracle(ref))
+    return "ctc T=%d B=%d C=%d mode=%d" % (T, B, C, mode)
+
+
+def case_db_fp16(rng):
+    import torch
+    H, W = int(rng.integers(64, 300)), int(rng.integers(64, 500))
+    maps = synth.db_batch(2, seed=int(rng.integers(1 << 30)), H=H, W=W)
+    big = torch.zeros((2, 1, H + 2, W + 8), dtype=torch.float16, device="cuda")     # strided half view
+    big[:, :, 1:H + 1, 8:W + 8] = torch.from_numpy(maps).cuda().half()
+    dev = big[:, :, 1:H + 1, 8:W + 8]
+    tdb._check(dev, np.array([[H, W, 1.0, 1.0]] * 2), oracle_maps=dev.float().cpu().numpy(), max_unmatched=0)
+    return "db_fp16 %dx%d" % (H, W)
+
+
+CASES = [case_ctc, case_db_fp16, case_db, case_db_synth, case_pse, case_pse_synth, case_pan, case_pan_synth, case_crop]
 
 
 def main():
