@@ -260,6 +260,11 @@ class DbWorkload(DetWorkload):
     def make_device_maps(self, dev):
         return self.torch.from_numpy(self.maps).pin_memory().to(dev)
 
+    def e2e_step(self):
+        # the operator takes the pinned HOST maps (as the reference's operator takes `.cpu().numpy()` maps) and
+        # does the H2D itself, chunked and overlapped with the kernels of the previous chunk
+        return self.op({"maps": self.host_maps}, self.shape_list)
+
     def device_step(self, L, stream):
         from pytorchocr_b200 import _lib
         buf, m = self.buf, self.dev_maps

@@ -1440,7 +1440,7 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
   // on: the event marks describe one whole-batch chain.)
   int nsplit = N >= 192 ? 4 : (N >= 64 ? 2 : 1);
   static const int forced = [] { const char* e = getenv("OCRPP_DB_SPLIT"); return e ? atoi(e) : 0; }();   // tuning aid
-  if (forced > 0) nsplit = forced > 4 ? 4 : forced;
+  if (forced > 0) nsplit = forced > kDbAuxStreams + 1 ? kDbAuxStreams + 1 : forced;
   DbAux* aux = (nsplit > 1 && nsplit <= N && !profile_on()) ? db_aux() : nullptr;
   if (aux) {
     static std::mutex enqueue_mu;   // the auxiliary streams/events are shared: one fork/join section at a time

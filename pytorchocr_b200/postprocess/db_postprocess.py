@@ -66,7 +66,8 @@ class DBPostProcess(object):
         key = (str(device), N, H, W, R, cap)
         buf = self._cache.get(key)
         if buf is None:
-            self._cache.clear()
+            while len(self._cache) >= 2:     # two shapes stay resident (the chunked host path uses two chunk sizes)
+                self._cache.pop(next(iter(self._cache)))
             L = _lib.lib()
             ws_bytes = L.ocrpp_db_workspace_bytes(N, H, W, R)
             nb, ns = N * cap * 8 * 2, N * cap * 4
@@ -152,9 +153,46 @@ class DBPostProcess(object):
         extras = {k: v.cpu().numpy() for k, v in extras_dev.items()}
         return boxes, scores, counts, status, extras
 
+    upload_chunk = 64   # images per H2D chunk of the host-input path
+
+    def _call_host_batch(self, maps, shape_list, use_padding_resize):
+        """Host maps (numpy / CPU tensor), large batch: the upload is PCIe-bound and ~20x longer than the kernels,
+        so the batch is uploaded in chunks on a copy stream and every chunk is post-processed (kernels, D2H of its
+        boxes, host assembly) while the next ones are still in flight."""
+        torch = _lib.require_cuda()
+        t = torch.from_numpy(np.ascontiguousarray(maps)) if isinstance(maps, np.ndarray) else maps.detach()
+        if t.dtype not in (torch.float32, torch.float16):
+            t = t.float()
+        N = t.shape[0]
+        dev = torch.device("cuda", torch.cuda.current_device())
+        shape = np.asarray(shape_list, dtype=np.float64).reshape(N, -1)
+        nchunks = (N + self.upload_chunk - 1) // self.upload_chunk
+        bounds = [N * i // nchunks for i in range(nchunks + 1)]
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        full = torch.empty(t.shape, dtype=t.dtype, device=dev)
+        self._copy_stream.wait_stream(main)
+        events = []
+        with torch.cuda.stream(self._copy_stream):
+            for lo, hi in zip(bounds[:-1], bounds[1:]):
+                full[lo:hi].copy_(t[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+                events.append(ev)
+        full.record_stream(self._copy_stream)
+        res = []
+        for ev, lo, hi in zip(events, bounds[:-1], bounds[1:]):
+            main.wait_event(ev)
+            res += self({"maps": full[lo:hi]}, shape[lo:hi], use_padding_resize)
+        return res
+
     def __call__(self, outs_dict, shape_list, use_padding_resize=False):
-        boxes, scores, counts, _, _ = self.run_device(outs_dict["maps"], shape_list,
-                                                      use_padding_resize=use_padding_resize)
+        maps = outs_dict["maps"]
+        on_host = isinstance(maps, np.ndarray) or not getattr(maps, "is_cuda", True)
+        if on_host and len(maps) >= 2 * self.upload_chunk:
+            return self._call_host_batch(maps, shape_list, use_padding_resize)
+        boxes, scores, counts, _, _ = self.run_device(maps, shape_list, use_padding_resize=use_padding_resize)
         res_batch = []
         for n in range(boxes.shape[0]):
             k = int(counts[n])

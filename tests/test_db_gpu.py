@@ -226,3 +226,20 @@ def test_db_thin_diagonal_boxes():
                 k += 1
     want, counts = _check(m[None, None], np.array([[H, W, 1.0, 1.0]]), loose=0.0)
     assert counts[0] >= 8
+
+
+def test_db_host_batch_is_uploaded_in_chunks():
+    """numpy / CPU-tensor maps of a large batch take the chunked upload path (H2D of chunk i+1 overlaps the kernels of
+    chunk i): same results as the device-tensor path, also with chunks of unequal size."""
+    import torch
+    H, W = 96, 160
+    maps = synth.db_batch(37, seed=5, H=H, W=W)
+    sl = np.array([[H + n, W + 2 * n, 1.0, 1.0] for n in range(37)], np.float64)
+    op = _op()
+    op.upload_chunk = 8                                    # 37 images -> 5 chunks of 7/8 images
+    want = op({"maps": torch.from_numpy(maps).cuda()}, sl)
+    for host in (maps, torch.from_numpy(maps).pin_memory()):
+        got = op({"maps": host}, sl)
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert np.array_equal(g["points"], w["points"]) and np.array_equal(g["box_scores"], w["box_scores"])
