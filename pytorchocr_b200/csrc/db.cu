@@ -1013,15 +1013,20 @@ __global__ void __launch_bounds__(kHullThreads) db_hull_kernel(DbParams p) {
   const int32_t* ext_r = p.ext_r + (size_t)n * p.E + off;
   int* gout = reinterpret_cast<int*>(p.hull + ((size_t)n * p.E + off) * 4);   // >= 8 * (nrows + 1) ints
   int out[2 * kFastRows + 2];   // dynamically indexed => thread-local memory, which L1 caches write-back
-  // monotone chain over the points (ext_l[i], y0+i), (ext_r[i], y0+i), already sorted by (y, x);
-  // same result as hull_sorted32. The two top-of-stack points stay in registers.
-  const int npts = 2 * nrows;
-  auto pt = [&](int i) { return pk((i & 1) ? ext_r[i >> 1] : ext_l[i >> 1], y0 + (i >> 1)); };
+  // monotone chain over the points (ext_l[i], y0+i), (ext_r[i], y0+i), already sorted by (y, x); same result as
+  // hull_sorted32 on all of them, but every pass only visits the extents that can stay on its chain: with y
+  // ascending a kept turn (cross > 0) bulges towards +x, so the first pass is the chain of RIGHT extents and a left
+  // extent of a later row is always popped again by the right extent of its own row - and whatever it popped
+  // before, that right extent pops too (cross(o, a, q) only decreases as q moves right along a row). Mirrored for
+  // the second pass. The two top-of-stack points stay in registers.
+  const int last = nrows - 1;
   int kk = 0, a = 0, b = 0;   // a = out[kk-2], b = out[kk-1]
-  int prev = 0;
-  for (int i = 0; i < npts; ++i) {
-    const int q = pt(i);
-    if (i > 0 && q == prev) continue;
+  int prev = pk(ext_l[0], y0);
+  out[kk++] = prev;
+  b = prev;
+  for (int i = 0; i < nrows; ++i) {
+    const int q = pk(ext_r[i], y0 + i);
+    if (q == prev) continue;   // single-pixel first row
     prev = q;
     while (kk >= 2 && cross32(a, b, q) <= 0) {
       --kk;
@@ -1035,10 +1040,9 @@ __global__ void __launch_bounds__(kHullThreads) db_hull_kernel(DbParams p) {
   int hn = kk;
   if (kk > 1) {
     const int lo = kk + 1;
-    prev = pt(npts - 1);
-    for (int i = npts - 2; i >= 0; --i) {
-      const int q = pt(i);
-      if (q == prev) continue;
+    for (int i = last; i >= 0; --i) {
+      const int q = pk(ext_l[i], y0 + i);
+      if (q == prev) continue;   // single-pixel last row
       prev = q;
       while (kk >= lo && cross32(a, b, q) <= 0) {
         --kk;
