@@ -84,6 +84,33 @@ __device__ int hull_sorted32(const int* pts, int n, int* out) {
   return k - 1;
 }
 
+// hull_sorted32 for row extents: pts = (left_0, right_0, left_1, right_1, ...) of consecutive rows. Same hull, half
+// the visits: with y ascending a kept turn bulges towards +x, so the first pass can only keep RIGHT extents (a
+// left extent of a later row is popped again by the right extent of its own row, and so is everything it popped),
+// and the second pass only LEFT extents.
+__device__ int hull_row_extents32(const int* pts, int nrows, int* out) {
+  int k = 0;
+  int prev = pts[0];
+  out[k++] = prev;
+  for (int i = 0; i < nrows; ++i) {
+    const int q = pts[2 * i + 1];
+    if (q == prev) continue;
+    prev = q;
+    while (k >= 2 && cross32(out[k - 2], out[k - 1], q) <= 0) --k;
+    out[k++] = q;
+  }
+  if (k == 1) return 1;
+  const int lo = k + 1;
+  for (int i = nrows - 1; i >= 0; --i) {
+    const int q = pts[2 * i];
+    if (q == prev) continue;
+    prev = q;
+    while (k >= lo && cross32(out[k - 2], out[k - 1], q) <= 0) --k;
+    out[k++] = q;
+  }
+  return k - 1;
+}
+
 struct Fit32 {
   int smin, smax, tmin, tmax, len2, qx, qy, idx;
   double area;

@@ -1049,7 +1049,7 @@ __global__ void __launch_bounds__(kGeoThreads) ex_geometry_fast_kernel(ExParams 
   }
   __syncwarp(gmask);
   int hn = 0;
-  if (gl == 0) hn = hull_sorted32(A, 2 * nrows, B);
+  if (gl == 0) hn = hull_row_extents32(A, nrows, B);
   hn = __shfl_sync(gmask, hn, 0, kGrp);
   __syncwarp(gmask);
   geom::Rect rect;
