@@ -70,6 +70,8 @@ struct ExParams {
   int32_t *s_area, *s_cc, *s_cid, *s_alive, *s_flag;
   double* s_emb;    // [N][R][4] embedding sums of flagged kernels
   int32_t *l_area, *l_ymin, *l_ymax, *l_rowoff;
+  int32_t *l_rowbase, *l_row0;   // [R] row-extent block reserved at seeding time (rows of the seed's text component)
+  int32_t* extdefer;              // [N] some label of the image could not reserve its block: second pass needed
   long long* l_sum;
   int32_t *ext_l, *ext_r;  // [N][E]
   P2i* hull;               // [N][8*E]
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(kRunThreads) ex_runs_kernel(ExParams p) {
           p.t_seen[q] = 0; p.t_amin[q] = 0x7fffffff; p.t_amax[q] = 0; p.t_nseed[q] = 0; p.t_lab[q] = 0;
         } else {
           p.s_area[q] = 0; p.s_cc[q] = -1; p.s_cid[q] = 0; p.s_alive[q] = 0; p.s_flag[q] = 0;
-          p.l_area[q] = 0; p.l_ymin[q] = 0x7fffffff; p.l_ymax[q] = -1; p.l_rowoff[q] = -1; p.l_sum[q] = 0;
+          p.l_area[q] = 0; p.l_ymin[q] = 0x7fffffff; p.l_ymax[q] = -1; p.l_rowoff[q] = -1; p.l_rowbase[q] = -1; p.l_sum[q] = 0;
           if (p.mode == kModePan) {
             p.s_emb[q * 4 + 0] = 0.0; p.s_emb[q * 4 + 1] = 0.0; p.s_emb[q * 4 + 2] = 0.0; p.s_emb[q * 4 + 3] = 0.0;
           }
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(kRunThreads) ex_seed_kernel(ExParams p) {
   const int32_t* t_rowptr = p.rowptr + (size_t)(n * 2 + 0) * (p.H + 1);
   const int chunk = (nr + kRunThreads - 1) / kRunThreads;
   const int lo = min(nr, (int)threadIdx.x * chunk), hi = min(nr, lo + chunk);
-  int local = 0;
+  int local = 0, need = 0;
   for (int r = lo; r < hi; ++r) local += p.par[ro + r] == r ? 1 : 0;
   int total;
   int id = block_exclusive_scan(local, &total);
@@ -386,12 +388,42 @@ __global__ void __launch_bounds__(kRunThreads) ex_seed_kernel(ExParams p) {
     const int cc = p.par[to + ex_run_at(t_rowptr, p.run_xs + to, y, x)];
     p.s_cc[so + r] = cc;
     p.s_alive[so + r] = 1;
+    need += p.t_ymax[so + cc] - (int)p.run_y[to + cc] + 2;   // rows of the text component + 1 (see below)
     p.t_seen[so + cc] = 1;
     atomicAdd(&p.t_nseed[so + cc], 1);
     p.t_lab[so + cc] = r + 1;   // only read when the component owns exactly one seed
     if (p.mode == kModePan) {
       atomicMin(&p.t_amin[so + cc], area);
       atomicMax(&p.t_amax[so + cc], area);
+    }
+  }
+  {
+    // A label never leaves its text component, so the component's rows bound the label's rows: every surviving
+    // seed reserves a row-extent block of that many rows now, and the ONE pass over the label map after the
+    // expansion fills area, score sum, row range and row extents together (the exact per-label allocation needs
+    // the row range first and with it a second pass; it remains for the seeds whose block does not fit).
+    // Reservations use the first half of the extent storage only - the second half keeps the capacity the exact
+    // allocation always had. This CTA is the image's only allocator at this point: block scan, no atomics.
+    int reserved;
+    int off = block_exclusive_scan(need, &reserved);
+    const int limit = p.E / 2;
+    for (int r = lo; r < hi; ++r) {
+      if (p.par[ro + r] != r || !p.s_alive[so + r]) continue;
+      const int cc = p.s_cc[so + r];
+      const int y0 = p.run_y[to + cc], nrows = p.t_ymax[so + cc] - y0 + 1;
+      if (off + nrows + 1 <= limit) {
+        p.l_rowbase[so + r] = off;
+        p.l_row0[so + r] = y0;
+      } else {
+        p.extdefer[n] = 1;
+      }
+      off += nrows + 1;
+    }
+    reserved = min(reserved, limit);
+    if (threadIdx.x == 0) p.ext_alloc[n] = reserved;
+    for (int i = threadIdx.x; i < reserved; i += kRunThreads) {
+      p.ext_l[(size_t)n * p.E + i] = 0x7fffffff;
+      p.ext_r[(size_t)n * p.E + i] = -1;
     }
   }
   __syncthreads();
@@ -898,6 +930,7 @@ __global__ void __launch_bounds__(kRunBlk) ex_stats_kernel(ExParams p) {
   const size_t ro = (size_t)(n * 2 + 0) * p.R, so = (size_t)n * p.R;
   const uint32_t* st = p.st + (size_t)n * p.H * p.W;
   const int lane = threadIdx.x & 31, wpb = kRunBlk / 32;
+  if (PASS == 2 && !p.extdefer[n]) return;   // every label of the image got its extents in pass 1
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < nr; r += gridDim.x * wpb) {
     if (!p.t_seen[so + p.par[ro + r]]) continue;
     const int y = p.run_y[ro + r], a = p.run_xs[ro + r], b = p.run_xe[ro + r];
@@ -926,13 +959,20 @@ __global__ void __launch_bounds__(kRunBlk) ex_stats_kernel(ExParams p) {
           if (PASS == 1) {
             const unsigned lo = __reduce_add_sync(mk, (unsigned)(fx & 0xffffu));
             const unsigned hi = __reduce_add_sync(mk, (unsigned)(fx >> 16));
+            const int xmin = __reduce_min_sync(mk, x), xmax = __reduce_max_sync(mk, x);
             if (lane == leader) {
               atomicAdd(&p.l_area[q], __popc(mk));
               atomicAdd((unsigned long long*)&p.l_sum[q], ((unsigned long long)hi << 16) + lo);
               atomicMin(&p.l_ymin[q], y);
               atomicMax(&p.l_ymax[q], y);
+              const int base = p.l_rowbase[q];
+              if (base >= 0) {
+                const size_t e = (size_t)n * p.E + base + (y - p.l_row0[q]);
+                atomicMin(&p.ext_l[e], xmin);
+                atomicMax(&p.ext_r[e], xmax);
+              }
             }
-          } else {
+          } else if (p.l_rowbase[q] < 0) {
             const int xmin = __reduce_min_sync(mk, x), xmax = __reduce_max_sync(mk, x);
             const int off = p.l_rowoff[q];
             if (lane == leader && off >= 0) {
@@ -966,6 +1006,11 @@ __global__ void __launch_bounds__(kRunThreads) ex_cand_kernel(ExParams p) {
     if (rank < p.maxc) {
       p.cand[(size_t)n * p.maxc + rank] = r;
       const int nrows = p.l_ymax[so + r] - p.l_ymin[so + r] + 1;
+      if (p.l_rowbase[so + r] >= 0) {   // reserved at seeding time and already filled: rows start at the label's first row
+        p.l_rowoff[so + r] = p.l_rowbase[so + r] + (p.l_ymin[so + r] - p.l_row0[so + r]);
+        ++rank;
+        continue;
+      }
       const int off = atomicAdd(&p.ext_alloc[n], nrows + 1);
       if (off + nrows + 1 <= p.E) {
         p.l_rowoff[so + r] = off;
@@ -1165,10 +1210,11 @@ size_t ex_carve(ExParams& p, void* ws) {
   p.g_nwork = c.take<int32_t>(64);  // g_nwork[4] | g_next[4] | g_arena_used (2 words), cleared together
   p.g_next = p.g_nwork ? p.g_nwork + 4 : nullptr;
   p.g_arena_used = p.g_nwork ? reinterpret_cast<unsigned long long*>(p.g_nwork + 8) : nullptr;
-  p.nruns = c.take<int32_t>(5 * N);  // nruns[2N] | ext_alloc | imgflags | ncand, cleared together
+  p.nruns = c.take<int32_t>(6 * N);  // nruns[2N] | ext_alloc | imgflags | ncand | extdefer, cleared together
   p.ext_alloc = p.nruns ? p.nruns + 2 * N : nullptr;
   p.imgflags = p.nruns ? p.nruns + 3 * N : nullptr;
   p.ncand = p.nruns ? p.nruns + 4 * N : nullptr;
+  p.extdefer = p.nruns ? p.nruns + 5 * N : nullptr;
   p.kb = c.take<uint8_t>(N * HW);
   p.st = c.take<uint32_t>(N * HW);
   p.bits = c.take<uint32_t>(N * 2 * p.H * p.Wd);
@@ -1197,6 +1243,8 @@ size_t ex_carve(ExParams& p, void* ws) {
   p.l_ymin = c.take<int32_t>(N * R);
   p.l_ymax = c.take<int32_t>(N * R);
   p.l_rowoff = c.take<int32_t>(N * R);
+  p.l_rowbase = c.take<int32_t>(N * R);
+  p.l_row0 = c.take<int32_t>(N * R);
   p.l_sum = c.take<long long>(N * R);
   p.ext_l = c.take<int32_t>(N * E);
   p.ext_r = c.take<int32_t>(N * E);
@@ -1229,7 +1277,7 @@ void ex_fill(ExParams& p, int mode, int N, int C, int K, int h, int w, int fin, 
   p.N = N; p.C = C; p.K = K; p.h = h; p.w = w; p.fin = fin; p.fout = fout;
   p.H = h * fin; p.W = w * fin; p.Wd = (p.W + 31) / 32;
   p.R = ex_resolve_runs(p.H, p.W, max_runs);
-  p.E = 2 * p.R + 4;
+  p.E = 2 * (2 * p.R + 4);   // first half: blocks reserved at seeding time; second half: exact per-label blocks
   p.maxc = max_boxes;
   p.seed_bit = mode == kModePse ? K - 1 : 1;
   p.arena_cap = ex_resolve_arena(N, p.H, p.W, arena_elems);
@@ -1396,7 +1444,7 @@ ExSplitAux* ex_split_aux() {
 template <typename T>
 int ex_launch(ExParams& p, cudaStream_t s, bool vec) {
   OCRPP_CUDA(cudaMemsetAsync(p.g_nwork, 0, sizeof(int32_t) * 64, s));
-  OCRPP_CUDA(cudaMemsetAsync(p.nruns, 0, sizeof(int32_t) * 5 * p.N, s));
+  OCRPP_CUDA(cudaMemsetAsync(p.nruns, 0, sizeof(int32_t) * 6 * p.N, s));
   const int N = p.N;
   // Large batches run as 2 or 4 independent sub-batch pipelines on separate streams, so that the
   // bandwidth-bound binarisation of one overlaps the latency-bound expansion of another. (Not while

@@ -145,3 +145,18 @@ def test_pse_text_run_table_overflows_alone():
     junk = torch.full((64 << 20,), 0x7f7f7f7f, dtype=torch.int32, device="cuda")   # poison the allocator's pool
     del junk
     _check(maps, _shape(2, H, W), maps_at_processing_res=True, max_runs=1024, min_area=2, box_thresh=0.5, loose=0.5)
+
+
+def test_pse_row_extent_blocks_reserved_and_deferred():
+    """Row extents are filled in the single statistics pass from blocks reserved per seed (rows of its text
+    component); seeds whose block does not fit the reserved half of the storage take the exact two-pass path. One
+    tall text column with 8 stacked kernels and a run capacity that lets only some reservations through exercises
+    both paths in one image."""
+    H, W = 72, 64
+    maps = np.full((2, 3, H, W), -3.0, np.float32)
+    maps[:, 0, 4:68, 20:40] = 3.0                   # one text component of 64 rows
+    for i in range(8):
+        maps[:, 1:, 6 + 8 * i:10 + 8 * i, 24:36] = 3.0   # 8 kernels, each grows into ~8 rows of the column
+    maps[1, 0, 30:34, 44:60] = 3.0                  # second image: an extra short component with its own kernel
+    maps[1, 1:, 31:33, 46:58] = 3.0
+    _check(maps, _shape(2, H, W), maps_at_processing_res=True, max_runs=100, min_area=2, box_thresh=0.5, loose=0.5)
