@@ -78,3 +78,21 @@ def test_box_touching_page_border():
 def test_collinear_box_is_rejected_by_restatement():
     with pytest.raises(ValueError):
         co.get_part_img_restated(synth.page_image(0, 64, 64), np.array([[0, 0], [10, 10], [20, 20], [30, 30]], np.int16))
+
+
+def test_tied_min_area_rects_contains_cv2_choice():
+    """oracle/geometry_oracle.tied_min_area_rects (used by the GPU comparators to verify equal-area ties): cv2's
+    rectangle is always one of the enumerated minimal rectangles, and the known tied contour yields both."""
+    from oracle import geometry_oracle as G
+    tied = np.array([[132, 178], [133, 177], [134, 178], [134, 179], [135, 180], [134, 181], [131, 181], [130, 180],
+                     [130, 179], [131, 178], [132, 179]])
+    alts = G.tied_min_area_rects(tied)
+    assert len(alts) == 2 and all(abs(w * h - 18.0) < 1e-9 for _, (w, h), _ in alts)
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        pts = rng.integers(0, 40, (int(rng.integers(3, 30)), 2))
+        if len(cv2.convexHull(pts.astype(np.int32))) < 3:
+            continue
+        want = np.sort(cv2.boxPoints(cv2.minAreaRect(pts.astype(np.float32))), axis=0)
+        cands = G.tied_min_area_rects(pts, rel=2e-6, corners=True)
+        assert any(np.abs(np.sort(c, axis=0) - want).max() < 1e-2 for c in cands), pts.tolist()
