@@ -12,4 +12,7 @@ authoring container: its compiled Cython modules (oracle/_ref/pse, pa), its vend
 (tests/golden/make_golden.py -> tests/golden/*.npz). The DB C++ module cannot be built here
 (no OpenCV C++), so for DB the oracle is a line-by-line restatement over cv2-python 4.13:
 parity for DB is pinned only through that restatement ("parity unpinned" upstream).
+The text-line crop oracle (crop_oracle.py) is the reference's own sequence of cv2 calls; it is pinned against
+the reference's `sort_boxes` / `get_part_img` imported in place (tests/golden/reference_crops.npz) and, bit for
+bit, against a first-principles restatement of what those cv2 calls compute (tests/test_oracle_crop.py).
 """
