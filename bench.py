@@ -279,6 +279,10 @@ class DbWorkload(DetWorkload):
 
 
 class ExpandWorkload(DetWorkload):
+    def e2e_step(self):
+        # pinned HOST maps straight into the operator (chunked upload overlapped with the kernels)
+        return self.op({"maps": self.host_maps}, self.shape_list)
+
     def extra_cfg(self):
         return {"maps_at_processing_res": True}
 

@@ -76,7 +76,8 @@ class ExpandOperator(object):
         key = (str(device), N, C, h, w, fin, cap, R, arena)
         buf = self._cache.get(key)
         if buf is None:
-            self._cache.clear()
+            while len(self._cache) >= 2:     # two shapes stay resident (the chunked host path uses two chunk sizes)
+                self._cache.pop(next(iter(self._cache)))
             L = _lib.lib()
             ws_bytes = self._workspace_bytes(L, N, C, h, w, fin, cap, R, arena)
             nb, ns = N * cap * 16, N * cap * 4
@@ -166,10 +167,48 @@ class ExpandOperator(object):
         extras = {k: v.cpu().numpy() for k, v in extras_dev.items()}
         return boxes, scores, counts, status, extras
 
+    upload_chunk_bytes = 128 << 20   # H2D chunk of the host-input path
+
+    def _call_host_batch(self, pred, shape_list, per):
+        """CPU-tensor maps: the upload is PCIe-bound and an order of magnitude longer than the kernels, so the batch
+        goes up in chunks of `per` images on a copy stream and every chunk is post-processed while the next ones are
+        still in flight (as DBPostProcess does)."""
+        torch = _lib.require_cuda()
+        t = pred.detach()
+        if t.dtype not in (torch.float32, torch.float16):
+            t = t.float()
+        N = t.shape[0]
+        dev = torch.device("cuda", torch.cuda.current_device())
+        shape = np.asarray(shape_list, dtype=np.float64).reshape(N, -1)
+        nchunks = (N + per - 1) // per
+        bounds = [N * i // nchunks for i in range(nchunks + 1)]
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        full = torch.empty(t.shape, dtype=t.dtype, device=dev)
+        self._copy_stream.wait_stream(main)
+        events = []
+        with torch.cuda.stream(self._copy_stream):
+            for lo, hi in zip(bounds[:-1], bounds[1:]):
+                full[lo:hi].copy_(t[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+                events.append(ev)
+        full.record_stream(self._copy_stream)
+        res = []
+        for ev, lo, hi in zip(events, bounds[:-1], bounds[1:]):
+            main.wait_event(ev)
+            res += self({"maps": full[lo:hi]}, shape[lo:hi])
+        return res
+
     def __call__(self, outs_dict, shape_list):
         torch = _lib.require_cuda()
         pred = outs_dict["maps"]
         assert isinstance(pred, torch.Tensor)      # pse_postprocess.py:30 / pan_postprocess.py:32
+        if not pred.is_cuda and pred.dim() == 4 and pred.shape[0] >= 2:
+            per = max(1, self.upload_chunk_bytes // max(1, pred[0].numel() * pred.element_size()))
+            if pred.shape[0] >= 2 * per:
+                return self._call_host_batch(pred, shape_list, per)
         boxes, scores, counts, _, _ = self.run_device(pred, shape_list)
         res_batch = []
         for n in range(boxes.shape[0]):

@@ -160,3 +160,18 @@ def test_pse_row_extent_blocks_reserved_and_deferred():
     maps[1, 0, 30:34, 44:60] = 3.0                  # second image: an extra short component with its own kernel
     maps[1, 1:, 31:33, 46:58] = 3.0
     _check(maps, _shape(2, H, W), maps_at_processing_res=True, max_runs=100, min_area=2, box_thresh=0.5, loose=0.5)
+
+
+def test_pse_host_batch_is_uploaded_in_chunks():
+    """CPU-tensor maps of a large batch take the chunked upload path: same results as the device-tensor path."""
+    import torch
+    H, W = 96, 128
+    maps = np.stack([synth.pse_maps(60 + i, H, W) for i in range(9)])
+    sl = _shape(9, H, W)
+    op = _op(maps_at_processing_res=True)
+    op.upload_chunk_bytes = 2 * maps[0].nbytes            # 9 images -> chunks of 2 (5 chunks, unequal sizes)
+    want = op({"maps": torch.from_numpy(maps).cuda()}, sl)
+    got = op({"maps": torch.from_numpy(maps).pin_memory()}, sl)
+    assert len(got) == len(want) == 9
+    for g, w in zip(got, want):
+        assert np.array_equal(g["points"], w["points"]) and np.allclose(g["scores"], w["scores"])
