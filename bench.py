@@ -661,6 +661,12 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev_max, ms_e2e_max = float(t[0]), float(t[1])
+    rank_ms = [ms_dev / args.steps]
+    if world > 1:   # per-rank step times next to the max the headline uses (which GPU is the slow one, and by how much)
+        mine = torch.tensor([ms_dev / args.steps], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rank_ms = [float(x[0]) for x in allr]
 
     if rank == 0:
         peaks = {}
@@ -700,6 +706,7 @@ def run_ours(args):
             "e2e": {"value": world * e2e_units * e2e_steps / (ms_e2e_max * 1e-3), "unit": wl.unit,
                     "h2d_bytes_per_step": wl.h2d_bytes(), "d2h_bytes_per_step": wl.d2h_bytes(), "steps": e2e_steps},
             "gpu_launches": int(launches),
+            "ms_per_step_by_rank": rank_ms,
             "clocks": sampler.summary(),
         }
         if cpu_base is not None:
