@@ -179,3 +179,79 @@ def test_box_points_order_matches_cv2(shim):
         if i % 3 == 0:
             n_diamond += 1
     assert n_diamond > 300
+
+
+def _cross(o, a, b):
+    return (a[0] - o[0]) * (b[1] - o[1]) - (a[1] - o[1]) * (b[0] - o[0])
+
+
+def _hull_sorted(pts):
+    """hull_sorted32 (dev_geom.cuh) / geom::hull_sorted: monotone chain over points sorted by (y, x)."""
+    out = []
+    for i, q in enumerate(pts):
+        if i > 0 and q == pts[i - 1]:
+            continue
+        while len(out) >= 2 and _cross(out[-2], out[-1], q) <= 0:
+            out.pop()
+        out.append(q)
+    if len(out) == 1:
+        return out
+    lo = len(out) + 1
+    for i in range(len(pts) - 2, -1, -1):
+        q = pts[i]
+        if q == pts[i + 1]:
+            continue
+        while len(out) >= lo and _cross(out[-2], out[-1], q) <= 0:
+            out.pop()
+        out.append(q)
+    return out[:-1]
+
+
+def _hull_row_extents(ext):
+    """hull_row_extents32 (dev_geom.cuh) / the loops of db_hull_kernel: the first pass visits right extents only,
+    the second left extents only."""
+    out = [ext[0][0]]
+    prev = ext[0][0]
+    for l, r in ext:
+        if r == prev:
+            continue
+        prev = r
+        while len(out) >= 2 and _cross(out[-2], out[-1], r) <= 0:
+            out.pop()
+        out.append(r)
+    if len(out) == 1:
+        return out
+    lo = len(out) + 1
+    for l, r in reversed(ext):
+        if l == prev:
+            continue
+        prev = l
+        while len(out) >= lo and _cross(out[-2], out[-1], l) <= 0:
+            out.pop()
+        out.append(l)
+    return out[:-1]
+
+
+def test_row_extent_hull_equals_generic_monotone_chain():
+    """The CUDA hull kernels visit each row extent once per chain (right extents going down, left extents coming
+    back). Same vertices in the same order as the generic chain over all 2*rows points, for any row-extent set:
+    ragged blobs, single-pixel rows, straight edges, one-row and one-column sets."""
+    rng = np.random.default_rng(0)
+    for it in range(6000):
+        nrows = int(rng.integers(1, 40))
+        y0 = int(rng.integers(0, 50))
+        mode = it % 4
+        ext = []
+        c = int(rng.integers(20, 60))
+        for i in range(nrows):
+            if mode == 0:
+                l = int(rng.integers(0, 80)); r = l + int(rng.integers(0, 30))
+            elif mode == 1:      # smooth blob
+                c += int(rng.integers(-2, 3)); w = int(rng.integers(0, 12)); l, r = c - w, c + w
+            elif mode == 2:      # many single-pixel rows / straight diagonals
+                l = r = 10 + i * int(rng.integers(0, 3))
+            else:                # straight left edge, ragged right edge
+                l = 5; r = 5 + int(rng.integers(0, 20))
+            ext.append(((l, y0 + i), (r, y0 + i)))
+        flat = [p for pair in ext for p in pair]
+        assert _hull_row_extents(ext) == _hull_sorted(flat), ext
