@@ -96,3 +96,17 @@ def test_tied_min_area_rects_contains_cv2_choice():
         want = np.sort(cv2.boxPoints(cv2.minAreaRect(pts.astype(np.float32))), axis=0)
         cands = G.tied_min_area_rects(pts, rel=2e-6, corners=True)
         assert any(np.abs(np.sort(c, axis=0) - want).max() < 1e-2 for c in cands), pts.tolist()
+
+
+def test_sort_order_is_sort_boxes_as_a_permutation():
+    """`sort_order` (the form the CUDA plan kernel implements: stable rank by (y, x, index) of the first corner, then
+    ONE carried-element swap pass) reproduces `sort_boxes` on clustered rows, exact ties and long swap chains."""
+    rng = np.random.default_rng(1)
+    for it in range(400):
+        n = int(rng.integers(1, 60))
+        boxes = np.zeros((n, 4, 2), np.int16)
+        boxes[:, 0, 1] = rng.choice([10, 14, 19, 21, 30, 39, 40, 41], n) if it % 2 else rng.integers(0, 100, n)
+        boxes[:, 0, 0] = rng.integers(0, 12 if it % 3 == 0 else 300, n)
+        boxes[:, 1:] = rng.integers(0, 300, (n, 3, 2))
+        want = np.asarray(co.sort_boxes(boxes), np.int16).reshape(-1, 4, 2)
+        assert np.array_equal(boxes[co.sort_order(boxes)], want)
