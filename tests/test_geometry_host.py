@@ -255,3 +255,27 @@ def test_row_extent_hull_equals_generic_monotone_chain():
             ext.append(((l, y0 + i), (r, y0 + i)))
         flat = [p for pair in ext for p in pair]
         assert _hull_row_extents(ext) == _hull_sorted(flat), ext
+
+
+def test_scan_kernel_fixed_point_trick():
+    """db_scan_kernel turns a probability f in [0,1] into round(f * 2^23) with `bits(f + 1.0f) - 0x3f800000` (one FADD,
+    one IADD) and flags everything else through the same number: restated in numpy - the trick is exact
+    round-to-nearest-even on the 2^-23 grid for every float32 in [0,1], and any value outside [0,1] (negative, > 1,
+    NaN, +-Inf) yields a result > 2^23, which is what sets OCRPP_IMG_VALUE_OUT_OF_RANGE."""
+    rng = np.random.default_rng(0)
+    f = np.concatenate([rng.random(1 << 20, dtype=np.float32),
+                        np.float32(2.0) ** -np.arange(1, 60, dtype=np.float32),          # tiny values and ties
+                        (np.arange(0, 4096, dtype=np.float32) + np.float32(0.5)) * np.float32(2.0 ** -23),
+                        np.array([0.0, 1.0, np.nextafter(np.float32(1), np.float32(0)), 1e-45], np.float32)])
+    with np.errstate(invalid="ignore"):
+        u = (f + np.float32(1.0)).astype(np.float32).view(np.uint32) - np.uint32(0x3f800000)
+    assert np.array_equal(u.astype(np.int64), np.rint(f.astype(np.float64) * 2.0 ** 23).astype(np.int64))
+    one_2ulp = np.nextafter(np.nextafter(np.float32(1), np.float32(2)), np.float32(2))
+    bad = np.array([-1e-45, -1e-8, -0.5, -3.0, one_2ulp, 1.5, 2.0, 1e30, np.inf, -np.inf, np.nan], np.float32)
+    with np.errstate(invalid="ignore", over="ignore"):
+        ub = ((bad + np.float32(1.0)).astype(np.float32).view(np.uint32) - np.uint32(0x3f800000)).astype(np.uint32)
+    # -1e-45 and -1e-8 round to +1.0f exactly (they are below half an ulp of 1.0): indistinguishable from 0 and harmless,
+    # as is 1 + 1 ulp, which rounds to 2.0f like 1.0 does; everything further out is flagged
+    assert (ub[2:] > (1 << 23)).all() and (ub[:2] == 0).all()
+    one_1ulp = np.array([np.nextafter(np.float32(1), np.float32(2))], np.float32)
+    assert int(((one_1ulp + np.float32(1.0)).view(np.uint32) - np.uint32(0x3f800000))[0]) == 1 << 23
