@@ -110,3 +110,17 @@ def test_sort_order_is_sort_boxes_as_a_permutation():
         boxes[:, 1:] = rng.integers(0, 300, (n, 3, 2))
         want = np.asarray(co.sort_boxes(boxes), np.int16).reshape(-1, 4, 2)
         assert np.array_equal(boxes[co.sort_order(boxes)], want)
+
+
+def test_integer_bilinear_weights_equal_the_float32_table():
+    """crop_warp_kernel computes cv2's int16 bilinear table entries as 32*(32-ay)*(32-ax) etc. (saturated at 32767)
+    instead of saturate_cast<short>((1-fy)(1-fx) * 32768) in float32: identical for all 32 x 32 fractions."""
+    f32 = np.float32
+    for ay in range(32):
+        for ax in range(32):
+            fy, fx = f32(ay) / f32(32), f32(ax) / f32(32)
+            tab = [(f32(1) - fy) * (f32(1) - fx), (f32(1) - fy) * fx, fy * (f32(1) - fx), fy * fx]
+            tab = [int(np.clip(np.rint(t * f32(32768)), -32768, 32767)) for t in tab]
+            ints = [min(32767, 32 * (32 - ay) * (32 - ax)), 32 * (32 - ay) * ax, 32 * ay * (32 - ax), 32 * ay * ax]
+            assert tab == ints, (ay, ax)
+            assert sum(ints) in (32768, 32767)
