@@ -279,3 +279,42 @@ def test_scan_kernel_fixed_point_trick():
     assert (ub[2:] > (1 << 23)).all() and (ub[:2] == 0).all()
     one_1ulp = np.array([np.nextafter(np.float32(1), np.float32(2))], np.float32)
     assert int(((one_1ulp + np.float32(1.0)).view(np.uint32) - np.uint32(0x3f800000))[0]) == 1 << 23
+
+
+def test_dilated_scan_word_formula_equals_cv2_dilate():
+    """use_dilation: db_scan_kernel<kDilate> builds the dilated mask from the raw threshold bits in the lane-major
+    layout (word k of a 128-pixel group, bit `lane` = pixel 4*lane + k): pixel x-1 is word k-1 at the same bit, or
+    word 3 shifted up by one lane (with the last bit of the previous group carried in) for k = 0; rows y and y-1 are
+    ORed. Restated word for word in numpy and compared with cv2.dilate(seg, [[1,1],[1,1]])."""
+    rng = np.random.default_rng(3)
+    epl = 4
+    for W in (128, 256, 200, 131, 1280):
+        H = 9
+        seg = (rng.random((H, W)) > 0.7).astype(np.uint8)
+        ng = (W + 32 * epl - 1) // (32 * epl)
+
+        def pack(row):
+            words = np.zeros((ng, epl), np.uint64)
+            for x in np.nonzero(row)[0]:
+                g, r = divmod(int(x), 32 * epl)
+                words[g, r % epl] |= np.uint64(1) << np.uint64(r // epl)
+            return words
+        raw = [pack(seg[y]) for y in range(H)]
+        got = np.zeros_like(seg)
+        M32 = np.uint64(0xffffffff)
+        for y in range(H):
+            cy = cu = np.uint64(0)
+            for g in range(ng):
+                ry = raw[y][g]
+                ru = raw[y - 1][g] if y > 0 else np.zeros(epl, np.uint64)
+                for k in range(epl):
+                    py = (((ry[epl - 1] << np.uint64(1)) | cy) & M32) if k == 0 else ry[k - 1]
+                    pu = (((ru[epl - 1] << np.uint64(1)) | cu) & M32) if k == 0 else ru[k - 1]
+                    m = int(ry[k] | py | ru[k] | pu)
+                    for lane in range(32):
+                        x = g * 32 * epl + lane * epl + k
+                        if x < W and (m >> lane) & 1:
+                            got[y, x] = 1
+                cy, cu = ry[epl - 1] >> np.uint64(31), ru[epl - 1] >> np.uint64(31)
+        want = cv2.dilate(seg, np.array([[1, 1], [1, 1]], np.uint8))
+        assert np.array_equal(got, want), W
