@@ -81,6 +81,10 @@ float shim_unclip_distance(const float* bxy, float ratio) {
   return unclip_distance(bx, by, ratio);
 }
 
+void shim_db_rescale(float mx, float my, int W, int H, float sw, float sh, int use_padding_resize, float* out) {
+  db_rescale(mx, my, W, H, sw, sh, use_padding_resize, &out[0], &out[1]);
+}
+
 float shim_roundf(float v) { return roundf_half_away(v); }
 double shim_round_half_even(double v) { return round_half_even(v); }
 }

@@ -318,3 +318,32 @@ def test_dilated_scan_word_formula_equals_cv2_dilate():
                 cy, cu = ry[epl - 1] >> np.uint64(31), ru[epl - 1] >> np.uint64(31)
         want = cv2.dilate(seg, np.array([[1, 1], [1, 1]], np.uint8))
         assert np.array_equal(got, want), W
+
+
+def test_db_rescale_padding_resize_matches_the_reference_affine_map(shim):
+    """use_padding_resize (db_postprocess.cpp:111-145,293-302): the closed form in geom::db_rescale equals the
+    reference's get_affine_transform (cv::getAffineTransform on three float32 point pairs, inverse direction) +
+    transform_preds (float64 product, cast to float32), for landscape, portrait and square sources."""
+    shim.shim_db_rescale.argtypes = [C.c_float, C.c_float, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(2)
+    f = np.float32
+    for src_w, src_h, side in ((640, 480, 256), (600, 900, 256), (512, 512, 128), (1279, 733, 736), (31, 977, 320)):
+        center = np.array([f(src_w / 2.0), f(src_h / 2.0)], np.float32)
+        img_max = f(src_w if src_w > src_h else src_h)
+        s_tri, d_tri = np.zeros((3, 2), np.float32), np.zeros((3, 2), np.float32)
+        s_tri[0] = center
+        s_tri[1] = center + np.array([0, img_max / 2.0], np.float32)
+        d_tri[0] = (f(side) / 2.0, f(side) / 2.0)
+        d_tri[1] = d_tri[0] + np.array([0, f(side) / 2.0], np.float32)
+        d_tri[2] = (0, 0)
+        s_tri[2] = (0, center[1] - center[0]) if center[0] >= center[1] else (center[0] - center[1], 0)
+        warp = cv2.getAffineTransform(d_tri, s_tri).T          # map -> source, as the reference builds it (inv=1)
+        out = np.zeros(2, np.float32)
+        for _ in range(200):
+            mx, my = f(rng.uniform(0, side)), f(rng.uniform(0, side))
+            want = np.array([[float(mx), float(my), 1.0]], np.float64) @ warp
+            shim.shim_db_rescale(mx, my, side, side, f(src_w), f(src_h), 1, out.ctypes.data_as(C.c_void_p))
+            assert abs(float(out[0]) - float(f(want[0, 0]))) <= 1e-3 and abs(float(out[1]) - float(f(want[0, 1]))) <= 1e-3
+        # plain scaling branch (:303-311), float32 in source order
+        shim.shim_db_rescale(f(100.25), f(7.5), side, side, f(src_w), f(src_h), 0, out.ctypes.data_as(C.c_void_p))
+        assert out[0] == f(f(f(100.25) / f(side)) * f(src_w)) and out[1] == f(f(f(7.5) / f(side)) * f(src_h))
