@@ -2,6 +2,7 @@
 
     python tests/golden/make_golden.py          (needs /root/reference and oracle/_ref built)
     python tests/golden/make_golden.py crops    (reference_crops.npz only: sort_boxes / get_part_img)
+    python tests/golden/make_golden.py dbpy     (reference_db_python.npz only: the reference's pure-Python DB branch)
 
 What runs unmodified from /root/reference (imported in place, nothing is copied):
   * pytocr.postprocess.pse_postprocess.PSEPostProcess    (whole operator incl. generate_box)
@@ -10,11 +11,14 @@ What runs unmodified from /root/reference (imported in place, nothing is copied)
   * pytocr.postprocess.db_postprocess.DBPostProcess.__call__ (cpp_speedup=True wrapper semantics)
   * the compiled pse.pyx / pa.pyx (oracle/_ref, built unmodified by oracle/build_ref.py) behind the
     package names the operators import them from
-What is stubbed and why: `pyclipper` / `shapely` (absent; only the non-cpp_speedup DB
-branch uses them), and `pytocr.postprocess.db_postprocess_fast.cpp_boxes_from_bitmap` (the C++ module
-needs OpenCV C++ headers, absent) -> oracle/db_oracle.boxes_from_bitmap, the cv2-python restatement
-that calls the reference's own compiled Clipper. So the DB fixture pins the operator wrapper, not the
-C++ box extraction (DB parity stays "unpinned upstream", see oracle/__init__.py).
+What is stubbed and why: `pyclipper` / `shapely` (absent from the image) -> oracle/ref_shims.py
+(the reference's own compiled Clipper behind pyclipper's three calls; GEOS' ring area / length), and
+`pytocr.postprocess.db_postprocess_fast.cpp_boxes_from_bitmap` (the C++ module needs OpenCV C++ headers,
+absent) -> oracle/db_oracle.boxes_from_bitmap, the cv2-python restatement that calls the reference's own
+compiled Clipper. So `reference_outputs.npz`'s DB entries pin the operator wrapper only, while
+`reference_db_python.npz` (main_db_python) holds outputs of the reference's UNMODIFIED pure-Python DB branch
+(`DBPostProcess(cpp_speedup=False)`, db_postprocess.py:76-194: findContours -> get_mini_boxes -> box_score ->
+unclip -> get_mini_boxes -> rescale) - per stage and final - which pin the stages both branches share.
 
 The fixtures are small (inputs + outputs, a few hundred KB) and are checked by
 tests/test_golden.py against the oracle (CPU) and against the CUDA path (-m gpu).
@@ -34,9 +38,8 @@ sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
 
 def import_reference():
     import torch  # noqa: F401
-    for name in ("pyclipper", "shapely", "shapely.geometry"):
-        sys.modules[name] = types.ModuleType(name)
-    sys.modules["shapely.geometry"].Polygon = object
+    from oracle import ref_shims
+    ref_shims.install()
     import pa as pa_mod
     import pse as pse_mod
     from oracle import db_oracle
@@ -193,8 +196,107 @@ def main_crops():
     print("wrote reference_crops.npz", out["dims"].tolist())
 
 
+def db_python_maps():
+    """10 maps 160x256 (stored as float16, exact round trip): 8 synthetic DB pages (rotated regions, holes, low-score
+    regions, specks, 1-px runs, border regions) and 2 blurred noise fields (many nested holes, ragged contours)."""
+    import cv2
+    from pytorchocr_b200 import synth
+    Hd, Wd = 160, 256
+    maps = [synth.db_map(900 + i, H=Hd, W=Wd, n_regions=200) for i in range(8)]
+    rng = np.random.default_rng(77)
+    for sigma in (1.5, 2.5):
+        f = cv2.GaussianBlur(rng.random((Hd, Wd)).astype(np.float32), (0, 0), sigma)
+        f = (f - f.min()) / (f.max() - f.min())
+        maps.append(np.clip(0.3 + (f - np.quantile(f, 0.55)) * 6.0, 0, 1).astype(np.float32))
+    return np.stack(maps)[:, None].astype(np.float16)
+
+
+DBPY_CONFIGS = {   # name -> (constructor kwargs, use_padding_resize)
+    "poly": (dict(), False),
+    "box": (dict(score_mode="box"), False),
+    "dilate": (dict(use_dilation=True), False),
+    "pad": (dict(), True),
+    "cand5": (dict(max_candidates=5), False),
+    "r20": (dict(unclip_ratio=2.0, box_thresh=0.6, thresh=0.2), False),
+}
+
+
+def main_db_python():
+    """tests/golden/reference_db_python.npz: the reference's pure-Python DB branch, unmodified, per stage and final."""
+    import torch
+    build = import_reference()
+    maps16 = db_python_maps()
+    maps = maps16.astype(np.float32)
+    N, _, Hd, Wd = maps.shape
+    sl = np.array([[Hd, Wd, 1.0, 1.0], [240, 320, 1.5, 1.25], [200, 200, 1.25, 0.78], [97, 301, 0.6, 1.18]] * 3,
+                  np.float64)[:N]
+    out = {"maps": maps16, "shape": sl}
+    for name, (kw, pad) in DBPY_CONFIGS.items():
+        cfg = dict({"name": "DBPostProcess", "thresh": 0.3, "box_thresh": 0.5, "max_candidates": 1000,
+                    "unclip_ratio": 1.7, "score_mode": "poly", "cpp_speedup": False}, **kw)
+        op = build(cfg)
+        # record every stage call of the unmodified methods (inputs are reproducible from the maps)
+        trace = {"mini_in_n": [], "mini_box": [], "mini_side": [], "score": [], "unclip_in": [], "unclip_n": [],
+                 "unclip_pts": []}
+        g, b, u = op.get_mini_boxes, op.box_score, op.unclip
+
+        def get_mini_boxes(contour, g=g, t=trace):
+            box, side = g(contour)
+            t["mini_in_n"].append(len(contour))
+            t["mini_box"].append(np.asarray(box, np.float32))
+            t["mini_side"].append(np.float32(side))
+            return box, side
+
+        def box_score(bitmap, pts, b=b, t=trace):
+            s = b(bitmap, pts)
+            t["score"].append(s)
+            return s
+
+        def unclip(box, u=u, t=trace):
+            e = u(box)
+            t["unclip_in"].append(np.asarray(box, np.float32))
+            t["unclip_n"].append(0 if len(e) != 1 else e.shape[1])
+            if len(e) == 1:
+                t["unclip_pts"].append(np.asarray(e[0], np.int32))
+            return e
+        op.get_mini_boxes, op.box_score, op.unclip = get_mini_boxes, box_score, unclip
+        res = op({"maps": torch.from_numpy(maps)}, sl, use_padding_resize=pad)
+        for n, r in enumerate(res):
+            out["%s_points_%d" % (name, n)] = np.asarray(r["points"], np.int16).reshape(-1, 4, 2)
+            out["%s_scores_%d" % (name, n)] = np.asarray(r["scores"], np.float64)
+        out[name + "_mini_in_n"] = np.asarray(trace["mini_in_n"], np.int32)
+        out[name + "_mini_box"] = np.asarray(trace["mini_box"], np.float32).reshape(-1, 4, 2)
+        out[name + "_mini_side"] = np.asarray(trace["mini_side"], np.float32)
+        out[name + "_score"] = np.asarray(trace["score"], np.float64)
+        out[name + "_unclip_in"] = np.asarray(trace["unclip_in"], np.float32).reshape(-1, 4, 2)
+        out[name + "_unclip_n"] = np.asarray(trace["unclip_n"], np.int32)
+        out[name + "_unclip_pts"] = (np.concatenate(trace["unclip_pts"]) if trace["unclip_pts"]
+                                     else np.zeros((0, 2), np.int32))
+    # out_polygon=True (db_postprocess.py:98-103,119-122,142): polygons of different lengths end in
+    # np.array(boxes, dtype=np.int16) -> ValueError under every numpy version (an explicit numeric dtype never
+    # builds a ragged object array). Recorded as evidence that the branch has no behaviour to reproduce.
+    op = build({"name": "DBPostProcess", "thresh": 0.3, "box_thresh": 0.5, "unclip_ratio": 1.7,
+                "cpp_speedup": False, "out_polygon": True})
+    errs = []
+    for n in range(N):
+        try:
+            r = op({"maps": torch.from_numpy(maps[n:n + 1])}, sl[n:n + 1])
+            errs.append("ok shape=%s" % (np.asarray(r[0]["points"]).shape,))
+        except Exception as e:      # noqa: BLE001
+            errs.append("%s: %s" % (type(e).__name__, str(e)[:60]))
+    out["out_polygon_outcome"] = np.array(errs)
+    np.savez_compressed(os.path.join(HERE, "reference_db_python.npz"), **out)
+    print("wrote reference_db_python.npz")
+    for name in DBPY_CONFIGS:
+        print(" ", name, [len(out["%s_points_%d" % (name, n)]) for n in range(N)], "stage calls:",
+              len(out[name + "_mini_side"]), len(out[name + "_score"]), len(out[name + "_unclip_n"]))
+    print("  out_polygon:", errs)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "crops":
         main_crops()
+    elif len(sys.argv) > 1 and sys.argv[1] == "dbpy":
+        main_db_python()
     else:
         main()
