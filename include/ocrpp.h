@@ -70,6 +70,15 @@ OCRPP_API const char* ocrpp_last_error(void);
 OCRPP_API int64_t ocrpp_launch_count(void);
 OCRPP_API void ocrpp_reset_launch_count(void);
 
+/* Test / tuning hook (process-wide, not part of the reference-facing surface): selects between code paths that
+ * produce identical results, so that the parity tests can exercise each of them and bench.py can sweep them.
+ * value 0 always restores the default. */
+#define OCRPP_TUNE_DB_PATH 0   /* 0 auto | 1 one-kernel-per-image stage, shared-memory tables | 2 same, global tables |
+                                * 3 run-parallel multi-kernel chain (what large images take) */
+#define OCRPP_TUNE_DB_SPLIT 1  /* sub-batch pipelines of one DB call (0 = chosen from the batch size) */
+#define OCRPP_TUNE_COUNT 8
+OCRPP_API int ocrpp_set_tuning(int key, int value);
+
 /* Per-kernel device timing for bench.py's roofline. While enabled, every detection entry point
  * brackets each of its kernels with cudaEventRecord on the caller's stream (events only, no
  * synchronisation). After the stream is synchronised, ocrpp_profile_read() returns, for phase i,

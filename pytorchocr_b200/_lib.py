@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libocrpp.so")
 OK = 0
 F32, F16 = 0, 1
 IMG_RUN_OVERFLOW, IMG_CANDIDATES_TRUNCATED, IMG_VALUE_OUT_OF_RANGE = 1, 2, 4
+TUNE_DB_PATH, TUNE_DB_SPLIT = 0, 1
 
 _lib = None
 
@@ -23,6 +24,7 @@ SIGNATURES = {
     "ocrpp_last_error": (C.c_char_p, []),
     "ocrpp_launch_count": (C.c_int64, []),
     "ocrpp_reset_launch_count": (None, []),
+    "ocrpp_set_tuning": (C.c_int, [C.c_int, C.c_int]),
     "ocrpp_profile_enable": (None, [C.c_int]),
     "ocrpp_profile_reset": (None, []),
     "ocrpp_profile_read": (C.c_int, [C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),

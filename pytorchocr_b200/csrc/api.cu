@@ -20,6 +20,11 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+namespace {
+std::atomic<int> g_tuning[OCRPP_TUNE_COUNT];
+}  // namespace
+int tuning(int key) { return (key >= 0 && key < OCRPP_TUNE_COUNT) ? g_tuning[key].load(std::memory_order_relaxed) : 0; }
+
 bool debug_sync() {
   static const bool on = [] {
     const char* e = getenv("OCRPP_DEBUG_SYNC");
@@ -84,6 +89,13 @@ const char* ocrpp_profile_phase_name(int phase) {
   return (phase >= 0 && phase < g_prof_phases && g_prof_names[phase]) ? g_prof_names[phase] : "";
 }
 
+
+int ocrpp_set_tuning(int key, int value) {
+  using namespace ocrpp;
+  OCRPP_CHECK_ARG(key >= 0 && key < OCRPP_TUNE_COUNT, "set_tuning: unknown key %d", key);
+  g_tuning[key].store(value);
+  return OCRPP_OK;
+}
 
 int ocrpp_abi_version(void) { return OCRPP_ABI_VERSION; }
 const char* ocrpp_last_error(void) { return ocrpp::last_error_buf(); }

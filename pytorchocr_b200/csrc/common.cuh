@@ -19,6 +19,7 @@ constexpr int kNumSMs = 148;  // B200
 char* last_error_buf();
 int set_error(int code, const char* fmt, ...);
 extern std::atomic<long long> g_launch_count;
+int tuning(int key);   // ocrpp_set_tuning value of `key` (0 = default)
 
 #define OCRPP_CHECK_ARG(cond, ...)                                           \
   do {                                                                       \

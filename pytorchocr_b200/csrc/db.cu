@@ -68,7 +68,11 @@ struct DbParams {
   int32_t* big;          // [maxc] candidates deferred to the generic geometry kernel
   int32_t* cand;         // [maxc]
   int32_t* res_keep;     // [maxc]
-  int32_t* hull_n;       // [maxc] vertices of the precomputed hull (db_hull_kernel)
+  int32_t* hull_n;       // [maxc] vertices of the precomputed hull (db_image_kernel / db_hull_kernel)
+  int32_t *cand_off, *cand_y0, *cand_nrows;   // [maxc] candidate -> slice of the extent/hull scratch, first row, rows
+  int32_t* cand_root;    // [R] root run of every dense component id (db_image_kernel, global-table variant)
+  uint32_t* flagw;       // [R/32+1] run flag words (db_image_kernel, global-table variant)
+  int stairs, skip2;     // reference-branch switches: 4-connected fillPoly boundary (stair pixels), <= 2-point skip
   int16_t* res_box;      // [maxc*8]
   float* res_boxf;       // [maxc*8]
   float* res_score;      // [maxc]
@@ -850,31 +854,14 @@ __global__ void __launch_bounds__(kGeoWarps * 32) db_geometry_big_kernel(DbParam
   __shared__ P2i s_offh[kGeoWarps][kOffCap + 2];
   const int n = blockIdx.y + p.n0;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t ro = (size_t)n * p.R;
   const int nbig = min(p.nbig[n], p.maxc);
   for (int bi = blockIdx.x * kGeoWarps + wib; bi < nbig; bi += gridDim.x * kGeoWarps) {
   const int k = p.big[(size_t)n * p.maxc + bi];
   const size_t ko = (size_t)n * p.maxc + k;
-  const int c = p.cand[ko];
-  const int fg = p.run_yf[ro + c] >> 15;
-  const int y_first = p.run_yf[ro + c] & 0x7fff;
   if (lane == 0) p.res_keep[ko] = 0;
-
-  // "contour has <= 2 points" <=> one pixel or a 1-px straight run (-, |, /, \) (db_postprocess.cpp:255-257)
-  if (fg) {
-    const int area = p.area[ro + c];
-    const int bw = p.xmax[ro + c] - p.xmin[ro + c] + 1, bh = p.ymax[ro + c] - y_first + 1;
-    const bool diag = (bw == bh && bw == area) &&
-                      (p.dmin[ro + c] == p.dmax[ro + c] || p.smin[ro + c] == p.smax[ro + c]);
-    if (area == 1 || (bh == 1 && area == bw) || (bw == 1 && area == bh) || diag) continue;
-  }
-  const int off = p.rowoff[ro + c];
-  if (off < 0) {  // extent arena exhausted (cannot happen with E = 4R); fail loudly
-    if (lane == 0) atomicOr(&p.imgflags[n], OCRPP_IMG_RUN_OVERFLOW);
-    continue;
-  }
-  const int nrows = fg ? (p.ymax[ro + c] - y_first + 1) : (p.ymax[ro + c] - y_first + 3);
-  const int y0 = fg ? y_first : y_first - 1;
+  // triaged by db_image_kernel / db_hull_kernel: <= 2-point rule and BoxScore passed
+  const float score = p.res_score[ko];
+  const int off = p.cand_off[ko], nrows = p.cand_nrows[ko], y0 = p.cand_y0[ko];
   const int32_t* ext_l = p.ext_l + (size_t)n * p.E + off;
   const int32_t* ext_r = p.ext_r + (size_t)n * p.E + off;
   P2i* pts;
@@ -907,12 +894,6 @@ __global__ void __launch_bounds__(kGeoWarps * 32) db_geometry_big_kernel(DbParam
   geom::mini_box(cx, cy, mx, my);
   const float ssid = fmaxf((float)rect.w, (float)rect.h);
   if (ssid < 3.f) continue;
-
-  // BoxScore (db_postprocess.cpp:194-229): mean over the filled contour, double accumulation
-  const long long tot = p.sum[ro + c] + p.fsum[ro + c] + p.xsum[ro + c];
-  const int cnt = p.area[ro + c] + p.fcnt[ro + c] + p.xcnt[ro + c];
-  const float score = (float)(((double)tot / kFixScale) / (double)cnt);
-  if (score < p.box_thresh) continue;
 
   // UnClip (db_postprocess.cpp:34-64)
   const float distance = geom::unclip_distance(mx, my, p.unclip_ratio);
@@ -988,7 +969,7 @@ __global__ void __launch_bounds__(kHullThreads) db_hull_kernel(DbParams p) {
   const int ymax = p.ymax[ro + c];
   const int area = p.area[ro + c];
   p.res_keep[ko] = 0;
-  if (fg) {  // "contour has <= 2 points" (db_postprocess.cpp:255-257)
+  if (fg && p.skip2) {  // "contour has <= 2 points" (db_postprocess.cpp:255-257)
     const int bw = p.xmax[ro + c] - p.xmin[ro + c] + 1, bh = ymax - y_first + 1;
     const bool diag = (bw == bh && bw == area) &&
                       (p.dmin[ro + c] == p.dmax[ro + c] || p.smin[ro + c] == p.smax[ro + c]);
@@ -996,10 +977,8 @@ __global__ void __launch_bounds__(kHullThreads) db_hull_kernel(DbParams p) {
   }
   const int nrows = fg ? (ymax - y_first + 1) : (ymax - y_first + 3);
   const int off = p.rowoff[ro + c];
-  if (nrows > kFastRows || off < 0 || p.W >= 16384 || p.H >= 16384) {
-    const int slot = atomicAdd(&p.nbig[n], 1);
-    if (slot < p.maxc) p.big[(size_t)n * p.maxc + slot] = k;
-    p.res_keep[ko] = 2;
+  if (off < 0) {  // extent arena exhausted (cannot happen with E = 4R); fail loudly
+    atomicOr(&p.imgflags[n], OCRPP_IMG_RUN_OVERFLOW);
     return;
   }
   // BoxScore first: a low score drops the candidate whatever its rectangle is
@@ -1007,6 +986,16 @@ __global__ void __launch_bounds__(kHullThreads) db_hull_kernel(DbParams p) {
   const int cnt = area + p.fcnt[ro + c] + p.xcnt[ro + c];
   const float score = (float)(((double)tot / kFixScale) / (double)cnt);
   if (score < p.box_thresh) return;
+  p.res_score[ko] = score;
+  p.cand_off[ko] = off;
+  p.cand_y0[ko] = fg ? y_first : y_first - 1;
+  p.cand_nrows[ko] = nrows;
+  if (nrows > kFastRows || p.W >= 16384 || p.H >= 16384) {
+    const int slot = atomicAdd(&p.nbig[n], 1);
+    if (slot < p.maxc) p.big[(size_t)n * p.maxc + slot] = k;
+    p.res_keep[ko] = 2;
+    return;
+  }
 
   const int y0 = fg ? y_first : y_first - 1;
   const int32_t* ext_l = p.ext_l + (size_t)n * p.E + off;
@@ -1057,9 +1046,10 @@ __global__ void __launch_bounds__(kHullThreads) db_hull_kernel(DbParams p) {
   }
   for (int i = 0; i < hn; ++i) gout[i] = out[i];
   p.hull_n[ko] = hn;
-  p.res_score[ko] = score;
   p.res_keep[ko] = 3;
 }
+
+#include "db_image.cuh"
 
 __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
   constexpr int kGroups = kGeoThreads / kGrp;
@@ -1071,14 +1061,12 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
   const unsigned gmask = ((1u << kGrp) - 1u) << ((threadIdx.x & 31) / kGrp * kGrp);
   const int k = blockIdx.x * kGroups + g;
   if (k >= p.ncand[n]) return;
-  const size_t ro = (size_t)n * p.R;
   const size_t ko = (size_t)n * p.maxc + k;
-  if (p.res_keep[ko] != 3) return;   // dropped or deferred by db_hull_kernel
+  if (p.res_keep[ko] != 3) return;   // dropped or deferred by the triage (db_image_kernel / db_hull_kernel)
   __syncwarp(gmask);
   if (gl == 0) p.res_keep[ko] = 0;
-  const int c = p.cand[ko];
   const float score = p.res_score[ko];
-  const int off = p.rowoff[ro + c];
+  const int off = p.cand_off[ko];
   auto defer = [&]() {
     if (gl == 0) {
       const int slot = atomicAdd(&p.nbig[n], 1);
@@ -1250,6 +1238,11 @@ size_t carve(DbParams& p, void* ws) {
   p.cand = c.take<int32_t>(N * p.maxc);
   p.res_keep = c.take<int32_t>(N * p.maxc);
   p.hull_n = c.take<int32_t>(N * p.maxc);
+  p.cand_off = c.take<int32_t>(N * p.maxc);
+  p.cand_y0 = c.take<int32_t>(N * p.maxc);
+  p.cand_nrows = c.take<int32_t>(N * p.maxc);
+  p.cand_root = c.take<int32_t>(N * R);
+  p.flagw = c.take<uint32_t>(N * (R / 32 + 1));
   p.res_box = c.take<int16_t>(N * p.maxc * 8);
   p.res_boxf = c.take<float>(N * p.maxc * 8);
   p.res_score = c.take<float>(N * p.maxc);
@@ -1270,6 +1263,8 @@ int resolve_max_runs(int H, int W, int max_runs) {
   if (max_runs <= 0 || max_runs > worst) return (int)worst;
   return max_runs;
 }
+
+constexpr int kImgSmemMax = 225 * 1024;   // dynamic shared memory of db_image_kernel (227 KB per CTA minus static)
 
 // auxiliary stream / events of the current device (created once, never destroyed)
 constexpr int kDbAuxStreams = 3;
@@ -1333,49 +1328,70 @@ int db_pipeline(DbParams p, int N, int dtype, cudaStream_t s, ProfileScope* prof
     OCRPP_LAUNCHED();
     if (prof) prof->mark("db_scan");
   }
-  const int ictas = max(kImgCtas, min(64, (kNumSMs * 4 + N - 1) / N));   // fill the GPU at small batch sizes too
-  db_runs_kernel<<<dim3(ictas, N), kRunThreads, sizeof(int) * (p.H + 1), s>>>(p);
-  OCRPP_LAUNCHED();
-  if (prof) prof->mark("db_runs");
-  dim3 rgrid(ictas, N);
-  const size_t ccl_smem = sizeof(int) * ((size_t)p.R + (p.R + 31) / 32 + 1);
-  if (ccl_smem <= (size_t)kCclSmemMax) {
-    // opt in to > 48 KB of dynamic shared memory (a per-device function attribute: set on every call)
-    OCRPP_CUDA(cudaFuncSetAttribute(db_ccl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCclSmemMax));
-    db_ccl_kernel<<<N, kCclThreads, kCclSmemMax, s>>>(p);
+  // Stage 2. Default: ONE kernel, one CTA per image, tables in shared memory (db_image.cuh). Large images
+  // (many rows / pixels: a single CTA per image would be the bottleneck) and the test hook take the run-parallel
+  // multi-kernel chain, which spreads every image over several CTAs with its tables in the global workspace.
+  const int path = tuning(OCRPP_TUNE_DB_PATH);
+  const bool fused = path != 3 && p.H <= 8191 && (long long)p.H * p.W <= (4ll << 20);
+  if (fused) {
+    const size_t want = sizeof(int) * (p.H + 1) + 10 * (size_t)p.R + 68 * ((size_t)p.R / 4 + 64) +
+                        8 * ((size_t)p.R + p.H) + 64;
+    const int smem = (int)(want < (size_t)kImgSmemMax ? want : (size_t)kImgSmemMax);
+    const int mode = path == 2 ? 1 : 0;
+    if (dtype == OCRPP_F32) {
+      OCRPP_CUDA(cudaFuncSetAttribute(db_image_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kImgSmemMax));
+      db_image_kernel<float><<<N, kImgThreads, smem, s>>>(p, smem, mode);
+    } else {
+      OCRPP_CUDA(cudaFuncSetAttribute(db_image_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kImgSmemMax));
+      db_image_kernel<__half><<<N, kImgThreads, smem, s>>>(p, smem, mode);
+    }
     OCRPP_LAUNCHED();
-    if (prof) prof->mark("db_ccl");
+    if (prof) prof->mark("db_image");
   } else {
-    db_slots_init_kernel<<<rgrid, 256, 0, s>>>(p);
+    const int ictas = max(kImgCtas, min(64, (kNumSMs * 4 + N - 1) / N));   // fill the GPU at small batch sizes too
+    db_runs_kernel<<<dim3(ictas, N), kRunThreads, sizeof(int) * (p.H + 1), s>>>(p);
     OCRPP_LAUNCHED();
-    db_link_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
+    if (prof) prof->mark("db_runs");
+    dim3 rgrid(ictas, N);
+    const size_t ccl_smem = sizeof(int) * ((size_t)p.R + (p.R + 31) / 32 + 1);
+    if (ccl_smem <= (size_t)kCclSmemMax) {
+      // opt in to > 48 KB of dynamic shared memory (a per-device function attribute: set on every call)
+      OCRPP_CUDA(cudaFuncSetAttribute(db_ccl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCclSmemMax));
+      db_ccl_kernel<<<N, kCclThreads, kCclSmemMax, s>>>(p);
+      OCRPP_LAUNCHED();
+      if (prof) prof->mark("db_ccl");
+    } else {
+      db_slots_init_kernel<<<rgrid, 256, 0, s>>>(p);
+      OCRPP_LAUNCHED();
+      db_link_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
+      OCRPP_LAUNCHED();
+      db_flatten_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
+      OCRPP_LAUNCHED();
+      if (prof) prof->mark("db_ccl");
+    }
+    db_stats_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
     OCRPP_LAUNCHED();
-    db_flatten_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
+    if (prof) prof->mark("db_stats");
+    db_tree_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
     OCRPP_LAUNCHED();
-    if (prof) prof->mark("db_ccl");
-  }
-  db_stats_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
-  OCRPP_LAUNCHED();
-  if (prof) prof->mark("db_stats");
-  db_tree_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
-  OCRPP_LAUNCHED();
-  if (prof) prof->mark("db_tree");
-  db_fill_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
-  OCRPP_LAUNCHED();
-  if (prof) prof->mark("db_fill");
-  if (dtype == OCRPP_F32) db_extents_kernel<float><<<rgrid, kRunBlk, 0, s>>>(p);
-  else db_extents_kernel<__half><<<rgrid, kRunBlk, 0, s>>>(p);
-  OCRPP_LAUNCHED();
-  if (prof) prof->mark("db_extents");
-  db_rank_kernel<<<N, kRunThreads, 0, s>>>(p);
-  OCRPP_LAUNCHED();
-  if (prof) prof->mark("db_rank");
-  {
-    constexpr int kGroups = kGeoThreads / kGrp;
-    dim3 grid((p.maxc + kGroups - 1) / kGroups, N);
+    if (prof) prof->mark("db_tree");
+    db_fill_kernel<<<rgrid, kRunBlk, 0, s>>>(p);
+    OCRPP_LAUNCHED();
+    if (prof) prof->mark("db_fill");
+    if (dtype == OCRPP_F32) db_extents_kernel<float><<<rgrid, kRunBlk, 0, s>>>(p);
+    else db_extents_kernel<__half><<<rgrid, kRunBlk, 0, s>>>(p);
+    OCRPP_LAUNCHED();
+    if (prof) prof->mark("db_extents");
+    db_rank_kernel<<<N, kRunThreads, 0, s>>>(p);
+    OCRPP_LAUNCHED();
+    if (prof) prof->mark("db_rank");
     db_hull_kernel<<<dim3((p.maxc + kHullThreads - 1) / kHullThreads, N), kHullThreads, 0, s>>>(p);
     OCRPP_LAUNCHED();
     if (prof) prof->mark("db_hull");
+  }
+  {
+    constexpr int kGroups = kGeoThreads / kGrp;
+    dim3 grid((p.maxc + kGroups - 1) / kGroups, N);
     db_geometry_kernel<<<grid, kGeoThreads, 0, s>>>(p);
     OCRPP_LAUNCHED();
     if (prof) prof->mark("db_geometry");
@@ -1431,6 +1447,8 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
   p.thresh = thresh; p.box_thresh = box_thresh; p.unclip_ratio = unclip_ratio;
   p.pad_resize = use_padding_resize ? 1 : 0;
   p.dilate = use_dilation ? 1 : 0;
+  p.stairs = 1;
+  p.skip2 = 1;
   const size_t need = carve(p, workspace_dev);
   if (need > workspace_bytes)
     return set_error(OCRPP_ERR_WORKSPACE_TOO_SMALL, "db: workspace needs %zu bytes, got %zu", need, workspace_bytes);
@@ -1443,7 +1461,7 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
   // scan of one sub-batch overlaps the ALU-bound geometry of another. (Not while per-phase profiling is
   // on: the event marks describe one whole-batch chain.)
   int nsplit = N >= 192 ? 4 : (N >= 64 ? 2 : 1);
-  static const int forced = [] { const char* e = getenv("OCRPP_DB_SPLIT"); return e ? atoi(e) : 0; }();   // tuning aid
+  const int forced = tuning(OCRPP_TUNE_DB_SPLIT);
   if (forced > 0) nsplit = forced > kDbAuxStreams + 1 ? kDbAuxStreams + 1 : forced;
   DbAux* aux = (nsplit > 1 && nsplit <= N && !profile_on()) ? db_aux() : nullptr;
   if (aux) {

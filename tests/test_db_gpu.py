@@ -15,6 +15,19 @@ pytestmark = pytest.mark.gpu
 CFG = dict(thresh=0.3, box_thresh=0.5, max_candidates=1000, unclip_ratio=1.7, score_mode="poly", cpp_speedup=True)
 
 
+@pytest.fixture(autouse=True, params=["image_smem", "image_global", "chain"])
+def db_path(request):
+    """Every test of this module runs on each of the library's three equivalent stage-2 code paths (include/ocrpp.h
+    OCRPP_TUNE_DB_PATH): one CTA per image with the tables in shared memory (the default for maps up to 4 Mpx), the
+    same kernel with the tables in the global workspace (what an image takes whose tables do not fit), and the
+    run-parallel multi-kernel chain (what larger maps take)."""
+    from pytorchocr_b200 import _lib
+    L = _lib.lib()
+    _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_PATH, {"image_smem": 1, "image_global": 2, "chain": 3}[request.param]))
+    yield request.param
+    _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_PATH, 0))
+
+
 def _op(**kw):
     from pytorchocr_b200.postprocess import build_post_process
     cfg = dict(CFG, name="DBPostProcess", cuda_speedup=True)
