@@ -70,6 +70,7 @@ struct DbParams {
   int32_t* res_keep;     // [maxc]
   int32_t* hull_n;       // [maxc] vertices of the precomputed hull (db_image_kernel / db_hull_kernel)
   int32_t *cand_off, *cand_y0, *cand_nrows;   // [maxc] candidate -> slice of the extent/hull scratch, first row, rows
+  int32_t* hcnt;         // [2*maxc] hull half lengths (db_image_kernel, global-table variant)
   int32_t* cand_root;    // [R] root run of every dense component id (db_image_kernel, global-table variant)
   uint32_t* flagw;       // [R/32+1] run flag words (db_image_kernel, global-table variant)
   int stairs, skip2;     // reference-branch switches: 4-connected fillPoly boundary (stair pixels), <= 2-point skip
@@ -1241,6 +1242,7 @@ size_t carve(DbParams& p, void* ws) {
   p.cand_off = c.take<int32_t>(N * p.maxc);
   p.cand_y0 = c.take<int32_t>(N * p.maxc);
   p.cand_nrows = c.take<int32_t>(N * p.maxc);
+  p.hcnt = c.take<int32_t>(N * p.maxc * 2);
   p.cand_root = c.take<int32_t>(N * R);
   p.flagw = c.take<uint32_t>(N * (R / 32 + 1));
   p.res_box = c.take<int16_t>(N * p.maxc * 8);
@@ -1388,6 +1390,10 @@ int db_pipeline(DbParams p, int N, int dtype, cudaStream_t s, ProfileScope* prof
     db_hull_kernel<<<dim3((p.maxc + kHullThreads - 1) / kHullThreads, N), kHullThreads, 0, s>>>(p);
     OCRPP_LAUNCHED();
     if (prof) prof->mark("db_hull");
+    if (p.labels_dbg) {
+      db_labels_kernel<<<N, kRunThreads, 0, s>>>(p);
+      OCRPP_LAUNCHED();
+    }
   }
   {
     constexpr int kGroups = kGeoThreads / kGrp;
@@ -1457,6 +1463,7 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
   cudaStream_t s = (cudaStream_t)stream;
 
   OCRPP_CUDA(cudaMemsetAsync(p.nruns, 0, sizeof(int32_t) * 5 * N, s));
+  if (labels_dbg_dev) OCRPP_CUDA(cudaMemsetAsync(labels_dbg_dev, 0, sizeof(int32_t) * (size_t)N * H * W, s));
   // Large batches run as 2 or 4 independent sub-batch pipelines on separate streams: the bandwidth-bound
   // scan of one sub-batch overlaps the ALU-bound geometry of another. (Not while per-phase profiling is
   // on: the event marks describe one whole-batch chain.)
@@ -1486,11 +1493,6 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
     p.n0 = 0;
     const int rc = db_pipeline(p, N, dtype, s, &prof);
     if (rc != OCRPP_OK) return rc;
-  }
-  if (labels_dbg_dev) {
-    OCRPP_CUDA(cudaMemsetAsync(labels_dbg_dev, 0, sizeof(int32_t) * (size_t)N * H * W, s));
-    db_labels_kernel<<<N, kRunThreads, 0, s>>>(p);
-    OCRPP_LAUNCHED();
   }
   return OCRPP_OK;
 }

@@ -104,6 +104,48 @@ def tie_alternatives(d):
     return outs if len(outs) > 1 else []
 
 
+def encloses_minimally(rect, pts, rel=2e-3, tol=2e-3):
+    """True when the rectangle `rect` (float [4,2], corners in order) contains every point of `pts` (distance to each
+    edge line >= -tol) and its area is within `rel` of the minimum-area enclosing rectangle of `pts`."""
+    import cv2
+    rect = np.asarray(rect, np.float64)
+    pts = np.asarray(pts, np.float64).reshape(-1, 2)
+    e0, e1 = rect[1] - rect[0], rect[2] - rect[1]
+    l0, l1 = np.linalg.norm(e0), np.linalg.norm(e1)
+    if l0 < 1e-9 or l1 < 1e-9:
+        return False
+    if abs(e0 @ e1) > 1e-3 * l0 * l1 + 1e-6:           # not a rectangle
+        return False
+    s = (pts - rect[0]) @ (e0 / l0)
+    t = (pts - rect[0]) @ (e1 / l1)
+    inside = s.min() >= -tol and s.max() <= l0 + tol and t.min() >= -tol and t.max() <= l1 + tol
+    (_, (w, h), _) = cv2.minAreaRect(pts.astype(np.float32))
+    return bool(inside and l0 * l1 <= w * h * (1 + rel) + 0.05)
+
+
+def near_tie_valid(d, gpu_box_f):
+    """The GPU box (pre-rounding corners in source-image coordinates) is what the reference's remaining steps make of
+    SOME near-minimal rectangle of the oracle's contour: for every edge-aligned rectangle of the contour within 1e-3
+    of the minimal area, run the oracle's unclip on its mini box and require the GPU box, mapped back to map pixels,
+    to enclose that offset polygon with (nearly) its minimal area."""
+    from oracle import db_oracle as O
+    if "contour" not in d:
+        return False
+    width, height, src_w, src_h = d["scale"]
+    g = np.asarray(gpu_box_f, np.float64) * np.array([width / float(src_w), height / float(src_h)])
+    py = d.get("semantics") == "python"
+    for c1 in G.tied_min_area_rects(d["contour"], rel=1e-3, corners=True):
+        a = sorted(np.asarray(c1, np.float32).tolist(), key=lambda q: q[0])
+        i2, i3 = (a[3], a[2]) if a[3][1] <= a[2][1] else (a[2], a[3])
+        i1, i4 = (a[1], a[0]) if a[1][1] <= a[0][1] else (a[0], a[1])
+        mini = np.array([i1, i2, i3, i4], np.float32)
+        soln = (O.unclip_py(mini, d["unclip_ratio"]) if py else O.unclip(mini, d["unclip_ratio"]))[3]
+        pts = [q for path in soln for q in path]
+        if len(pts) >= 3 and encloses_minimally(g, pts):
+            return True
+    return False
+
+
 def compare_image(boxes, boxes_f, scores, details, tol_px=1e-3, tol_score=1e-5):
     """boxes int16 [K,4,2], boxes_f float32 [K,4,2], scores [K] from the GPU; details from
     oracle.db_oracle.boxes_from_bitmap(return_details=True).
@@ -152,10 +194,9 @@ def compare_image(boxes, boxes_f, scores, details, tol_px=1e-3, tol_score=1e-5):
             # tied minimal rectangles
             stats["tie"] += 1
         else:
-            # different rectangle of the same area around the same points: equal-area tie
-            def area(b):
-                return np.linalg.norm(b[1] - b[0]) * np.linalg.norm(b[2] - b[1])
-            assert abs(area(of[i]) - area(gf[j])) <= 2e-3 * area(of[i]) + 0.6, ("box mismatch", dd, d["out_f"], gf[j].tolist(), d["mini"])
+            # a different rectangle: only acceptable as a near-tie below cv2's float32 resolution, and then it must be
+            # a VALID answer - enclose the points it is the minimal rectangle of and have (nearly) their minimal area
+            assert near_tie_valid(d, gf[j]), ("box mismatch", dd, d["out_f"], gf[j].tolist(), d["mini"])
             stats["tie"] += 1
     # an oracle box without a GPU box within 2.5 px: a verified equal-area tie can move the box further than that
     if stats["unmatched_oracle"]:

@@ -54,9 +54,10 @@ def compare_image(boxes, boxes_f, scores, want, shape, tol_px=1e-3, tol_score=1e
             assert _set_dist(of, gf) <= 0.75 * max(d["rect"][1]) + 1.5, ("tiny box far off", of, gf, d["rect"])
             stats["tiny"] = stats.get("tiny", 0) + 1
         else:
-            def area(b):
-                return np.linalg.norm(b[1] - b[0]) * np.linalg.norm(b[2] - b[1])
-            assert abs(area(of) - area(gf)) <= 2e-3 * area(of) + 0.6, ("box mismatch", of, gf)
+            # a different rectangle: acceptable only as a near-tie below cv2's float32 resolution, and then it must be a
+            # valid answer - enclose the label's hull and have (nearly) its minimal area
+            from db_compare import encloses_minimally
+            assert encloses_minimally(gf * ratio, d["hull"]), ("box mismatch", of, gf)
             stats["tie"] += 1
     return stats
 
