@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libocrpp.so")
 OK = 0
 F32, F16 = 0, 1
 IMG_RUN_OVERFLOW, IMG_CANDIDATES_TRUNCATED, IMG_VALUE_OUT_OF_RANGE = 1, 2, 4
-TUNE_DB_PATH, TUNE_DB_SPLIT = 0, 1
+TUNE_DB_PATH, TUNE_DB_SPLIT, TUNE_DB_PRIO, TUNE_DB_SCAN = 0, 1, 2, 3
 
 _lib = None
 

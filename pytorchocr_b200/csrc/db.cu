@@ -331,6 +331,160 @@ __global__ void __launch_bounds__(kBinWarps * 32) db_rawbits_kernel(DbParams p) 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1': the same pass as db_scan_kernel with the per-run bookkeeping moved off the streaming loop (what the
+// one-kernel-per-image stage takes: it does not need the bit mask in global memory).
+//   phase 1 (streaming, per group of 32*kEpl pixels): load, fixed-point conversion, range check, kEpl ballots;
+//     the pixel values, the sum of every lane's cell of kEpl pixels and the ballot words go to the warp's slice of
+//     shared memory - no run logic, no warp reductions: ~26 instructions per group;
+//   phase 2 (once per row): every lane takes C CONSECUTIVE cells (a contiguous chunk of the row). The bits of its
+//     chunk are C-bit fields of the ballot words, so ALL transitions inside the chunk come from kEpl XORs; two warp
+//     scans (transition counts, chunk sums) give every lane its first output slot and the row's cumulative sum
+//     at its first pixel; only lanes that own a transition go to shared memory again for the values inside the cell.
+// Same output as db_scan_kernel: per row the run starts `x << 48 | cumulative sum before x`, the run count and the
+// polarity of the first run. About 450 instead of 915 warp instructions per 1280-pixel row.
+// ------------------------------------------------------------------------------------------------
+constexpr int kScan2Warps = 8;
+
+__host__ __device__ inline int scan2_row_words(int C, int epl) { return (32 * C * epl + 32 * C + (C + 1) * epl + 3) & ~3; }
+
+template <typename T, int kEpl>
+__global__ void __launch_bounds__(kScan2Warps * 32) db_scan2_kernel(DbParams p, int C) {
+  extern __shared__ __align__(16) uint32_t s_scan[];
+  const int n = blockIdx.y + p.n0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int y = blockIdx.x * kScan2Warps + warp;
+  if (y >= p.H) return;
+  const int W = p.W;
+  const int ncells = W / kEpl;               // the vector path requires W % kEpl == 0
+  uint32_t* uval = s_scan + (size_t)warp * scan2_row_words(C, kEpl);   // [32*C*kEpl] pixel values, 2^-23 units
+  uint32_t* csum = uval + 32 * C * kEpl;                               // [32*C] cell sums, later prefixes
+  uint32_t* bits = csum + 32 * C;                                      // [(C+1)*kEpl] ballot words, g-major
+  const T* row = reinterpret_cast<const T*>(p.maps) + n * p.stride_n + y * p.stride_h;
+  const size_t rowid = (size_t)n * p.H + y;
+  unsigned long long* sc = p.scum + rowid * (p.cap + 1);
+  unsigned worst = 0;
+
+  // ---- phase 1 ----
+  constexpr int U = 5;   // groups per step, all loads issued up front
+  if (lane < kEpl) bits[C * kEpl + lane] = 0u;
+  for (int g0 = 0; g0 < C; g0 += U) {
+    float v[U][kEpl];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int x = ((g0 + u) * 32 + lane) * kEpl;
+      RowLoader<T, kEpl>::load(row, x, (g0 + u) < C ? W : 0, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int g = g0 + u;
+      if (g < C) {
+        const int c = g * 32 + lane;
+        const bool valid = c < ncells;
+        unsigned uu[kEpl], m[kEpl], run = 0;
+#pragma unroll
+        for (int k = 0; k < kEpl; ++k) {
+          const float f = v[u][k];
+          m[k] = __ballot_sync(0xffffffffu, valid && f > p.thresh);
+          // f in [0,1]: the mantissa of f + 1.0f is round(f * 2^23); anything else (negative, > 1, NaN, Inf)
+          // gives a value > 2^23 and is reported through `worst`
+          unsigned q = __float_as_uint(f + 1.0f) - 0x3f800000u;
+          q = valid ? q : 0u;
+          worst = max(worst, q);
+          run += q;
+          uu[k] = q;
+        }
+        if (kEpl == 4) {
+          *reinterpret_cast<uint4*>(uval + c * 4) = make_uint4(uu[0], uu[1 % kEpl], uu[2 % kEpl], uu[3 % kEpl]);
+          if (lane == 0) *reinterpret_cast<uint4*>(bits + g * 4) = make_uint4(m[0], m[1 % kEpl], m[2 % kEpl], m[3 % kEpl]);
+        } else {
+          *reinterpret_cast<uint4*>(uval + c * 8) = make_uint4(uu[0], uu[1 % kEpl], uu[2 % kEpl], uu[3 % kEpl]);
+          *reinterpret_cast<uint4*>(uval + c * 8 + 4) = make_uint4(uu[4 % kEpl], uu[5 % kEpl], uu[6 % kEpl], uu[7 % kEpl]);
+          if (lane == 0) {
+            *reinterpret_cast<uint4*>(bits + g * 8) = make_uint4(m[0], m[1 % kEpl], m[2 % kEpl], m[3 % kEpl]);
+            *reinterpret_cast<uint4*>(bits + g * 8 + 4) = make_uint4(m[4 % kEpl], m[5 % kEpl], m[6 % kEpl], m[7 % kEpl]);
+          }
+        }
+        csum[c] = run;
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- phase 2: lane owns cells [c0, c0 + C), pixels [c0 * kEpl, ...) ----
+  const int c0 = C * lane;
+  const int nv = max(0, min(C, ncells - c0));                 // valid cells of the chunk
+  const unsigned vmask = nv >= 32 ? 0xffffffffu : ((1u << nv) - 1u);
+  unsigned F[kEpl], Tm[kEpl];
+  {
+    const int w0 = c0 >> 5, sh = c0 & 31;
+#pragma unroll
+    for (int k = 0; k < kEpl; ++k)
+      F[k] = __funnelshift_r(bits[w0 * kEpl + k], bits[(w0 + 1) * kEpl + k], sh) & vmask;
+  }
+  // bit of the pixel just before the chunk (the previous lane's last valid pixel; pixel 0 has none)
+  const unsigned mylast = nv > 0 ? (F[kEpl - 1] >> (nv - 1)) & 1u : 0u;
+  unsigned prevbit = __shfl_up_sync(0xffffffffu, mylast, 1);
+  if (lane == 0) prevbit = F[0] & 1u;
+  int cnt_l = 0;
+  unsigned cellmask = 0;
+#pragma unroll
+  for (int k = 0; k < kEpl; ++k) {
+    const unsigned prev = k == 0 ? ((F[kEpl - 1] << 1) | prevbit) : F[k - 1];
+    Tm[k] = (F[k] ^ prev) & vmask;
+    cnt_l += __popc(Tm[k]);
+    cellmask |= Tm[k];
+  }
+  // chunk-local exclusive prefix of the cell sums, in place
+  unsigned acc = 0;
+  for (int i = 0; i < C; ++i) {
+    const unsigned t = csum[c0 + i];
+    csum[c0 + i] = acc;
+    acc += t;
+  }
+  // warp scans: transitions before this lane, sum of the row before this lane's first pixel
+  int pos = cnt_l;
+  unsigned long long base = acc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int tp = __shfl_up_sync(0xffffffffu, pos, o);
+    const unsigned long long tb = __shfl_up_sync(0xffffffffu, base, o);
+    if (lane >= o) {
+      pos += tp;
+      base += tb;
+    }
+  }
+  const int total_cnt = __shfl_sync(0xffffffffu, pos, 31) + 1;          // run 0 starts at x = 0
+  const unsigned long long total_sum = __shfl_sync(0xffffffffu, base, 31);
+  pos -= cnt_l;     // exclusive
+  base -= acc;
+  // emission: cells of this chunk that hold a transition
+  for (unsigned rest = cellmask; rest; rest &= rest - 1) {
+    const int i = __ffs(rest) - 1;
+    const unsigned below = (1u << i) - 1u;
+    int j = 1 + pos;
+#pragma unroll
+    for (int k = 0; k < kEpl; ++k) j += __popc(Tm[k] & below);
+    const unsigned long long cb = base + csum[c0 + i];
+    const uint32_t* uv = uval + (size_t)(c0 + i) * kEpl;
+    unsigned within = 0;
+#pragma unroll
+    for (int k = 0; k < kEpl; ++k) {
+      if ((Tm[k] >> i) & 1u) {
+        if (j < p.cap) sc[j] = ((unsigned long long)((c0 + i) * kEpl + k) << 48) | (cb + within);
+        ++j;
+      }
+      within += uv[k];
+    }
+  }
+  if (lane == 0) {
+    sc[0] = 0ull;   // run 0: x = 0, nothing before it
+    p.srow_cnt[rowid] = total_cnt | ((F[0] & 1u) << 31);
+    if (total_cnt <= p.cap) sc[total_cnt] = total_sum;
+  }
+  if (__any_sync(0xffffffffu, worst > 0x800000u) && lane == 0) atomicOr(&p.imgflags[n], OCRPP_IMG_VALUE_OUT_OF_RANGE);
+}
+
 // pixel (x,y) of the lane-major bit mask written by db_scan_kernel
 struct BitView {
   const uint32_t* bits;
@@ -1268,12 +1422,16 @@ int resolve_max_runs(int H, int W, int max_runs) {
 
 constexpr int kImgSmemMax = 225 * 1024;   // dynamic shared memory of db_image_kernel (227 KB per CTA minus static)
 
-// auxiliary stream / events of the current device (created once, never destroyed)
-constexpr int kDbAuxStreams = 3;
+// auxiliary streams / events of the current device (created once, never destroyed). Every sub-batch pipeline has a
+// LOW-priority stream for its map scan and a HIGH-priority stream for everything after it: the block scheduler
+// then places the (few, latency-bound) stage-2 / geometry CTAs of sub-batch i as soon as SM resources free up,
+// instead of queueing them behind the thousands of scan CTAs of sub-batches i+1.. that are already pending.
+constexpr int kDbMaxSplit = 8;
 struct DbAux {
-  cudaStream_t st[kDbAuxStreams];
-  cudaEvent_t fork, join[kDbAuxStreams];
+  cudaStream_t lo[kDbMaxSplit], hi[kDbMaxSplit];
+  cudaEvent_t fork, scanned[kDbMaxSplit], join[kDbMaxSplit];
 };
+std::mutex g_db_enqueue_mu;   // the auxiliary streams/events are shared: one fork/join section at a time
 
 DbAux* db_aux() {
   static std::mutex mu;   // first use may come from several host threads
@@ -1283,8 +1441,12 @@ DbAux* db_aux() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   if (!ready[dev]) {
-    for (int i = 0; i < kDbAuxStreams; ++i) {
-      if (cudaStreamCreateWithFlags(&aux[dev].st[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return nullptr;
+    for (int i = 0; i < kDbMaxSplit; ++i) {
+      if (cudaStreamCreateWithPriority(&aux[dev].lo[i], cudaStreamNonBlocking, least) != cudaSuccess) return nullptr;
+      if (cudaStreamCreateWithPriority(&aux[dev].hi[i], cudaStreamNonBlocking, greatest) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&aux[dev].scanned[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
       if (cudaEventCreateWithFlags(&aux[dev].join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     }
     if (cudaEventCreateWithFlags(&aux[dev].fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -1293,48 +1455,69 @@ DbAux* db_aux() {
   return &aux[dev];
 }
 
-// the whole chain for images [p.n0, p.n0 + N) on stream s
-int db_pipeline(DbParams p, int N, int dtype, cudaStream_t s, ProfileScope* prof) {
+// the whole chain for images [p.n0, p.n0 + N): the map scan on stream s_scan, everything after it on stream s
+// (when they differ, `scanned` orders the two)
+int db_pipeline(DbParams p, int N, int dtype, cudaStream_t s_scan, cudaStream_t s, cudaEvent_t scanned,
+                ProfileScope* prof) {
   const int epl = dtype == OCRPP_F32 ? 4 : 8;
   const bool vec = ((uintptr_t)p.maps % 16 == 0) && (p.stride_n % epl == 0) && (p.stride_h % epl == 0) && (p.W % epl == 0);
-  {
-    dim3 grid((p.H + kBinWarps - 1) / kBinWarps, N);
-    p.epl = vec ? epl : 1;
-    if (p.dilate) {
-      if (dtype == OCRPP_F32) {
-        if (vec) db_rawbits_kernel<float, 4><<<grid, kBinWarps * 32, 0, s>>>(p);
-        else db_rawbits_kernel<float, 1><<<grid, kBinWarps * 32, 0, s>>>(p);
-      } else {
-        if (vec) db_rawbits_kernel<__half, 8><<<grid, kBinWarps * 32, 0, s>>>(p);
-        else db_rawbits_kernel<__half, 1><<<grid, kBinWarps * 32, 0, s>>>(p);
-      }
-      OCRPP_LAUNCHED();
-      if (dtype == OCRPP_F32) {
-        if (vec) db_scan_kernel<float, 4, 4, true><<<grid, kBinWarps * 32, 0, s>>>(p);
-        else db_scan_kernel<float, 1, 4, true><<<grid, kBinWarps * 32, 0, s>>>(p);
-      } else {
-        if (vec) db_scan_kernel<__half, 8, 4, true><<<grid, kBinWarps * 32, 0, s>>>(p);
-        else db_scan_kernel<__half, 1, 4, true><<<grid, kBinWarps * 32, 0, s>>>(p);
-      }
-    } else if (dtype == OCRPP_F32) {
-      // the tail loop (one group per iteration, its load latency exposed) costs ~15 % on short rows
-      const int ng = p.W % 128 == 0 ? p.W / 128 : 0;   // whole groups per row: pick U so that no tail loop is left
-      if (vec && ng > 0 && ng % 5 == 0) db_scan_kernel<float, 4, 5><<<grid, kBinWarps * 32, 0, s>>>(p);
-      else if (vec && ng > 0 && ng % 4 != 0 && ng % 3 == 0) db_scan_kernel<float, 4, 3><<<grid, kBinWarps * 32, 0, s>>>(p);
-      else if (vec) db_scan_kernel<float, 4><<<grid, kBinWarps * 32, 0, s>>>(p);
-      else db_scan_kernel<float, 1><<<grid, kBinWarps * 32, 0, s>>>(p);
-    } else {
-      if (vec) db_scan_kernel<__half, 8><<<grid, kBinWarps * 32, 0, s>>>(p);
-      else db_scan_kernel<__half, 1><<<grid, kBinWarps * 32, 0, s>>>(p);
-    }
-    OCRPP_LAUNCHED();
-    if (prof) prof->mark("db_scan");
-  }
   // Stage 2. Default: ONE kernel, one CTA per image, tables in shared memory (db_image.cuh). Large images
   // (many rows / pixels: a single CTA per image would be the bottleneck) and the test hook take the run-parallel
   // multi-kernel chain, which spreads every image over several CTAs with its tables in the global workspace.
   const int path = tuning(OCRPP_TUNE_DB_PATH);
   const bool fused = path != 3 && p.H <= 8191 && (long long)p.H * p.W <= (4ll << 20);
+  // the two-phase scan: needs the vector layout, no dilation, a consumer that does not read the global bit mask
+  // (the one-kernel stage 2) and a row that fits the warp's shared-memory slice
+  const int scan2_C = (p.W / epl + 31) / 32;
+  const bool scan2 = fused && vec && !p.dilate && scan2_C <= 32 && tuning(OCRPP_TUNE_DB_SCAN) != 1 &&
+                     kScan2Warps * scan2_row_words(scan2_C, epl) * sizeof(uint32_t) <= 100 * 1024;
+  {
+    dim3 grid((p.H + kBinWarps - 1) / kBinWarps, N);
+    p.epl = vec ? epl : 1;
+    if (p.dilate) {
+      if (dtype == OCRPP_F32) {
+        if (vec) db_rawbits_kernel<float, 4><<<grid, kBinWarps * 32, 0, s_scan>>>(p);
+        else db_rawbits_kernel<float, 1><<<grid, kBinWarps * 32, 0, s_scan>>>(p);
+      } else {
+        if (vec) db_rawbits_kernel<__half, 8><<<grid, kBinWarps * 32, 0, s_scan>>>(p);
+        else db_rawbits_kernel<__half, 1><<<grid, kBinWarps * 32, 0, s_scan>>>(p);
+      }
+      OCRPP_LAUNCHED();
+      if (dtype == OCRPP_F32) {
+        if (vec) db_scan_kernel<float, 4, 4, true><<<grid, kBinWarps * 32, 0, s_scan>>>(p);
+        else db_scan_kernel<float, 1, 4, true><<<grid, kBinWarps * 32, 0, s_scan>>>(p);
+      } else {
+        if (vec) db_scan_kernel<__half, 8, 4, true><<<grid, kBinWarps * 32, 0, s_scan>>>(p);
+        else db_scan_kernel<__half, 1, 4, true><<<grid, kBinWarps * 32, 0, s_scan>>>(p);
+      }
+    } else if (scan2) {
+      const int smem = kScan2Warps * scan2_row_words(scan2_C, epl) * (int)sizeof(uint32_t);
+      dim3 grid2((p.H + kScan2Warps - 1) / kScan2Warps, N);
+      if (dtype == OCRPP_F32) {
+        OCRPP_CUDA(cudaFuncSetAttribute(db_scan2_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        db_scan2_kernel<float, 4><<<grid2, kScan2Warps * 32, smem, s_scan>>>(p, scan2_C);
+      } else {
+        OCRPP_CUDA(cudaFuncSetAttribute(db_scan2_kernel<__half, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        db_scan2_kernel<__half, 8><<<grid2, kScan2Warps * 32, smem, s_scan>>>(p, scan2_C);
+      }
+    } else if (dtype == OCRPP_F32) {
+      // the tail loop (one group per iteration, its load latency exposed) costs ~15 % on short rows
+      const int ng = p.W % 128 == 0 ? p.W / 128 : 0;   // whole groups per row: pick U so that no tail loop is left
+      if (vec && ng > 0 && ng % 5 == 0) db_scan_kernel<float, 4, 5><<<grid, kBinWarps * 32, 0, s_scan>>>(p);
+      else if (vec && ng > 0 && ng % 4 != 0 && ng % 3 == 0) db_scan_kernel<float, 4, 3><<<grid, kBinWarps * 32, 0, s_scan>>>(p);
+      else if (vec) db_scan_kernel<float, 4><<<grid, kBinWarps * 32, 0, s_scan>>>(p);
+      else db_scan_kernel<float, 1><<<grid, kBinWarps * 32, 0, s_scan>>>(p);
+    } else {
+      if (vec) db_scan_kernel<__half, 8><<<grid, kBinWarps * 32, 0, s_scan>>>(p);
+      else db_scan_kernel<__half, 1><<<grid, kBinWarps * 32, 0, s_scan>>>(p);
+    }
+    OCRPP_LAUNCHED();
+    if (prof) prof->mark("db_scan");
+    if (s_scan != s) {
+      OCRPP_CUDA(cudaEventRecord(scanned, s_scan));
+      OCRPP_CUDA(cudaStreamWaitEvent(s, scanned, 0));
+    }
+  }
   if (fused) {
     const size_t want = sizeof(int) * (p.H + 1) + 10 * (size_t)p.R + 68 * ((size_t)p.R / 4 + 64) +
                         8 * ((size_t)p.R + p.H) + 64;
@@ -1464,34 +1647,38 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
 
   OCRPP_CUDA(cudaMemsetAsync(p.nruns, 0, sizeof(int32_t) * 5 * N, s));
   if (labels_dbg_dev) OCRPP_CUDA(cudaMemsetAsync(labels_dbg_dev, 0, sizeof(int32_t) * (size_t)N * H * W, s));
-  // Large batches run as 2 or 4 independent sub-batch pipelines on separate streams: the bandwidth-bound
-  // scan of one sub-batch overlaps the ALU-bound geometry of another. (Not while per-phase profiling is
-  // on: the event marks describe one whole-batch chain.)
+  // Large batches run as independent sub-batch pipelines on separate streams: the issue-bound map scan of one
+  // sub-batch overlaps the latency-bound stage 2 and the ALU-bound geometry of another. (Not while per-phase
+  // profiling is on: the event marks describe one whole-batch chain.)
   int nsplit = N >= 192 ? 4 : (N >= 64 ? 2 : 1);
   const int forced = tuning(OCRPP_TUNE_DB_SPLIT);
-  if (forced > 0) nsplit = forced > kDbAuxStreams + 1 ? kDbAuxStreams + 1 : forced;
+  if (forced > 0) nsplit = forced > kDbMaxSplit ? kDbMaxSplit : forced;
   DbAux* aux = (nsplit > 1 && nsplit <= N && !profile_on()) ? db_aux() : nullptr;
   if (aux) {
-    static std::mutex enqueue_mu;   // the auxiliary streams/events are shared: one fork/join section at a time
-    std::lock_guard<std::mutex> lock(enqueue_mu);
+    const bool prio = tuning(OCRPP_TUNE_DB_PRIO) != 1;
+    std::lock_guard<std::mutex> lock(g_db_enqueue_mu);
     OCRPP_CUDA(cudaEventRecord(aux->fork, s));
+    int rc = OCRPP_OK;
     for (int i = 0; i < nsplit; ++i) {
-      cudaStream_t si = i == 0 ? s : aux->st[i - 1];
-      if (i > 0) OCRPP_CUDA(cudaStreamWaitEvent(si, aux->fork, 0));
+      cudaStream_t ss = aux->lo[i], sp = prio ? aux->hi[i] : aux->lo[i];
+      if (cudaStreamWaitEvent(ss, aux->fork, 0) != cudaSuccess) rc = set_error(OCRPP_ERR_CUDA, "db: cudaStreamWaitEvent failed");
       const int lo = (int)((long long)N * i / nsplit), hi = (int)((long long)N * (i + 1) / nsplit);
       p.n0 = lo;
-      const int rc = db_pipeline(p, hi - lo, dtype, si, nullptr);
-      if (rc != OCRPP_OK) return rc;
-      if (i > 0) {
-        OCRPP_CUDA(cudaEventRecord(aux->join[i - 1], si));
-        OCRPP_CUDA(cudaStreamWaitEvent(s, aux->join[i - 1], 0));
+      if (rc == OCRPP_OK) rc = db_pipeline(p, hi - lo, dtype, ss, sp, aux->scanned[i], nullptr);
+      // always join, also after a failed launch: the auxiliary streams may still touch the caller's buffers
+      cudaEventRecord(aux->join[i], sp);
+      cudaStreamWaitEvent(s, aux->join[i], 0);
+      if (sp != ss) {
+        cudaEventRecord(aux->scanned[i], ss);
+        cudaStreamWaitEvent(s, aux->scanned[i], 0);
       }
     }
     p.n0 = 0;
+    if (rc != OCRPP_OK) return rc;
   } else {
     ProfileScope prof(s);
     p.n0 = 0;
-    const int rc = db_pipeline(p, N, dtype, s, &prof);
+    const int rc = db_pipeline(p, N, dtype, s, s, nullptr, &prof);
     if (rc != OCRPP_OK) return rc;
   }
   return OCRPP_OK;

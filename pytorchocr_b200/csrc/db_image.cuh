@@ -639,15 +639,15 @@ __device__ bool db_image_run(const DbParams& p, const int n, char* smem, const s
   const int ntask = min(s_ntask, t.ntask_cap);
   constexpr int kU = 4;
   int2 tk[kU];
-  unsigned long long tv[kU];
+  float tv[kU];   // raw values: converting here would wait for the loads
 #pragma unroll
   for (int k = 0; k < kU; ++k) {
     const int i = tid + k * nt;
     tk[k] = make_int2(-1, 0);
-    tv[k] = 0ull;
+    tv[k] = 0.f;
     if (i < ntask) {
       tk[k] = t.tasks[i];
-      tv[k] = px(tk[k].y & 0xffff, (int)((unsigned)tk[k].y >> 16));
+      tv[k] = load_px<T>(p.maps, img + (long long)((unsigned)tk[k].y >> 16) * p.stride_h + (tk[k].y & 0xffff));
     }
   }
   __syncthreads();   // clist
@@ -739,7 +739,7 @@ __device__ bool db_image_run(const DbParams& p, const int n, char* smem, const s
       for (int q = 0; q < kU; ++q)
         if (tk[q].x >= 0) {
           atomicAdd(&t.ecnt[tk[q].x], 1);
-          add64<kSmem>(&t.esum[tk[q].x], tv[q]);
+          add64<kSmem>(&t.esum[tk[q].x], (unsigned long long)to_fixed(tv[q]));
         }
       for (int i = tid + kU * nt; i < ntask; i += nt) {
         const int2 e = t.tasks[i];

@@ -1,0 +1,5 @@
+set -x
+for k in db_geometry_kernel db_image_kernel db_scan_kernel; do
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip 2 -c 1 -f -o gpurun_out/r2_$k python tests/dev_db_image_clk.py 64 > gpurun_out/ncu_$k.log 2>&1
+done
+ls -la gpurun_out/*.ncu-rep
