@@ -1259,20 +1259,49 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
   }
   if (m == 0) return;  // empty solution -> RotatedRect((0,0),(1,1),0) -> dropped by the 1.001 test
   __syncwarp(gmask);
-  // rank sort by (y, x, index) into A: every lane ranks its own points against all of them
+  // rank sort by (y, x, index) into A: every lane ranks its own points against all of them (one packed key per point:
+  // coordinates are within +-16384 on this path)
   for (int i = gl; i < m; i += kGrp) {
     const P2i q = s_off[g][i];
+    const unsigned kq = ((unsigned)(q.y + 16384) << 16) | (unsigned)(q.x + 16384);
     int rank = 0;
     for (int j = 0; j < m; ++j) {
       const P2i o = s_off[g][j];
-      rank += (o.y < q.y || (o.y == q.y && (o.x < q.x || (o.x == q.x && j < i)))) ? 1 : 0;
+      const unsigned ko = ((unsigned)(o.y + 16384) << 16) | (unsigned)(o.x + 16384);
+      rank += (ko < kq || (ko == kq && j < i)) ? 1 : 0;
     }
     A[rank] = pk(q.x, q.y);
   }
   __syncwarp(gmask);
+  // monotone chain (same result as hull_sorted32): its two passes are independent - the second starts from the last
+  // point of the sorted list, which the first always ends on - so lanes 0 and 1 run them at the same time with ONE
+  // instruction stream (direction = lane): base point + a stack of the points pushed after it, popped while the
+  // turn is not strictly left. Lane 0's stack is B[1..], lane 1's goes to the (dead) raw polygon buffer.
   int hm = 0;
-  if (gl == 0) hm = hull_sorted32(A, m, B);
-  hm = __shfl_sync(gmask, hm, 0, kGrp);
+  {
+    int* S = gl == 0 ? B + 1 : reinterpret_cast<int*>(s_off[g]);
+    int cnt = 0;
+    if (gl < 2) {
+      const int dir = gl;
+      const int base = A[dir ? m - 1 : 0];
+      int prevq = base;
+      for (int step = 1; step < m; ++step) {
+        const int q = A[dir ? m - 1 - step : step];
+        if (q == prevq) continue;
+        prevq = q;
+        while (cnt >= 1 && cross32(cnt >= 2 ? S[cnt - 2] : base, S[cnt - 1], q) <= 0) --cnt;
+        S[cnt++] = q;
+      }
+      if (gl == 0) B[0] = base;
+    }
+    const int lane0 = (threadIdx.x & 31) & ~(kGrp - 1);
+    const int c1 = __shfl_sync(gmask, cnt, lane0), c2 = __shfl_sync(gmask, cnt, lane0 + 1);
+    const int k1 = 1 + c1;
+    hm = k1 > 1 ? k1 + c2 - 1 : 1;
+    __syncwarp(gmask);
+    const int* S2 = reinterpret_cast<const int*>(s_off[g]);
+    for (int j = gl; j < c2 - 1; j += kGrp) B[k1 + j] = S2[j];
+  }
   __syncwarp(gmask);
   geom::Rect rect2;
   group_min_area_rect(B, hm, &rect2, gl, gmask);
@@ -1466,10 +1495,11 @@ int db_pipeline(DbParams p, int N, int dtype, cudaStream_t s_scan, cudaStream_t 
   // multi-kernel chain, which spreads every image over several CTAs with its tables in the global workspace.
   const int path = tuning(OCRPP_TUNE_DB_PATH);
   const bool fused = path != 3 && p.H <= 8191 && (long long)p.H * p.W <= (4ll << 20);
-  // the two-phase scan: needs the vector layout, no dilation, a consumer that does not read the global bit mask
-  // (the one-kernel stage 2) and a row that fits the warp's shared-memory slice
+  // the two-phase scan (opt-in through the tuning hook: measured 5 % slower than the single-phase scan on B200, see
+  // DESIGN.md): needs the vector layout, no dilation, a consumer that does not read the global bit mask (the
+  // one-kernel stage 2) and a row that fits the warp's shared-memory slice
   const int scan2_C = (p.W / epl + 31) / 32;
-  const bool scan2 = fused && vec && !p.dilate && scan2_C <= 32 && tuning(OCRPP_TUNE_DB_SCAN) != 1 &&
+  const bool scan2 = fused && vec && !p.dilate && scan2_C <= 32 && tuning(OCRPP_TUNE_DB_SCAN) == 2 &&
                      kScan2Warps * scan2_row_words(scan2_C, epl) * sizeof(uint32_t) <= 100 * 1024;
   {
     dim3 grid((p.H + kBinWarps - 1) / kBinWarps, N);

@@ -558,11 +558,25 @@ __device__ bool db_image_run(const DbParams& p, const int n, char* smem, const s
     //     its up / left / right / down neighbours that lies in the hole - with their row extents, and (c) the stair
     //     pixels of the hole contour. One WARP per hole run: lanes take the pixels of the run (one thread walking a
     //     run alone would be the critical path of the whole image), lane 0 the two ends.
-    for (int w = warp; w < nwords; w += nw) {
+    // the hole runs are first collected in a list (they cluster in a few rows), then dealt to the warps in turn
+    int* hlist = reinterpret_cast<int*>(t.hcnt);   // [2*maxc] ints, not in use before stage G
+    const int hcap = 2 * p.maxc;
+    if (tid == 0) s_etot = 0;
+    __syncthreads();
+    for (int rr = tid; rr < nr; rr += nt) {
+      if (!(t.yf[rr] >> 15) && ~t.par[rr] != cout) {
+        const int slot = atomicAdd(&s_etot, 1);
+        if (slot < hcap) hlist[slot] = rr;
+      }
+    }
+    __syncthreads();
+    const int nhole = s_etot;
+    const bool listed = nhole <= hcap;
+    for (int w = warp; w < (listed ? nhole : nwords); w += nw) {
       const int rr = w * 32 + lane;
-      const bool hole = rr < nr && !(t.yf[rr] >> 15) && ~t.par[rr] != cout;
-      for (unsigned todo = __ballot_sync(0xffffffffu, hole); todo; todo &= todo - 1) {
-        const int r = w * 32 + __ffs(todo) - 1;
+      const bool hole = !listed && rr < nr && !(t.yf[rr] >> 15) && ~t.par[rr] != cout;
+      for (unsigned todo = listed ? 1u : __ballot_sync(0xffffffffu, hole); todo; todo &= todo - 1) {
+        const int r = listed ? hlist[w] : w * 32 + __ffs(todo) - 1;
         const int y = t.yf[r] & 0x7fff;
         const int a = t.xs[r], b = xe_of(r, t.rowptr[y + 1]);
         const int h = ~t.par[r];
@@ -735,6 +749,8 @@ __device__ bool db_image_run(const DbParams& p, const int n, char* smem, const s
     if (k < ncand) t.hcnt[side * p.maxc + k] = cntk;
     if (kb == 0) {
       // the pixels requested above have arrived by now; further ones (more than kU per thread) in the plain way
+#pragma unroll
+      for (int q = 0; q < kU; ++q) asm volatile("" : "+f"(tv[q]));   // keeps the conversion (= the wait) down here
 #pragma unroll
       for (int q = 0; q < kU; ++q)
         if (tk[q].x >= 0) {

@@ -15,17 +15,17 @@ pytestmark = pytest.mark.gpu
 CFG = dict(thresh=0.3, box_thresh=0.5, max_candidates=1000, unclip_ratio=1.7, score_mode="poly", cpp_speedup=True)
 
 
-@pytest.fixture(autouse=True, params=["image_smem", "image_global", "chain", "image_scan1"])
+@pytest.fixture(autouse=True, params=["image_smem", "image_global", "chain", "image_scan2"])
 def db_path(request):
     """Every test of this module runs on each of the library's three equivalent stage-2 code paths (include/ocrpp.h
     OCRPP_TUNE_DB_PATH): one CTA per image with the tables in shared memory (the default for maps up to 4 Mpx), the
     same kernel with the tables in the global workspace (what an image takes whose tables do not fit), and the
     run-parallel multi-kernel chain (what larger maps take). The first two run behind the two-phase map scan
-    (db_scan2_kernel) whenever the map layout allows it; "image_scan1" puts the single-phase scan in front instead."""
+    (db_scan2_kernel) whenever the map layout allows it; "image_scan2" puts the single-phase scan in front instead."""
     from pytorchocr_b200 import _lib
     L = _lib.lib()
-    _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_PATH, {"image_smem": 1, "image_global": 2, "chain": 3, "image_scan1": 1}[request.param]))
-    _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_SCAN, 1 if request.param == "image_scan1" else 0))
+    _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_PATH, {"image_smem": 1, "image_global": 2, "chain": 3, "image_scan2": 1}[request.param]))
+    _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_SCAN, 2 if request.param == "image_scan2" else 0))
     yield request.param
     _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_PATH, 0))
     _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_SCAN, 0))

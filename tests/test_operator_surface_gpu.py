@@ -140,8 +140,9 @@ def test_det_metric_handoff():
     gt = np.zeros((3, K, 4, 2), np.int16)
     ignore = np.ones((3, K), bool)
     for n, w in enumerate(want):
-        gt[n, :len(w["points"])] = w["points"]
-        ignore[n, :len(w["points"])] = False
+        if len(w["points"]):
+            gt[n, :len(w["points"])] = w["points"]
+            ignore[n, :len(w["points"])] = False
     batch = [None, None, gt, ignore]
     matched = n_gt = n_det = 0
     for pred, gt_polys, tags in zip(preds, batch[2], batch[3]):            # det_metric.py:24-36
