@@ -20,8 +20,8 @@ def db_path(request):
     """Every test of this module runs on each of the library's three equivalent stage-2 code paths (include/ocrpp.h
     OCRPP_TUNE_DB_PATH): one CTA per image with the tables in shared memory (the default for maps up to 4 Mpx), the
     same kernel with the tables in the global workspace (what an image takes whose tables do not fit), and the
-    run-parallel multi-kernel chain (what larger maps take). The first two run behind the two-phase map scan
-    (db_scan2_kernel) whenever the map layout allows it; "image_scan2" puts the single-phase scan in front instead."""
+    run-parallel multi-kernel chain (what larger maps take). "image_scan2" runs the first behind the
+    opt-in two-phase map scan (db_scan2_kernel) instead of the single-phase db_scan_kernel."""
     from pytorchocr_b200 import _lib
     L = _lib.lib()
     _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_PATH, {"image_smem": 1, "image_global": 2, "chain": 3, "image_scan2": 1}[request.param]))
