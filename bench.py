@@ -2,11 +2,14 @@
 """Benchmark of the post-processing hot path (contract: see DESIGN.md "Measurement").
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload db|pse|pan|ctc] [--batch B] [--no-cpu]
+                    [--workload db|pse|pan|ctc|crop|db_fp16|pse_api|pan_api] [--batch B] [--no-cpu] [--headline-only]
 
-A "step" is one pass of the hot path over one batch of synthetic input. The default workload is
+A "step" is one pass of the hot path over one batch of synthetic input. The headline workload is
 BASELINE.json configs[1]: DB++ r18 post-process, batch 256 synthetic 736x1280 maps (~200 text
-regions each) per GPU. The other workloads are BASELINE.json configs[2..4] (PSE, PAN, CTC).
+regions each) per GPU. The default run then also times BASELINE.json configs[2..4] (PSE batch 16, PAN batch 128,
+CTC 8192 lines per GPU), the two API-faithful twins (1/4-resolution head outputs through the operators' own
+up-sampling) and the fp16 DB variant for a few steps each and reports them under `other_workloads` on the same
+JSON line (same measurement rules; headline keys unchanged).
 Scaling is WEAK: every rank processes its own batch (the path shards by image / text line, no
 collective on the data path); `value` = units all ranks processed / max-over-ranks device time.
 Rank 0 prints ONE JSON line.
@@ -52,12 +55,20 @@ def _gen_pan_scene(seed):
     return synth.pan_scene(seed, H, W)[:4]
 
 
-def _cpu_db(m):
+_SHARED = {}    # arrays the CPU workers inherit through fork (nothing is pickled through the pool's pipes)
+
+
+def _cpu_db(i):
+    """The reference's CPU path for map i of the inherited batch: db_postprocess.py:43-46 (threshold, uint8 cast)
+    + BoxesFromBitmap (oracle/db_oracle_fast.py: the oracle's C++-branch semantics, vectorised between the same cv2 /
+    Clipper calls so that Python interpreter overhead is not billed to the reference)."""
     import cv2
     cv2.setNumThreads(1)
-    from oracle.db_oracle import DBPostProcessOracle
-    r = DBPostProcessOracle(**DB_CFG)({"maps": m[None, None]}, [[H, W, 1.0, 1.0]])
-    return len(r[0]["points"])
+    from oracle import db_oracle_fast
+    m = _SHARED["db_maps"][i, 0]
+    boxes = db_oracle_fast.boxes_from_bitmap(m, (m > DB_CFG["thresh"]).astype(np.uint8), DB_CFG["box_thresh"],
+                                             DB_CFG["unclip_ratio"], W, H)
+    return len(boxes)
 
 
 def _cpu_pse(seed):
@@ -112,7 +123,7 @@ def _cpu_crop(page):
 
 
 def _timed_pool(pool, fn, items, cores):
-    """Runs fn over items on the pool; returns (units per second of wall time, n, seconds)."""
+    """Runs fn over items on the pool; returns (outputs, seconds of wall time)."""
     pool.map(fn, items[:cores])  # warm the workers (imports, page-in)
     t0 = time.perf_counter()
     out = pool.map(fn, items, chunksize=1)
@@ -120,31 +131,81 @@ def _timed_pool(pool, fn, items, cores):
     return out, dt
 
 
+def _cpu_db_batch(maps, cores, passes=1):
+    """Times the CPU path over `maps` ([B,1,H,W] float32): a fresh fork pool inherits the array; >= 8 tasks per
+    worker at B = 256 on 32 cores. Returns (maps per second, boxes found, seconds)."""
+    import multiprocessing as mp
+    _SHARED["db_maps"] = maps
+    idx = list(range(len(maps)))
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_cpu_db, idx[:cores])
+        t0 = time.perf_counter()
+        for _ in range(passes):
+            out = pool.map(_cpu_db, idx, chunksize=1)
+        dt = time.perf_counter() - t0
+    return len(maps) * passes / dt, int(sum(out)), dt
+
+
 # ----------------------------------------------------------------------------------------------
 # clocks
 # ----------------------------------------------------------------------------------------------
 class ClockSampler(object):
+    """SM clock and throttle reasons of one GPU, sampled DURING the timed regions. Reads NVML in-process
+    (nvidia_ml_py; ~50 us per sample, no fork): forking `nvidia-smi` every 100 ms from every rank inside a 15 ms
+    event-timed window was the source of the per-rank jitter of the round-1 scaling run. Falls back to
+    `nvidia-smi` when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.samples = []
+        self.samples = []      # (sm_mhz, sm_max_mhz, set of reasons)
         self._stop = threading.Event()
         self._t = None
+        self.how = "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[gpu_index]) if visible and visible.split(",")[gpu_index].isdigit() else gpu_index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nv = pynvml
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+            self.how = "nvidia-smi"
+
+    def _sample_nvml(self):
+        nv = self._nv
+        sm = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        names = set()
+        for nm, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+                        ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                names.add(nm)
+        self.samples.append((sm, self._max, names))
+
+    def _sample_smi(self):
+        out = subprocess.check_output(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits"], timeout=5).decode().strip()
+        f = [x.strip() for x in out.split(",")]
+        names = {nm for nm, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9])
+                 if v.lower().startswith("active")}
+        self.samples.append((float(f[1]), float(f[2]), names))
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.check_output(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                               "--format=csv,noheader,nounits"], timeout=5).decode().strip()
-                self.samples.append([x.strip() for x in out.split(",")])
+                (self._sample_nvml if self._nv else self._sample_smi)()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02 if self._nv else 0.25)
 
     def start(self):
+        self._stop.clear()
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
 
@@ -154,21 +215,13 @@ class ClockSampler(object):
             self._t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for s in self.samples:
-            try:
-                sm.append(float(s[1]))
-                mx.append(float(s[2]))
-                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-                for nm, v in zip(names, s[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        if not sm:
+        if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        reasons = set()
+        for smp in self.samples:
+            reasons |= smp[2]
+        return {"sm_mhz": float(np.median([x[0] for x in self.samples])), "sm_max_mhz": float(max(x[1] for x in self.samples)),
+                "reasons": sorted(reasons), "samples": len(self.samples), "how": self.how}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -187,9 +240,19 @@ class Workload(object):
         self.batch = args.batch or self.default_batch
         self.cores = max(1, (os.cpu_count() or 1) // max(1, world))
 
-    # per-unit algorithmic bytes: the operator input at processing resolution read once
+    # per-unit algorithmic bytes: the operator input read once
     def alg_bytes_per_unit(self):
         raise NotImplementedError
+
+    def needs_flush(self):
+        return False
+
+    def release(self):
+        for k in list(vars(self)):
+            if k not in ("args", "rank", "world", "batch", "cores"):
+                delattr(self, k)
+        import torch
+        torch.cuda.empty_cache()
 
 
 class DetWorkload(Workload):
@@ -197,9 +260,11 @@ class DetWorkload(Workload):
     channels = 1
     op_name = None
     cfg = None
+    in_h, in_w = H, W          # resolution of the operator input (the API-faithful twins feed 1/4-resolution maps)
+    elem_bytes = 4
 
     def alg_bytes_per_unit(self):
-        return self.channels * H * W * 4
+        return self.channels * self.in_h * self.in_w * self.elem_bytes
 
     def device_prepare(self, dev):
         import torch
@@ -207,7 +272,7 @@ class DetWorkload(Workload):
         self.torch, self.dev = torch, dev
         self.op = build_post_process(dict(self.cfg, name=self.op_name, cuda_speedup=True, **self.extra_cfg()))
         self.dev_maps = self.make_device_maps(dev)
-        self.host_maps = torch.empty(self.dev_maps.shape, dtype=torch.float32, pin_memory=True)
+        self.host_maps = torch.empty(self.dev_maps.shape, dtype=self.dev_maps.dtype, pin_memory=True)
         self.host_maps.copy_(self.dev_maps)
         self.shape_list = np.array([[H, W, 1.0, 1.0]] * self.batch, np.float64)
         res = self.op({"maps": self.dev_maps}, self.shape_list)   # allocates/caches buffers, settles capacities
@@ -223,16 +288,25 @@ class DetWorkload(Workload):
         return self.op({"maps": d}, self.shape_list)             # kernels + D2H of boxes/counts + host assembly
 
     def h2d_bytes(self):
-        return int(self.host_maps.numel() * 4 + self.shape_list.size * 8)
+        return int(self.host_maps.numel() * self.host_maps.element_size() + self.shape_list.size * 8)
+
 
     def d2h_bytes(self):
         return int(self.buf["out_host"].numel())
 
     def config(self):
-        return {"batch_per_gpu": self.batch, "H": H, "W": W, "boxes_per_step_rank0": self.n_boxes,
-                "l2": "inputs (%.0f MB per GPU) larger than the 126 MB L2; no flush needed"
-                      % (self.batch * self.alg_bytes_per_unit() / 1e6),
+        return {"batch_per_gpu": self.batch, "H": H, "W": W, "input": list(self.dev_maps.shape[1:]) + [str(self.dev_maps.dtype)],
+                "boxes_per_step_rank0": self.n_boxes, "l2": self.l2_note(),
                 "timed_region": "device maps -> boxes/scores/counts in pinned host memory"}
+
+    def l2_note(self):
+        mb = self.batch * self.alg_bytes_per_unit() / 1e6
+        if mb > 2 * 126:
+            return "inputs (%.0f MB per GPU) larger than the 126 MB L2; no flush needed" % mb
+        return "inputs are %.0f MB per GPU: a 512 MB buffer is overwritten between timed steps to flush the L2" % mb
+
+    def needs_flush(self):
+        return self.batch * self.alg_bytes_per_unit() <= 2 * 126e6
 
 
 class DbWorkload(DetWorkload):
@@ -243,22 +317,25 @@ class DbWorkload(DetWorkload):
     stream_kernel = "db_scan_kernel"
     workload = ("DB++ r18 post-process, batch 256 synthetic 736x1280 maps with ~200 text regions each per GPU "
                 "(BASELINE.json configs[1])")
-    cpu_note = ("oracle/db_oracle.py (cv2-python restatement of db_postprocess.cpp + the reference's own "
-                "Clipper): the C++ module needs OpenCV C++ and cannot be built here")
+    cpu_note = ("oracle/db_oracle_fast.py = the oracle's db_postprocess.cpp semantics (cv2-python 4.13 + the reference's "
+                "own compiled Clipper) with the arithmetic between the cv2 calls vectorised per image; the C++ module "
+                "itself needs OpenCV C++ and cannot be built here")
+    map_dtype = "float32"
 
     def host_prepare(self, pool, want_cpu):
         maps = pool.map(_gen_db, [SEED + self.rank * self.batch + i for i in range(self.batch)], chunksize=4)
         self.maps = np.stack(maps)[:, None]
         if not want_cpu:
             return None
-        imgs = [self.maps[i, 0] for i in range(self.batch)]
-        _, dt = _timed_pool(pool, _cpu_db, imgs, self.cores)
-        return {"value": len(imgs) / dt, "unit": self.unit, "cores": self.cores, "kind": "port",
-                "sample": "%d of this step's 736x1280 maps in %.1f s, multiprocessing.Pool(%d), cv2.setNumThreads(1); %s"
-                          % (len(imgs), dt, self.cores, self.cpu_note)}
+        rate, nboxes, dt = _cpu_db_batch(self.maps, self.cores)
+        return {"value": rate, "unit": self.unit, "cores": self.cores, "kind": "port",
+                "sample": "all %d maps of this step (the ones the GPU arm processes; %d boxes) in %.1f s, fork pool of %d "
+                          "workers inheriting the array, cv2.setNumThreads(1); %s"
+                          % (len(self.maps), nboxes, dt, self.cores, self.cpu_note)}
 
     def make_device_maps(self, dev):
-        return self.torch.from_numpy(self.maps).pin_memory().to(dev)
+        t = self.torch.from_numpy(self.maps).pin_memory().to(dev)
+        return t.half() if self.map_dtype == "float16" else t
 
     def e2e_step(self):
         # the operator takes the pinned HOST maps (as the reference's operator takes `.cpu().numpy()` maps) and
@@ -271,11 +348,22 @@ class DbWorkload(DetWorkload):
         o_box, o_sc, o_cnt, o_st = buf["offs"]
         base = buf["out_dev"].data_ptr()
         _lib.check(L.ocrpp_db_postprocess(
-            m.data_ptr(), _lib.F32, self.batch, H, W, m.stride(0), m.stride(2), buf["wh_dev"].data_ptr(),
+            m.data_ptr(), _lib.F16 if self.map_dtype == "float16" else _lib.F32, self.batch, H, W, m.stride(0),
+            m.stride(2), buf["wh_dev"].data_ptr(),
             DB_CFG["thresh"], DB_CFG["box_thresh"], DB_CFG["unclip_ratio"], self.key[5], self.key[4], 0, 0,
             base + o_box, base + o_sc, base + o_cnt, base + o_st, None, None,
             buf["ws"].data_ptr(), buf["ws_bytes"], stream.cuda_stream))
         buf["out_host"].copy_(buf["out_dev"], non_blocking=True)
+
+
+class DbFp16Workload(DbWorkload):
+    name = "db_fp16"
+    dtype = "f16"
+    map_dtype = "float16"
+    elem_bytes = 2
+    stream_kernel = "db_scan_kernel<__half>"
+    workload = ("DB++ r18 post-process on fp16 probability maps (SURVEY 8(d) variant), batch 256 synthetic 736x1280 maps "
+                "per GPU")
 
 
 class ExpandWorkload(DetWorkload):
@@ -348,13 +436,63 @@ class PanWorkload(ExpandWorkload):
         return synth.pan_maps_torch(self.scenes, SEED + self.rank, dev)
 
     def alg_bytes_per_unit(self):
-        return 6 * H * W * 4
+        return 6 * self.in_h * self.in_w * 4
 
     def kernel_bytes_per_unit(self):
         # only the text and kernel channels are read unconditionally (the 4 embedding channels are
         # touched for flagged kernels only), so the streaming kernel is rated on the 2 channels it must read while
         # whole_step_frac keeps the 6-channel rule
-        return 2 * H * W * 4
+        return 2 * self.in_h * self.in_w * 4
+
+
+def _gen_pse_scene_q(seed):
+    from pytorchocr_b200 import synth
+    return synth.pse_scene(seed, H // 4, W // 4, n_abs=200, hh_rng=(2, 3), hw_rng=(4, 9))[:2]
+
+
+def _gen_pan_scene_q(seed):
+    from pytorchocr_b200 import synth
+    return synth.pan_scene(seed, H // 4, W // 4, n_abs=200, hh_rng=(2, 3), hw_rng=(4, 9))[:4]
+
+
+class PseApiWorkload(PseWorkload):
+    """SURVEY 8(d) API-faithful twin: the head's own output [N,7,184,320], scale 1 -> the operator's nearest x4
+    up-sampling is fused into the first kernel; processing resolution 736x1280."""
+    name = "pse_api"
+    in_h, in_w = H // 4, W // 4
+    cfg = dict(PSE_CFG, scale=1)
+    workload = ("PSENet r50 post-process through the operator API: head output [16,7,184,320] per GPU, scale 1 "
+                "(x4 nearest up-sampling fused, processing resolution 736x1280)")
+
+    def extra_cfg(self):
+        return {}
+
+    def host_prepare(self, pool, want_cpu):
+        self.scenes = pool.map(_gen_pse_scene_q, [SEED + self.rank * self.batch + i for i in range(self.batch)])
+        return None
+
+
+class PanApiWorkload(PanWorkload):
+    """SURVEY 8(d) API-faithful twin: head output [N,6,184,320], scale 4 (the shipped det_r18_pan.yml): processing at
+    184x320, labels up-sampled x4 for the boxes."""
+    name = "pan_api"
+    in_h, in_w = H // 4, W // 4
+    cfg = dict(PAN_CFG, scale=4)
+    workload = ("PAN++ r18 post-process through the operator API: head output [128,6,184,320] per GPU, scale 4 "
+                "(processing resolution 184x320, boxes at 736x1280)")
+
+    def extra_cfg(self):
+        return {}
+
+    def host_prepare(self, pool, want_cpu):
+        self.scenes = pool.map(_gen_pan_scene_q, [SEED + self.rank * self.batch + i for i in range(self.batch)])
+        return None
+
+    def alg_bytes_per_unit(self):
+        return 6 * self.in_h * self.in_w * 4
+
+    def kernel_bytes_per_unit(self):
+        return 2 * self.in_h * self.in_w * 4
 
 
 class CtcWorkload(Workload):
@@ -516,7 +654,9 @@ class CropWorkload(Workload):
                 "e2e_region": "pinned host pages + boxes -> crops in pinned host memory"}
 
 
-WORKLOADS = {"db": DbWorkload, "pse": PseWorkload, "pan": PanWorkload, "ctc": CtcWorkload, "crop": CropWorkload}
+WORKLOADS = {"db": DbWorkload, "pse": PseWorkload, "pan": PanWorkload, "ctc": CtcWorkload, "crop": CropWorkload,
+             "db_fp16": DbFp16Workload, "pse_api": PseApiWorkload, "pan_api": PanApiWorkload}
+OTHERS = ["pse", "pan", "ctc", "pse_api", "pan_api", "db_fp16"]     # reported under other_workloads by the default run
 
 
 # ----------------------------------------------------------------------------------------------
@@ -529,52 +669,53 @@ def run_reference(args):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     wl = WORKLOADS[args.workload](args, 0, 1)
-    with mp.get_context("fork").Pool(cores) as pool:
-        if args.workload == "db":
-            sample = 64
-            items = pool.map(_gen_db, [SEED + i for i in range(sample)], chunksize=4)
-            fn, units = _cpu_db, sample
-            what = "%d maps" % sample
-        elif args.workload in ("pse", "pan"):
-            sample = max(8, cores)
-            items = [SEED + i for i in range(sample)]
-            fn, units = (_cpu_pse if args.workload == "pse" else _cpu_pan), sample
-            what = "%d maps" % sample
-        elif args.workload == "crop":
-            sample = max(16, cores)
-            items = pool.map(_gen_page, [SEED + i for i in range(sample)], chunksize=2) * 8
-            fn, units = _cpu_crop, sample * 8
-            what = "%d pages" % (sample * 8)
-        else:
-            import tempfile
-            from pytorchocr_b200 import synth
-            dict_path = synth.write_char_dict(os.path.join(tempfile.mkdtemp(), "dict.txt"), CTC_C)
-            per, n = 128, cores * 2
-            items = [(SEED + i, per, dict_path) for i in range(n)]
-            fn, units = _cpu_ctc, per * n
-            what = "%d chunks of %d lines" % (n, per)
-        pool.map(fn, items[:cores])
-        for _ in range(args.warmup):
-            pool.map(fn, items, chunksize=1)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            pool.map(fn, items, chunksize=1)
-        dt = time.perf_counter() - t0
-    rate = units * args.steps / dt
+    note = ("the oracle port of the reference's CPU path (oracle/): db_postprocess.cpp needs OpenCV C++ and cannot be "
+            "built here, pse.pyx/pa.pyx are restated in C and pinned against the compiled reference")
+    if args.workload in ("db", "db_fp16"):
+        # the SAME maps our arm processes on rank 0 (same generator, same seeds, same batch)
+        with mp.get_context("fork").Pool(cores) as pool:
+            maps = np.stack(pool.map(_gen_db, [SEED + i for i in range(wl.batch)], chunksize=4))[:, None]
+        for _ in range(max(0, args.warmup - 1)):
+            _cpu_db_batch(maps, cores)
+        rate, nboxes, dt = _cpu_db_batch(maps, cores, passes=args.steps)
+        units, what, note = wl.batch, "all %d maps of the step (%d boxes per pass)" % (wl.batch, nboxes // max(1, args.steps)), DbWorkload.cpu_note
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            if args.workload in ("pse", "pan", "pse_api", "pan_api"):
+                sample = max(8, cores)
+                items = [SEED + i for i in range(sample)]
+                fn, units = (_cpu_pse if args.workload.startswith("pse") else _cpu_pan), sample
+                what = "%d maps at processing resolution" % sample
+            elif args.workload == "crop":
+                sample = max(16, cores)
+                items = pool.map(_gen_page, [SEED + i for i in range(sample)], chunksize=2) * 8
+                fn, units = _cpu_crop, sample * 8
+                what = "%d pages" % (sample * 8)
+                note = "oracle/crop_oracle.py: the reference's own sequence of cv2 calls (utility.py:32-78)"
+            else:
+                import tempfile
+                from pytorchocr_b200 import synth
+                dict_path = synth.write_char_dict(os.path.join(tempfile.mkdtemp(), "dict.txt"), CTC_C)
+                per, n = 128, cores * 2
+                items = [(SEED + i, per, dict_path) for i in range(n)]
+                fn, units = _cpu_ctc, per * n
+                what = "%d chunks of %d lines" % (n, per)
+            pool.map(fn, items[:cores])
+            for _ in range(args.warmup):
+                pool.map(fn, items, chunksize=1)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                pool.map(fn, items, chunksize=1)
+            dt = time.perf_counter() - t0
+        rate = units * args.steps / dt
     line = {
         "impl": "reference", "metric": wl.metric, "value": rate, "unit": wl.unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-        "config": {"workload": wl.workload + "; each step = a bounded sample (%s) on the host cores" % what,
-                   "H": H, "W": W},
+        "config": {"workload": wl.workload, "batch_per_gpu": wl.batch, "H": H, "W": W},
         "cpu_baseline": {"value": rate, "unit": wl.unit, "cores": cores, "kind": "port",
-                         "sample": "%s x %d steps, multiprocessing.Pool(%d), cv2.setNumThreads(1); %s"
-                                   % (what, args.steps, cores,
-                                      "oracle/crop_oracle.py: the reference's own sequence of cv2 calls (utility.py:32-78)"
-                                      if args.workload == "crop" else
-                                      "the oracle port of the reference's CPU path (oracle/): db_postprocess.cpp needs "
-                                      "OpenCV C++ and cannot be built here, pse.pyx/pa.pyx are restated in C and pinned "
-                                      "against the compiled reference")},
+                         "sample": "%s x %d steps, fork pool of %d workers, cv2.setNumThreads(1); %s"
+                                   % (what, args.steps, cores, note)},
         "e2e": {"value": rate, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -585,16 +726,184 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+def _pin_rank_to_cores(local_rank, world):
+    """Each rank gets its own slice of the host cores (the ranks of one node otherwise migrate over each other's
+    cores while they enqueue kernels, which shows up as per-rank jitter of the event-timed window)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(1, world))
+        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return len(mine)
+    except Exception:
+        return None
+
+
+def _traffic(wl):
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of the streaming kernel from one
+    `ncu --set full` capture (profiles/traffic.json holds it PER UNIT, with the capture it came from), scaled to the
+    units of one launch of this run."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[wl.name]
+        return float(t["dram_bytes_per_unit"]) * wl.batch
+    except Exception:
+        return None
+
+
+def measure(wl, args, steps, L, torch, dist, dev, local_rank, world, sampler):
+    """Device-resident timing, per-kernel phases and end-to-end timing of one prepared workload -> dict."""
+    from pytorchocr_b200 import _lib
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if wl.needs_flush() else None
+    for _ in range(max(3, args.warmup)):
+        wl.device_step(L, stream)
+    barrier()
+    launches0 = L.ocrpp_launch_count()
+    barrier()
+    if flush is None:
+        # inputs larger than the L2: K steps back to back between one pair of events
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.start()
+        e0.record(stream)
+        for _ in range(steps):
+            wl.device_step(L, stream)
+        e1.record(stream)
+        barrier()
+        sampler.stop()
+        ms_dev = e0.elapsed_time(e1)
+    else:
+        # small inputs: the L2 is flushed before every step; each step has its own pair of events
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        sampler.start()
+        for a, b in evs:
+            flush.fill_(1)
+            a.record(stream)
+            wl.device_step(L, stream)
+            b.record(stream)
+        barrier()
+        sampler.stop()
+        ms_dev = sum(a.elapsed_time(b) for a, b in evs)
+    launches = L.ocrpp_launch_count() - launches0
+    # ---- per-kernel durations (events around every kernel inside the library), in a separate pass: with the marks
+    #      on, the library runs each batch as ONE chain on the caller's stream, so the phases add up to an
+    #      un-overlapped step; the timed region above is the production configuration ----
+    L.ocrpp_profile_enable(1)
+    for _ in range(2):
+        wl.device_step(L, stream)
+    barrier()
+    L.ocrpp_profile_reset()
+    for _ in range(min(steps, 5)):
+        if flush is not None:
+            flush.fill_(1)
+        wl.device_step(L, stream)
+    barrier()
+    L.ocrpp_profile_enable(0)
+    calls, phases = _lib.profile_read()
+    # ---- end-to-end timing through the operator with HOST buffers ----
+    for _ in range(2):
+        wl.e2e_step()
+    barrier()
+    e2e_steps = max(1, min(args.e2e_steps, 20) if wl.name == "db" else min(steps, 5))
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        wl.e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    sampler.stop()
+
+    t = torch.tensor([ms_dev, t_e2e * 1e3], dtype=torch.float64, device=dev)
+    mine = t.clone()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev_max, ms_e2e_max = float(t[0]), float(t[1])
+    rank_ms, rank_e2e = [ms_dev / steps], [wl_units(wl) * e2e_steps / t_e2e]
+    if world > 1:   # per-rank step times next to the max the headline uses
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rank_ms = [float(x[0]) / steps for x in allr]
+        rank_e2e = [wl_units(wl) * e2e_steps / (float(x[1]) * 1e-3) for x in allr]
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = ("MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks
+                else "fallback 6.65 TB/s (B200_PROFILING.md)")
+    alg_bytes = wl.batch * wl.alg_bytes_per_unit()
+    kernel_bytes = wl.batch * (wl.kernel_bytes_per_unit() if hasattr(wl, "kernel_bytes_per_unit") else wl.alg_bytes_per_unit())
+    sp = getattr(wl, "stream_phase", 0)
+    k1_ms = phases[sp][1] / max(1, calls) if len(phases) > sp else None
+    achieved = kernel_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms else None
+    cfg = {"workload": wl.workload}
+    cfg.update(wl.config())
+    return {
+        "metric": wl.metric, "value": world * wl.batch * steps / (ms_dev_max * 1e-3), "unit": wl.unit,
+        "steps": steps, "ms_per_step": ms_dev_max / steps, "dtype": wl.dtype, "config": cfg,
+        "roofline": {"bound": "hbm", "kernel": wl.stream_kernel, "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": _traffic(wl),
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                     "kernel_bytes_per_launch": kernel_bytes, "kernel_ms": k1_ms,
+                     "whole_step_frac": alg_bytes / (ms_dev_max / steps * 1e-3) / 1e9 / peak},
+        "phases_ms": {nm: ms / max(1, calls) for nm, ms in phases},
+        "e2e": {"value": world * wl_units(wl) * e2e_steps / (ms_e2e_max * 1e-3), "unit": wl.unit,
+                "h2d_bytes_per_step": wl.h2d_bytes(), "d2h_bytes_per_step": wl.d2h_bytes(), "steps": e2e_steps,
+                "by_rank": rank_e2e},
+        "gpu_launches": int(launches),
+        "ms_per_step_by_rank": rank_ms,
+    }
+
+
+def wl_units(wl):
+    return getattr(wl, "e2e_units", wl.batch)
+
+
+def h2d_probe(torch, dist, dev, local_rank, world):
+    """Plain pinned host->device copy rate of every rank, all ranks copying at the same time: the ceiling the
+    end-to-end numbers are read against (8 ranks share one host's memory controllers and PCIe root complexes)."""
+    n = 256 << 20
+    src = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    dst = torch.empty(n, dtype=torch.uint8, device=dev)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(device_ids=[local_rank])
+    t0 = time.perf_counter()
+    for _ in range(4):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    gbs = torch.tensor([4 * n / (time.perf_counter() - t0) / 1e9], dtype=torch.float64, device=dev)
+    out = [gbs.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(out, gbs)
+    return [float(x[0]) for x in out]
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    wl = WORKLOADS[args.workload](args, rank, world)
+    pinned = _pin_rank_to_cores(local_rank, world) if world > 1 else None
+    names = [args.workload] + ([n for n in OTHERS if n != args.workload]
+                               if (args.workload == "db" and not args.headline_only and not args.batch) else [])
+    wls = [WORKLOADS[n](args, rank, world) for n in names]
 
     # ---- host phase (fork pool; CUDA not initialised yet) ----
     import multiprocessing as mp
-    with mp.get_context("fork").Pool(wl.cores) as pool:
-        cpu_base = wl.host_prepare(pool, rank == 0 and world == 1 and not args.no_cpu)
+    cpu_base = None
+    for i, wl in enumerate(wls):
+        with mp.get_context("fork").Pool(wl.cores) as pool:
+            cb = wl.host_prepare(pool, i == 0 and rank == 0 and world == 1 and not args.no_cpu)
+        if i == 0:
+            cpu_base = cb
 
     # ---- device phase ----
     import torch
@@ -605,112 +914,35 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier(device_ids=[local_rank])
-        torch.cuda.synchronize()
-
-    wl.device_prepare(dev)
     L = _lib.lib()
-    stream = torch.cuda.current_stream()
-
-    # ---- device-resident timing: inputs already in HBM and larger than the 126 MB L2 ----
-    for _ in range(args.warmup):
-        wl.device_step(L, stream)
-    barrier()
     sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = L.ocrpp_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        wl.device_step(L, stream)
-    e1.record(stream)
-    barrier()
-    launches = L.ocrpp_launch_count() - launches0
-    ms_dev = e0.elapsed_time(e1)
-    # ---- per-kernel durations (events around every kernel inside the library), in a separate pass: with
-    #      the marks on, the library runs each batch as ONE chain on the caller's stream, so the phases add
-    #      up to an un-overlapped step; the timed region above is the production configuration ----
-    L.ocrpp_profile_enable(1)
-    for _ in range(2):                      # warm the single-chain configuration (its streams are created lazily)
-        wl.device_step(L, stream)
-    barrier()
-    L.ocrpp_profile_reset()
-    for _ in range(min(args.steps, 5)):
-        wl.device_step(L, stream)
-    barrier()
-    L.ocrpp_profile_enable(0)
-    calls, phases = _lib.profile_read()
-
-    # ---- end-to-end timing through the operator with HOST buffers ----
-    for _ in range(2):
-        wl.e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        wl.e2e_step()
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    sampler.stop()
-
-    t = torch.tensor([ms_dev, t_e2e * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev_max, ms_e2e_max = float(t[0]), float(t[1])
-    rank_ms = [ms_dev / args.steps]
-    if world > 1:   # per-rank step times next to the max the headline uses (which GPU is the slow one, and by how much)
-        mine = torch.tensor([ms_dev / args.steps], dtype=torch.float64, device=dev)
-        allr = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allr, mine)
-        rank_ms = [float(x[0]) for x in allr]
+    results = []
+    for i, wl in enumerate(wls):
+        wl.device_prepare(dev)
+        steps = args.steps if i == 0 else max(3, min(args.steps, 5))
+        results.append(measure(wl, args, steps, L, torch, dist, dev, local_rank, world, sampler))
+        wl.release()
+    h2d = h2d_probe(torch, dist, dev, local_rank, world)
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = ("MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks
-                    else "fallback 6.65 TB/s (B200_PROFILING.md)")
-        alg_bytes = wl.batch * wl.alg_bytes_per_unit()
-        kernel_bytes = wl.batch * (wl.kernel_bytes_per_unit() if hasattr(wl, "kernel_bytes_per_unit")
-                                   else wl.alg_bytes_per_unit())
-        sp = getattr(wl, "stream_phase", 0)
-        k1_ms = phases[sp][1] / max(1, calls) if len(phases) > sp else None
-        achieved = kernel_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms else None
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[wl.name]["dram_bytes_per_launch"]
-        except Exception:
-            pass
-        value = world * wl.batch * args.steps / (ms_dev_max * 1e-3)
-        e2e_units = getattr(wl, "e2e_units", wl.batch)
-        cfg = {"workload": wl.workload}
-        cfg.update(wl.config())
+        head = results[0]
         line = {
-            "metric": wl.metric, "value": value, "unit": wl.unit,
+            "metric": head["metric"], "value": head["value"], "unit": head["unit"],
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev_max / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": cfg,
-            "roofline": {"bound": "hbm", "kernel": wl.stream_kernel, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_bytes_per_launch": kernel_bytes, "kernel_ms": k1_ms,
-                         "whole_step_frac": alg_bytes / (ms_dev_max / args.steps * 1e-3) / 1e9 / peak},
-            "phases_ms": {nm: ms / max(1, calls) for nm, ms in phases},
-            "e2e": {"value": world * e2e_units * e2e_steps / (ms_e2e_max * 1e-3), "unit": wl.unit,
-                    "h2d_bytes_per_step": wl.h2d_bytes(), "d2h_bytes_per_step": wl.d2h_bytes(), "steps": e2e_steps},
-            "gpu_launches": int(launches),
-            "ms_per_step_by_rank": rank_ms,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic", "config": head["config"],
+            "roofline": head["roofline"], "phases_ms": head["phases_ms"], "e2e": head["e2e"],
+            "gpu_launches": head["gpu_launches"], "ms_per_step_by_rank": head["ms_per_step_by_rank"],
+            "h2d_gbs_by_rank": h2d, "host_cores_per_rank": pinned,
             "clocks": sampler.summary(),
         }
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
+        if len(results) > 1:
+            line["other_workloads"] = {
+                wl.name: {k: r[k] for k in ("metric", "value", "unit", "steps", "ms_per_step", "dtype", "config", "roofline",
+                                            "phases_ms", "e2e", "gpu_launches", "ms_per_step_by_rank")}
+                for wl, r in zip(wls[1:], results[1:])}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -726,6 +958,8 @@ def main():
     ap.add_argument("--workload", default="db", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="units per GPU per step (0 = the workload's default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--headline-only", action="store_true", help="skip the other_workloads of the default run")
+    ap.add_argument("--e2e-steps", type=int, default=20, help="end-to-end steps of the headline workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -43,4 +43,38 @@ int clipper_ref_offset(const int64_t* xy, int n, double delta,
   return (int)soln.size();
 }
 
+// The same call sequence for `nquads` quads at once (the timing leg of bench.py: one ctypes call per image
+// instead of one per contour). quads: int64 [nquads,4,2]; deltas: double [nquads]. For quad q the points of ALL its
+// solution paths are written back to back starting at out_xy[2 * out_start[q]] (out_start has nquads+1 entries) and
+// the length of its LAST path goes to last_len[q], the number of its paths to npaths[q] (UnClip's quirky loop,
+// db_postprocess.cpp:52-57, needs both). Returns 0, or -1 if cap_points was exceeded.
+int clipper_ref_offset_batch(const int64_t* quads, const double* deltas, int nquads,
+                             int64_t* out_xy, int cap_points, int* out_start, int* npaths, int* last_len) {
+  int w = 0;
+  for (int q = 0; q < nquads; ++q) {
+    out_start[q] = w;
+    ClipperLib::ClipperOffset offset;
+    ClipperLib::Path p;
+    for (int i = 0; i < 4; ++i) p << ClipperLib::IntPoint(quads[8 * q + 2 * i], quads[8 * q + 2 * i + 1]);
+    offset.AddPath(p, ClipperLib::jtRound, ClipperLib::etClosedPolygon);
+    ClipperLib::Paths soln;
+    offset.Execute(soln, deltas[q]);
+    npaths[q] = (int)soln.size();
+    last_len[q] = soln.empty() ? 0 : (int)soln.back().size();
+    for (size_t j = 0; j < soln.size(); ++j) {
+      // the reference copies soln[j][i] for i < soln.back().size() (reads past the end of shorter paths are
+      // undefined there; the oracle clamps to the path's own length, as oracle/db_oracle.py does)
+      const size_t lim = soln[j].size() < soln.back().size() ? soln[j].size() : soln.back().size();
+      for (size_t i = 0; i < lim; ++i) {
+        if (w >= cap_points) return -1;
+        out_xy[2 * w] = soln[j][i].X;
+        out_xy[2 * w + 1] = soln[j][i].Y;
+        ++w;
+      }
+    }
+  }
+  out_start[nquads] = w;
+  return 0;
+}
+
 }  // extern "C"

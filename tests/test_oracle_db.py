@@ -61,3 +61,25 @@ def test_boxes_synth(seed):
         stable = np.abs(fa - np.floor(fa) - 0.5) > 2e-3
         assert np.array_equal(np.asarray(a["out"])[stable], np.asarray(b["out"])[stable])
     assert n_fragile <= 1
+
+
+def test_fast_port_equals_oracle():
+    """bench.py's CPU timing leg (oracle/db_oracle_fast.py: vectorised between the cv2 / Clipper calls) returns exactly
+    the boxes of the line-by-line oracle."""
+    import numpy as np
+    from oracle import db_oracle as O, db_oracle_fast as F
+    from pytorchocr_b200 import synth
+    if O._clipper() is None:
+        pytest.skip("oracle/_ref/libclipper_ref.so not built")
+    total = 0
+    for seed, (Hh, Ww) in enumerate([(192, 320), (160, 256), (97, 131), (736, 1280)]):
+        m = synth.db_map(500 + seed, H=Hh, W=Ww)
+        bm = (m > 0.3).astype(np.uint8)
+        for sw, sh in ((Ww, Hh), (Ww * 2 + 3, Hh + 11)):
+            a = O.boxes_from_bitmap(m, bm, 0.5, 1.7, sw, sh)
+            b = F.boxes_from_bitmap(m, bm, 0.5, 1.7, sw, sh)
+            assert a == b
+            total += len(a)
+    assert total > 300
+    z = np.zeros((64, 64), np.float32)
+    assert F.boxes_from_bitmap(z, z.astype(np.uint8), 0.5, 1.7, 64, 64) == []
