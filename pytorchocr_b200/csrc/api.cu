@@ -69,7 +69,10 @@ void profile_mark(int slot, int phase, const char* name, cudaStream_t s) {
 extern "C" {
 
 void ocrpp_profile_enable(int on) { ocrpp::g_prof_on = on != 0; }
-void ocrpp_profile_reset(void) { ocrpp::g_prof_calls = 0; }
+void ocrpp_profile_reset(void) {
+  ocrpp::g_prof_calls = 0;
+  ocrpp::g_prof_phases = 0;   // the next profiled call defines the phase list (another entry point may follow)
+}
 int ocrpp_profile_read(float* ms_out, int cap, int* calls_out) {
   using namespace ocrpp;
   const int np = g_prof_phases < cap ? g_prof_phases : cap;
