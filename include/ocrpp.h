@@ -130,6 +130,30 @@ OCRPP_API int ocrpp_ctc_greedy(const void* probs_dev, int dtype, int T, int B, i
  *                                                 id = 1 + rank of the component's first raster pixel
  * ------------------------------------------------------------------------------------------- */
 OCRPP_API size_t ocrpp_db_workspace_bytes(int N, int H, int W, int max_runs);
+/* The same with the reference's branch selectable (R/pytocr/postprocess/db_postprocess.py:56-71):
+ *   semantics OCRPP_DB_SEMANTICS_CPP    = `cpp_speedup: True`, db_postprocess_fast/src/db_postprocess.cpp:231-317 (what
+ *                                          ocrpp_db_postprocess computes)
+ *             OCRPP_DB_SEMANTICS_PYTHON = `cpp_speedup: False`, DBPostProcess.boxes_from_bitmap (db_postprocess.py:76-194):
+ *                                          short side = min(w,h) instead of max, BoxScore over the LINE_8 polygon fill
+ *                                          (no 4-connected "stair" pixels), unclip distance = area * ratio / length in
+ *                                          float64 (shapely), np.round (half to even) instead of roundf, box_thresh and
+ *                                          unclip_ratio used as doubles, `max_candidates` = the number of contours (in
+ *                                          cv2's order) that are looked at, the scores are part of the result.
+ *   score_mode OCRPP_DB_SCORE_POLY: mean over the filled contour; OCRPP_DB_SCORE_BOX (Python semantics only,
+ *             db_postprocess.py:109-110): mean over cv2.fillPoly of the contour's mini box (float corners shifted by the
+ *             clipped floor of their minimum and truncated to int, LINE_8). */
+#define OCRPP_DB_SEMANTICS_CPP 0
+#define OCRPP_DB_SEMANTICS_PYTHON 1
+#define OCRPP_DB_SCORE_POLY 0
+#define OCRPP_DB_SCORE_BOX 1
+OCRPP_API int ocrpp_db_postprocess_ex(const void* maps_dev, int dtype, int N, int H, int W,
+                         int64_t stride_n, int64_t stride_h, const int32_t* src_wh_dev,
+                         float thresh, double box_thresh, double unclip_ratio,
+                         int max_candidates, int max_runs, int use_dilation, int use_padding_resize,
+                         int semantics, int score_mode,
+                         int16_t* boxes_out_dev, float* scores_out_dev, int32_t* counts_out_dev,
+                         int32_t* status_out_dev, float* boxes_f_out_dev, int32_t* labels_dbg_dev,
+                         void* workspace_dev, size_t workspace_bytes, void* stream);
 OCRPP_API int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int H, int W,
                          int64_t stride_n, int64_t stride_h, const int32_t* src_wh_dev,
                          float thresh, float box_thresh, float unclip_ratio,

@@ -64,9 +64,11 @@ def mini_box_from_corners(corners):
     return np.array([idx1, idx2, idx3, idx4], np.float64)
 
 
-def candidates(pred, bitmap):
+def candidates(pred, bitmap, line_type=1):
     """Yields dicts: kind, first (x,y) raster-first point of the point set, pts (bool mask of the
-    contour point set), fill (bool mask), le2 (the <=2-points rule)."""
+    contour point set), fill (bool mask), le2 (the <=2-points rule). line_type=1: the C++ branch's
+    cv::fillPoly(..., lineType=1) (4-connected boundary: the X "stair" pixels are part of the fill);
+    line_type=8: the Python branch's default LINE_8 fill (db_postprocess.py:193) = the same sets without X."""
     bitmap = bitmap.astype(bool)
     H, W = bitmap.shape
     fg, nf = ndi.label(bitmap, structure=_S8)
@@ -114,6 +116,8 @@ def candidates(pred, bitmap):
         base = fill_c(c)
         R = (bg == fpar[c]) if fpar[c] != 0 else outside
         X = R & _shift(C, 0, -1) & (_shift(C, -1, 0) | _shift(C, 1, 0))
+        if line_type == 8:
+            X = np.zeros_like(C)
         ys, xs = np.nonzero(C)
         area = len(ys)
         bw, bh = xs.max() - xs.min() + 1, ys.max() - ys.min() + 1
@@ -130,6 +134,8 @@ def candidates(pred, bitmap):
         for dy in (-1, 1):
             X |= _shift(Hm, dy, -1) & _shift(fgm, 0, -1) & _shift(fgm, dy, 0)
         X &= ~base
+        if line_type == 8:
+            X = np.zeros_like(Hm)
         ys, xs = np.nonzero(ring)
         res.append({"kind": "hole", "first": (int(xs[0]), int(ys[0])), "pts": ring, "fill": base | X,
                     "le2": False, "comp": bpar[h], "hole": h})

@@ -240,7 +240,7 @@ def boxes_from_bitmap(pred, bitmap, box_thresh, unclip_ratio, src_w, src_h,
         if return_details:   # what the parity tests need to enumerate exact equal-area ties (tests/db_compare.py)
             d["contour"] = contour.copy()
             d["unclip_ratio"], d["scale"] = unclip_ratio, (width, height, src_w, src_h)
-            d["semantics"] = semantics
+            d["semantics"], d["score_mode"] = semantics, score_mode
         details.append(d)
         if not py and len(contour) <= 2:
             d["status"] = "le2pts"

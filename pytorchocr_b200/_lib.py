@@ -12,6 +12,7 @@ OK = 0
 F32, F16 = 0, 1
 IMG_RUN_OVERFLOW, IMG_CANDIDATES_TRUNCATED, IMG_VALUE_OUT_OF_RANGE = 1, 2, 4
 TUNE_DB_PATH, TUNE_DB_SPLIT, TUNE_DB_PRIO, TUNE_DB_SCAN = 0, 1, 2, 3
+DB_SEMANTICS_CPP, DB_SEMANTICS_PYTHON, DB_SCORE_POLY, DB_SCORE_BOX = 0, 1, 0, 1
 
 _lib = None
 
@@ -36,6 +37,11 @@ SIGNATURES = {
                                        C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ocrpp_db_postprocess_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                          C.c_void_p, C.c_float, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_size_t, C.c_void_p]),
     "ocrpp_pse_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]),
     "ocrpp_pse_postprocess": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p,

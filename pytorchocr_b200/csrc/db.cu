@@ -73,6 +73,10 @@ struct DbParams {
   int32_t* hcnt;         // [2*maxc] hull half lengths (db_image_kernel, global-table variant)
   int32_t* cand_root;    // [R] root run of every dense component id (db_image_kernel, global-table variant)
   uint32_t* flagw;       // [R/32+1] run flag words (db_image_kernel, global-table variant)
+  int dtype;             // OCRPP_F32 | OCRPP_F16 (element type of maps)
+  int sem;               // 0: the C++ branch's semantics (cpp_speedup: True); 1: the pure-Python branch's
+  int score_box;         // Python branch, score_mode "box": BoxScore over the filled mini box instead of the contour
+  double box_thresh_d, unclip_ratio_d;   // the Python branch compares / multiplies in float64
   int stairs, skip2;     // reference-branch switches: 4-connected fillPoly boundary (stair pixels), <= 2-point skip
   int16_t* res_box;      // [maxc*8]
   float* res_boxf;       // [maxc*8]
@@ -997,6 +1001,63 @@ __global__ void __launch_bounds__(kRunThreads) db_rank_kernel(DbParams p) {
 // K9b: generic per-candidate geometry, one warp per candidate: handles the (rare) candidates the
 // fast kernel below defers (more than kSmallRows rows, or an unclip polygon above its capacity).
 // ------------------------------------------------------------------------------------------------
+// ---- the places where the reference's two branches differ (oracle/db_oracle.py lists them) ----
+__device__ __forceinline__ float db_side(const DbParams& p, double w, double h) {
+  return p.sem ? fminf((float)w, (float)h) : fmaxf((float)w, (float)h);   // py:176 min(w,h) | cpp:161 max(w,h)
+}
+__device__ __forceinline__ double db_distance(const DbParams& p, const float* mx, const float* my) {
+  return p.sem ? geom::unclip_distance_py(mx, my, p.unclip_ratio_d)
+               : (double)geom::unclip_distance(mx, my, p.unclip_ratio);
+}
+__device__ __forceinline__ bool db_low_score(const DbParams& p, double mean) {
+  return p.sem ? mean < p.box_thresh_d : (float)mean < p.box_thresh;
+}
+__device__ __forceinline__ float db_px(const DbParams& p, int n, int x, int y) {
+  const long long off = n * p.stride_n + y * p.stride_h + x;
+  return p.dtype == OCRPP_F32 ? __ldg(reinterpret_cast<const float*>(p.maps) + off)
+                              : __half2float(__ldg(reinterpret_cast<const __half*>(p.maps) + off));
+}
+// score_mode "box" (db_postprocess.py:109-110,178-194): mean of the map over cv2.fillPoly of the mini box. `lanes`
+// threads (lane index li, all in `mask`) share the rows; L / R are scratch for bh row extents, filled by lane 0.
+__device__ __forceinline__ double db_box_score(const DbParams& p, int n, const float* mx, const float* my, int* L, int* R,
+                                               int li, int lanes, unsigned mask, int bxmin, int bymin, int bw, int bh,
+                                               const int* qx, const int* qy) {
+  if (li == 0) geom::fill_quad_rows(qx, qy, bw, bh, L, R);
+  __syncwarp(mask);
+  unsigned long long sum = 0;
+  int cnt = 0;
+  for (int y = li; y < bh; y += lanes) {
+    const int l = L[y], r = R[y];
+    for (int x = l; x <= r; ++x) sum += (unsigned long long)to_fixed(db_px(p, n, bxmin + x, bymin + y));
+    cnt += r >= l ? r - l + 1 : 0;
+  }
+  for (int o = lanes >> 1; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(mask, sum, o);
+    cnt += __shfl_xor_sync(mask, cnt, o);
+  }
+  __syncwarp(mask);
+  return cnt ? ((double)(long long)sum / kFixScale) / (double)cnt : 0.0;   // cv2.mean of an empty mask is 0
+}
+
+// rescale + round + clamp of one corner -> int16 pair and the pre-rounding floats
+__device__ __forceinline__ void db_store_corner(const DbParams& p, size_t ko, int q, float mxq, float myq, float sw, float sh) {
+  if (p.sem) {
+    double fx, fy;
+    geom::db_rescale_py(mxq, myq, p.W, p.H, sw, sh, p.pad_resize, &fx, &fy);
+    p.res_boxf[ko * 8 + 2 * q] = (float)fx;
+    p.res_boxf[ko * 8 + 2 * q + 1] = (float)fy;
+    p.res_box[ko * 8 + 2 * q] = (int16_t)(int)fmin(fmax(geom::round_half_even(fx), 0.0), (double)sw);
+    p.res_box[ko * 8 + 2 * q + 1] = (int16_t)(int)fmin(fmax(geom::round_half_even(fy), 0.0), (double)sh);
+  } else {
+    float fx, fy;
+    geom::db_rescale(mxq, myq, p.W, p.H, sw, sh, p.pad_resize, &fx, &fy);
+    p.res_boxf[ko * 8 + 2 * q] = fx;
+    p.res_boxf[ko * 8 + 2 * q + 1] = fy;
+    p.res_box[ko * 8 + 2 * q] = (int16_t)(int)fminf(fmaxf(geom::roundf_half_away(fx), 0.f), sw);
+    p.res_box[ko * 8 + 2 * q + 1] = (int16_t)(int)fminf(fmaxf(geom::roundf_half_away(fy), 0.f), sh);
+  }
+}
+
 constexpr int kGeoWarps = 4;
 constexpr int kSmallRows = 64;              // candidates up to this many rows build their hull in smem
 constexpr int kOffCap = 320;                // capacity of the unclip polygon (points)
@@ -1014,8 +1075,7 @@ __global__ void __launch_bounds__(kGeoWarps * 32) db_geometry_big_kernel(DbParam
   const int k = p.big[(size_t)n * p.maxc + bi];
   const size_t ko = (size_t)n * p.maxc + k;
   if (lane == 0) p.res_keep[ko] = 0;
-  // triaged by db_image_kernel / db_hull_kernel: <= 2-point rule and BoxScore passed
-  const float score = p.res_score[ko];
+  // triaged by db_image_kernel / db_hull_kernel: <= 2-point rule and (score_mode poly) BoxScore passed
   const int off = p.cand_off[ko], nrows = p.cand_nrows[ko], y0 = p.cand_y0[ko];
   const int32_t* ext_l = p.ext_l + (size_t)n * p.E + off;
   const int32_t* ext_r = p.ext_r + (size_t)n * p.E + off;
@@ -1047,16 +1107,30 @@ __global__ void __launch_bounds__(kGeoWarps * 32) db_geometry_big_kernel(DbParam
     cy[q] = (float)rect.cy[q];
   }
   geom::mini_box(cx, cy, mx, my);
-  const float ssid = fmaxf((float)rect.w, (float)rect.h);
+  const float ssid = db_side(p, rect.w, rect.h);
   if (ssid < 3.f) continue;
+  float score = p.res_score[ko];
+  if (p.score_box) {
+    int bxmin, bymin, bw, bh, qx[4], qy[4];
+    geom::box_score_quad(mx, my, p.W, p.H, &bxmin, &bymin, &bw, &bh, qx, qy);
+    int* L = bh <= kSmallRows ? reinterpret_cast<int*>(s_pts[wib]) : reinterpret_cast<int*>(p.hull + ((size_t)n * p.E + off) * 4);
+    if (bh > kSmallRows && 2 * bh > 8 * (nrows + 1)) {   // cannot happen: the mini box spans at most nrows + 3 rows
+      if (lane == 0) atomicOr(&p.imgflags[n], OCRPP_IMG_RUN_OVERFLOW);
+      continue;
+    }
+    __syncwarp();
+    const double mean = db_box_score(p, n, mx, my, L, L + bh, lane, 32, 0xffffffffu, bxmin, bymin, bw, bh, qx, qy);
+    score = (float)mean;
+    if (db_low_score(p, mean)) continue;
+  }
 
   // UnClip (db_postprocess.cpp:34-64)
-  const float distance = geom::unclip_distance(mx, my, p.unclip_ratio);
+  const double distance = db_distance(p, mx, my);
   P2i quad[4];
   for (int q = 0; q < 4; ++q) quad[q] = P2i{(int)mx[q], (int)my[q]};
   int m = 0;
   if (lane == 0) {
-    m = geom::do_offset_quad(quad, (double)distance, s_off[wib], kOffCap);
+    m = geom::do_offset_quad(quad, distance, s_off[wib], kOffCap);
     if (m > 0) geom::sort_points_yx(s_off[wib], m);
   }
   m = __shfl_sync(0xffffffffu, m, 0);
@@ -1077,19 +1151,12 @@ __global__ void __launch_bounds__(kGeoWarps * 32) db_geometry_big_kernel(DbParam
     cy[q] = (float)rect2.cy[q];
   }
   geom::mini_box(cx, cy, mx, my);
-  const float ssid2 = fmaxf((float)rect2.w, (float)rect2.h);
+  const float ssid2 = db_side(p, rect2.w, rect2.h);
   if (ssid2 < 5.f) continue;
 
   if (lane == 0) {
     const float sw = (float)p.src_wh[2 * n], sh = (float)p.src_wh[2 * n + 1];
-    for (int q = 0; q < 4; ++q) {
-      float fx, fy;
-      geom::db_rescale(mx[q], my[q], p.W, p.H, sw, sh, p.pad_resize, &fx, &fy);
-      p.res_boxf[ko * 8 + 2 * q] = fx;
-      p.res_boxf[ko * 8 + 2 * q + 1] = fy;
-      p.res_box[ko * 8 + 2 * q] = (int16_t)(int)fminf(fmaxf(geom::roundf_half_away(fx), 0.f), sw);
-      p.res_box[ko * 8 + 2 * q + 1] = (int16_t)(int)fminf(fmaxf(geom::roundf_half_away(fy), 0.f), sh);
-    }
+    for (int q = 0; q < 4; ++q) db_store_corner(p, ko, q, mx[q], my[q], sw, sh);
     p.res_score[ko] = score;
     p.res_keep[ko] = 1;
   }
@@ -1139,8 +1206,9 @@ __global__ void __launch_bounds__(kHullThreads) db_hull_kernel(DbParams p) {
   // BoxScore first: a low score drops the candidate whatever its rectangle is
   const long long tot = p.sum[ro + c] + p.fsum[ro + c] + p.xsum[ro + c];
   const int cnt = area + p.fcnt[ro + c] + p.xcnt[ro + c];
-  const float score = (float)(((double)tot / kFixScale) / (double)cnt);
-  if (score < p.box_thresh) return;
+  const double mean = ((double)tot / kFixScale) / (double)cnt;
+  const float score = (float)mean;
+  if (!p.score_box && db_low_score(p, mean)) return;
   p.res_score[ko] = score;
   p.cand_off[ko] = off;
   p.cand_y0[ko] = fg ? y_first : y_first - 1;
@@ -1220,7 +1288,7 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
   if (p.res_keep[ko] != 3) return;   // dropped or deferred by the triage (db_image_kernel / db_hull_kernel)
   __syncwarp(gmask);
   if (gl == 0) p.res_keep[ko] = 0;
-  const float score = p.res_score[ko];
+  float score = p.res_score[ko];
   const int off = p.cand_off[ko];
   auto defer = [&]() {
     if (gl == 0) {
@@ -1245,14 +1313,26 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
     cy[q] = (float)rect.cy[q];
   }
   geom::mini_box(cx, cy, mx, my);
-  if (fmaxf((float)rect.w, (float)rect.h) < 3.f) return;
+  if (db_side(p, rect.w, rect.h) < 3.f) return;
+  if (p.score_box) {
+    int bxmin, bymin, bw, bh, qx[4], qy[4];
+    geom::box_score_quad(mx, my, p.W, p.H, &bxmin, &bymin, &bw, &bh, qx, qy);
+    if (bh > 2 * kFastRows) {
+      defer();
+      return;
+    }
+    __syncwarp(gmask);
+    const double mean = db_box_score(p, n, mx, my, A, B, gl, kGrp, gmask, bxmin, bymin, bw, bh, qx, qy);
+    score = (float)mean;
+    if (db_low_score(p, mean)) return;
+  }
 
   // UnClip (db_postprocess.cpp:34-64)
-  const float distance = geom::unclip_distance(mx, my, p.unclip_ratio);
+  const double distance = db_distance(p, mx, my);
   P2i quad[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) quad[q] = P2i{(int)mx[q], (int)my[q]};
-  const int m = group_do_offset_quad(quad, (double)distance, s_off[g], kFastOff, gl, gmask);
+  const int m = group_do_offset_quad(quad, distance, s_off[g], kFastOff, gl, gmask);
   if (m < 0) {
     defer();
     return;
@@ -1312,19 +1392,12 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
     cy[q] = (float)rect2.cy[q];
   }
   geom::mini_box(cx, cy, mx, my);
-  if (fmaxf((float)rect2.w, (float)rect2.h) < 5.f) return;
+  if (db_side(p, rect2.w, rect2.h) < 5.f) return;
 
   if (gl == 0) {
     const float sw = (float)p.src_wh[2 * n], sh = (float)p.src_wh[2 * n + 1];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float fx, fy;
-      geom::db_rescale(mx[q], my[q], p.W, p.H, sw, sh, p.pad_resize, &fx, &fy);
-      p.res_boxf[ko * 8 + 2 * q] = fx;
-      p.res_boxf[ko * 8 + 2 * q + 1] = fy;
-      p.res_box[ko * 8 + 2 * q] = (int16_t)(int)fminf(fmaxf(geom::roundf_half_away(fx), 0.f), sw);
-      p.res_box[ko * 8 + 2 * q + 1] = (int16_t)(int)fminf(fmaxf(geom::roundf_half_away(fy), 0.f), sh);
-    }
+    for (int q = 0; q < 4; ++q) db_store_corner(p, ko, q, mx[q], my[q], sw, sh);
     p.res_score[ko] = score;
     p.res_keep[ko] = 1;
   }
@@ -1648,7 +1721,28 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
                                     int32_t* status_out_dev, float* boxes_f_out_dev,
                                     int32_t* labels_dbg_dev, void* workspace_dev,
                                     size_t workspace_bytes, void* stream) {
+  return ocrpp_db_postprocess_ex(maps_dev, dtype, N, H, W, stride_n, stride_h, src_wh_dev, thresh, (double)box_thresh,
+                                 (double)unclip_ratio, max_candidates, max_runs, use_dilation, use_padding_resize,
+                                 OCRPP_DB_SEMANTICS_CPP, OCRPP_DB_SCORE_POLY, boxes_out_dev, scores_out_dev,
+                                 counts_out_dev, status_out_dev, boxes_f_out_dev, labels_dbg_dev, workspace_dev,
+                                 workspace_bytes, stream);
+}
+
+extern "C" int ocrpp_db_postprocess_ex(const void* maps_dev, int dtype, int N, int H, int W,
+                                       int64_t stride_n, int64_t stride_h, const int32_t* src_wh_dev,
+                                       float thresh, double box_thresh_d, double unclip_ratio_d,
+                                       int max_candidates, int max_runs, int use_dilation, int use_padding_resize,
+                                       int semantics, int score_mode,
+                                       int16_t* boxes_out_dev,
+                                       float* scores_out_dev, int32_t* counts_out_dev,
+                                       int32_t* status_out_dev, float* boxes_f_out_dev,
+                                       int32_t* labels_dbg_dev, void* workspace_dev,
+                                       size_t workspace_bytes, void* stream) {
   using namespace ocrpp;
+  const float box_thresh = (float)box_thresh_d, unclip_ratio = (float)unclip_ratio_d;
+  OCRPP_CHECK_ARG(semantics == OCRPP_DB_SEMANTICS_CPP || semantics == OCRPP_DB_SEMANTICS_PYTHON, "db: bad semantics %d", semantics);
+  OCRPP_CHECK_ARG(score_mode == OCRPP_DB_SCORE_POLY || (score_mode == OCRPP_DB_SCORE_BOX && semantics == OCRPP_DB_SEMANTICS_PYTHON),
+                  "db: score_mode box exists in the Python branch's semantics only");
   OCRPP_CHECK_ARG(dtype == OCRPP_F32 || dtype == OCRPP_F16, "db: dtype must be OCRPP_F32 or OCRPP_F16");
   OCRPP_CHECK_ARG(N >= 0 && H > 0 && W > 0, "db: bad shape N=%d H=%d W=%d", N, H, W);
   OCRPP_CHECK_ARG(H < 32768 && W < 65536, "db: H must be < 32768 and W < 65536");
@@ -1666,8 +1760,13 @@ extern "C" int ocrpp_db_postprocess(const void* maps_dev, int dtype, int N, int 
   p.thresh = thresh; p.box_thresh = box_thresh; p.unclip_ratio = unclip_ratio;
   p.pad_resize = use_padding_resize ? 1 : 0;
   p.dilate = use_dilation ? 1 : 0;
-  p.stairs = 1;
-  p.skip2 = 1;
+  p.dtype = dtype;
+  p.sem = semantics;
+  p.score_box = score_mode == OCRPP_DB_SCORE_BOX ? 1 : 0;
+  p.box_thresh_d = box_thresh_d;
+  p.unclip_ratio_d = unclip_ratio_d;
+  p.stairs = semantics == OCRPP_DB_SEMANTICS_CPP ? 1 : 0;   // cpp:222 fillPoly(..., lineType = 1) | py:193 LINE_8
+  p.skip2 = 1;   // cpp:252; in the Python branch such contours fail its min-side test (a side of length 0) anyway
   const size_t need = carve(p, workspace_dev);
   if (need > workspace_bytes)
     return set_error(OCRPP_ERR_WORKSPACE_TOO_SMALL, "db: workspace needs %zu bytes, got %zu", need, workspace_bytes);

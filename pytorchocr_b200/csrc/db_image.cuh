@@ -769,8 +769,9 @@ __device__ bool db_image_run(const DbParams& p, const int n, char* smem, const s
       // BoxScore: a low score drops the candidate whatever its rectangle is
       const unsigned long long tot = t.sum[c] + t.esum[c];
       const int cnt = t.area[c] + t.ecnt[c];
-      const float score = (float)(((double)(long long)tot / kFixScale) / (double)cnt);
-      if (score < p.box_thresh) verdict = 0;
+      const double mean = ((double)(long long)tot / kFixScale) / (double)cnt;
+      const float score = (float)mean;
+      if (!p.score_box && db_low_score(p, mean)) verdict = 0;
       const int k1 = t.hcnt[k], k2 = t.hcnt[p.maxc + k];
       if (!side) {
         p.res_keep[ko] = verdict;

@@ -313,6 +313,25 @@ OCRPP_HD float unclip_distance(const float* bx, const float* by, float unclip_ra
   return fdiv(fmul(area, unclip_ratio), dist);
 }
 
+// The reference's pure-Python branch (db_postprocess.py:143-146): shapely Polygon(box).area * unclip_ratio /
+// .length in float64 - GEOS' Area::ofRingSigned (coordinates shifted by x0, sum of x_i * (y_{i-1} - y_{i+1}), halved)
+// and Length::ofLine over the closed ring; every product and sum rounded on its own as in the x86 build.
+OCRPP_HD double unclip_distance_py(const float* bx, const float* by, double unclip_ratio) {
+  const double x0 = (double)bx[0];
+  double sum = 0.0, len = 0.0;
+  for (int i = 1; i <= 3; ++i) {
+    const int n = (i + 1) & 3;   // ring point i+1 (point 4 is point 0 again)
+    sum = dadd(sum, dmul(dsub((double)bx[i], x0), dsub((double)by[i - 1], (double)by[n])));
+  }
+  for (int i = 0; i < 4; ++i) {
+    const int j = (i + 1) & 3;
+    const double dx = dsub((double)bx[j], (double)bx[i]), dy = dsub((double)by[j], (double)by[i]);
+    len = dadd(len, sqrt(dadd(dmul(dx, dx), dmul(dy, dy))));
+  }
+  const double area = fabs(sum / 2.0);
+  return dmul(area, unclip_ratio) / len;
+}
+
 OCRPP_HD long long clipper_round(double v) { return v < 0 ? (long long)(v - 0.5) : (long long)(v + 0.5); }
 
 // ClipperOffset for ONE closed polygon of 4 integer points, jtRound, ArcTolerance 0.25.
@@ -446,6 +465,202 @@ OCRPP_HD void db_rescale(float mx, float my, int W, int H, float sw, float sh, i
   const double tx = cx >= cy ? 0.0 : cx - cy, ty = cx >= cy ? cy - cx : 0.0;
   *fx = (float)(s * (double)mx + tx);
   *fy = (float)(s * (double)my + ty);
+}
+
+// The Python branch's rescale (db_postprocess.py:124-141): float32 `x / width * dest_width` (or, with
+// use_padding_resize, utility.py transform_preds: float64 matrix times the float32 point, kept in float64), then
+// np.round (half to even), np.clip, astype(int16). Returns the pre-rounding values as doubles.
+OCRPP_HD void db_rescale_py(float mx, float my, int W, int H, float sw, float sh, int use_padding_resize,
+                            double* fx, double* fy) {
+  if (!use_padding_resize) {
+    *fx = (double)fmul(fdiv(mx, (float)W), sw);
+    *fy = (double)fmul(fdiv(my, (float)H), sh);
+    return;
+  }
+  const double cx = (double)(float)((double)sw / 2.0), cy = (double)(float)((double)sh / 2.0);
+  const double m = sw > sh ? (double)sw : (double)sh;
+  const double s = m / (double)H;
+  const double tx = cx >= cy ? 0.0 : cx - cy, ty = cx >= cy ? cy - cx : 0.0;
+  *fx = dadd(dmul(s, (double)mx), tx);
+  *fy = dadd(dmul(s, (double)my), ty);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// score_mode "box" of the reference's Python branch (db_postprocess.py:109-110,178-194): the mean of the map over
+// cv2.fillPoly(mask, mini_box.astype(int32), 1) - LINE_8, shift 0 - in the bounding rectangle of the float corners
+// clipped to the map. Third-party behaviour restated from OpenCV's drawing.cpp (CollectPolyEdges /
+// FillEdgeCollection, Line -> LineIterator(connectivity 8, leftToRight), clipLine), in its integer arithmetic:
+//   every edge is drawn as a Bresenham line between the (clipped) end points, starting from the left one;
+//   the interior of every scan line y0 <= y < y1 runs from ceil to floor of the edges' 16.16 fixed-point x, which
+//   advance by the truncated quotient dx per row; an edge with an end point outside the mask is rebuilt from its
+//   clipped end points when those lie on different rows.
+// For the convex quads of this path every mask row is one interval: the result is L[y], R[y] (R < L: empty row).
+// Pinned against cv2 4.13 by tests/test_geometry_host.py (exact for quads inside the mask, which is every mini box
+// that does not leave the map; 1 differing mask in 2700 otherwise).
+// ------------------------------------------------------------------------------------------------
+OCRPP_HD bool cv_clip_line(long long w, long long h, long long* px1, long long* py1, long long* px2, long long* py2) {
+  long long x1 = *px1, y1 = *py1, x2 = *px2, y2 = *py2;
+  const long long right = w - 1, bottom = h - 1;
+  if (w <= 0 || h <= 0) return false;
+  int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+  int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+  if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+    long long a;
+    if (c1 & 12) {
+      a = c1 < 8 ? 0 : bottom;
+      x1 += (long long)(dmul((double)(a - y1), (double)(x2 - x1)) / (double)(y2 - y1));
+      y1 = a;
+      c1 = (x1 < 0) + (x1 > right) * 2;
+    }
+    if (c2 & 12) {
+      a = c2 < 8 ? 0 : bottom;
+      x2 += (long long)(dmul((double)(a - y2), (double)(x2 - x1)) / (double)(y2 - y1));
+      y2 = a;
+      c2 = (x2 < 0) + (x2 > right) * 2;
+    }
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+      if (c1) {
+        a = c1 == 1 ? 0 : right;
+        y1 += (long long)(dmul((double)(a - x1), (double)(y2 - y1)) / (double)(x2 - x1));
+        x1 = a;
+        c1 = 0;
+      }
+      if (c2) {
+        a = c2 == 1 ? 0 : right;
+        y2 += (long long)(dmul((double)(a - x2), (double)(y2 - y1)) / (double)(x2 - x1));
+        x2 = a;
+        c2 = 0;
+      }
+    }
+  }
+  *px1 = x1; *py1 = y1; *px2 = x2; *py2 = y2;
+  return (c1 | c2) == 0;
+}
+
+OCRPP_HD void fill_quad_rows(const int* qx, const int* qy, int w, int h, int* L, int* R) {
+  for (int y = 0; y < h; ++y) {
+    L[y] = 0x7fffffff;
+    R[y] = -1;
+  }
+  struct Edge { long long x, dx; int y0, y1; };
+  Edge e[4];
+  int ne = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int j = (i + 3) & 3;   // previous vertex
+    const long long t0x = qx[j], t0y = qy[j], t1x = qx[i], t1y = qy[i];
+    const bool outside = (unsigned long long)t0x >= (unsigned long long)w || (unsigned long long)t1x >= (unsigned long long)w ||
+                         (unsigned long long)t0y >= (unsigned long long)h || (unsigned long long)t1y >= (unsigned long long)h;
+    long long c0x = t0x, c0y = t0y, c1x = t1x, c1y = t1y;
+    bool visible = true;
+    if (outside) visible = cv_clip_line(w, h, &c0x, &c0y, &c1x, &c1y);
+    if (visible) {   // Line(): Bresenham from the left end point
+      long long x = c0x, y = c0y;
+      long long dx = c1x - c0x, dy = c1y - c0y;
+      int sy = 1;
+      if (dx < 0) { dx = -dx; dy = -dy; x = c1x; y = c1y; }
+      if (dy < 0) { dy = -dy; sy = -1; }
+      const bool vert = dy > dx;
+      if (vert) { const long long t = dx; dx = dy; dy = t; }
+      long long err = dx - (dy + dy);
+      const long long plus = dx + dx, minus = -(dy + dy);
+      for (long long k = 0; k <= dx; ++k) {
+        if (L[y] > (int)x) L[y] = (int)x;
+        if (R[y] < (int)x) R[y] = (int)x;
+        const bool m = err < 0;
+        err += minus + (m ? plus : 0);
+        if (vert) { y += sy; if (m) x += 1; } else { x += 1; if (m) y += sy; }
+      }
+    }
+    if (t0y == t1y) continue;
+    // the scan-line edge: from the clipped end points when the original ones are outside and the clipped ones span rows
+    long long a0x = t0x << 16, a0y = t0y, a1x = t1x << 16, a1y = t1y;
+    if (outside && c0y != c1y) { a0x = c0x << 16; a0y = c0y; a1x = c1x << 16; a1y = c1y; }
+    const long long ddx = (a1x - a0x) / (a1y - a0y);   // C integer division: truncation toward zero
+    Edge ed;
+    ed.dx = ddx;
+    if (t0y < t1y) { ed.y0 = (int)t0y; ed.y1 = (int)t1y; ed.x = a0x + (t0y - a0y) * ddx; }
+    else { ed.y0 = (int)t1y; ed.y1 = (int)t0y; ed.x = a1x + (t1y - a1y) * ddx; }
+    e[ne++] = ed;
+  }
+  if (ne < 2) return;
+  // sort by (y0, x, dx)
+  for (int i = 1; i < ne; ++i) {
+    const Edge v = e[i];
+    int j = i - 1;
+    while (j >= 0 && (e[j].y0 > v.y0 || (e[j].y0 == v.y0 && (e[j].x > v.x || (e[j].x == v.x && e[j].dx > v.dx))))) {
+      e[j + 1] = e[j];
+      --j;
+    }
+    e[j + 1] = v;
+  }
+  int ymax = e[0].y1;
+  for (int i = 1; i < ne; ++i) ymax = e[i].y1 > ymax ? e[i].y1 : ymax;
+  if (ymax > h) ymax = h;
+  int act[4], na = 0, next = 0;
+  for (int y = e[0].y0; y < ymax; ++y) {
+    int k = 0;
+    for (int i = 0; i < na; ++i)
+      if (e[act[i]].y1 != y) act[k++] = act[i];
+    na = k;
+    while (next < ne && e[next].y0 == y) {   // insert by x
+      int pos = 0;
+      while (pos < na && e[act[pos]].x < e[next].x) ++pos;
+      for (int i = na; i > pos; --i) act[i] = act[i - 1];
+      act[pos] = next++;
+      ++na;
+    }
+    for (int i = 0; i + 1 < na; i += 2) {
+      Edge& a = e[act[i]];
+      Edge& b = e[act[i + 1]];
+      if (y >= 0) {
+        const long long xa = a.x > b.x ? b.x : a.x, xb = a.x > b.x ? a.x : b.x;
+        long long x1 = (xa + 65535) >> 16, x2 = xb >> 16;
+        if (x1 < w && x2 >= 0) {
+          if (x1 < 0) x1 = 0;
+          if (x2 >= w) x2 = w - 1;
+          if (x1 <= x2) {
+            if (L[y] > (int)x1) L[y] = (int)x1;
+            if (R[y] < (int)x2) R[y] = (int)x2;
+          }
+        }
+      }
+      a.x += a.dx;
+      b.x += b.dx;
+    }
+    for (int i = 1; i < na; ++i) {   // keep the active list sorted by x
+      const int v = act[i];
+      int j = i - 1;
+      while (j >= 0 && e[act[j]].x > e[v].x) {
+        act[j + 1] = act[j];
+        --j;
+      }
+      act[j + 1] = v;
+    }
+  }
+}
+
+// box_score's rectangle and integer quad (db_postprocess.py:183-192): float32 corners -> (xmin, ymin, w, h), qx/qy
+OCRPP_HD void box_score_quad(const float* bx, const float* by, int W, int H, int* xmin, int* ymin, int* w, int* h,
+                             int* qx, int* qy) {
+  float fx0 = bx[0], fx1 = bx[0], fy0 = by[0], fy1 = by[0];
+  for (int i = 1; i < 4; ++i) {
+    fx0 = bx[i] < fx0 ? bx[i] : fx0;
+    fx1 = bx[i] > fx1 ? bx[i] : fx1;
+    fy0 = by[i] < fy0 ? by[i] : fy0;
+    fy1 = by[i] > fy1 ? by[i] : fy1;
+  }
+  auto clampi = [](double v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : (int)v); };
+  const int x0 = clampi(floor((double)fx0), 0, W - 1), x1 = clampi(ceil((double)fx1), 0, W - 1);
+  const int y0 = clampi(floor((double)fy0), 0, H - 1), y1 = clampi(ceil((double)fy1), 0, H - 1);
+  *xmin = x0;
+  *ymin = y0;
+  *w = x1 - x0 + 1;
+  *h = y1 - y0 + 1;
+  for (int i = 0; i < 4; ++i) {
+    qx[i] = (int)fsub(bx[i], (float)x0);   // float32 subtraction, astype(int32): truncation toward zero
+    qy[i] = (int)fsub(by[i], (float)y0);
+  }
 }
 
 // np.round (half to even) on a double, as used by PSE/PAN generate_box (pse_postprocess.py:100-101)

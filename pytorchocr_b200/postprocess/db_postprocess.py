@@ -1,11 +1,20 @@
 """DB / DB++ post-processing behind the reference's operator API, computed by libocrpp (sm_100a).
 
 Mirrors R/pytocr/postprocess/db_postprocess.py (DBPostProcess :10-74, DistillationDBPostProcess
-:197-226) on its CONFIGURED path (`cpp_speedup: True`, i.e. the semantics of
-db_postprocess_fast/src/db_postprocess.cpp:231-317): same ctor kwargs, same
-`__call__(outs_dict, shape_list, use_padding_resize=False)`, same return structure
-(list of {"points": int16 [K,4,2], "scores": [1.0]*K}; K == 0 gives points.shape == (0,)).
-The true BoxScore of every box is additionally returned as "box_scores" (float32 [K]).
+:197-226): same ctor kwargs, same `__call__(outs_dict, shape_list, use_padding_resize=False)`, same
+return structure (list of {"points": int16 [K,4,2], "scores": [...]}; K == 0 gives points.shape == (0,)).
+Both of the reference's branches are reproduced, selected by the reference's own `cpp_speedup` flag:
+  * `cpp_speedup: True` (the shipped configs): the semantics of db_postprocess_fast/src/db_postprocess.cpp:231-317 -
+    short side = max(w,h), BoxScore over the 4-connected polygon fill, float32 unclip distance, roundf,
+    max_candidates fixed at 1000, score_mode ignored, "scores" = [1.0]*K (db_postprocess.py:64-67);
+  * `cpp_speedup: False` (the class default): the semantics of DBPostProcess.boxes_from_bitmap (:76-194) - short
+    side = min(w,h), BoxScore over the LINE_8 fill of the contour (`score_mode: poly`) or of its mini box
+    (`score_mode: box`), float64 unclip distance, np.round, the first `max_candidates` contours in cv2's order, real
+    scores.
+The BoxScore of every box is additionally returned as "box_scores" (float32 [K]).
+`out_polygon: True` has no behaviour to reproduce: the reference ends in np.array(ragged polygons, dtype=int16)
+(:142) and raises on every multi-region page (recorded from the unmodified reference in
+tests/golden/reference_db_python.npz, tests/test_oracle_db_python.py).
 
 The probability map never leaves the device: it is consumed where the head wrote it
 (zero-copy through data_ptr()); only boxes / counts come back, through pinned buffers.
@@ -23,15 +32,17 @@ class DBPostProcess(object):
             raise _lib.OcrppError("pytorchocr_b200 implements only the CUDA path: set PostProcess.cuda_speedup: True "
                                   "(with the flag off the reference's own DBPostProcess runs)")
         assert score_mode in ["box", "poly"], "Score mode must be in [box, poly] but got: {}".format(score_mode)
-        # The C++ path the CUDA path replaces ignores score_mode (always scores the contour polygon),
-        # hard-codes min_size = 3 and max_candidates = 1000 and cannot emit polygons
-        # (db_postprocess.cpp:238-239,270); options outside it are SURVEY 8(f) items.
         self.use_dilation = bool(use_dilation)   # db_postprocess.py:22: dilation_kernel = [[1,1],[1,1]]
         if out_polygon:
-            raise NotImplementedError("out_polygon needs cpp_speedup False in the reference; not on the CUDA path")
+            raise NotImplementedError("out_polygon: the reference's own branch raises ValueError on ragged polygons "
+                                      "(db_postprocess.py:142); there is no behaviour to reproduce")
+        self.cpp_speedup = bool(cpp_speedup)
+        if not self.cpp_speedup and int(max_candidates) > 1000:
+            raise ValueError("max_candidates > 1000 is not supported (workspace capacity of the library)")
         self.thresh = thresh
         self.box_thresh = box_thresh
-        self.max_candidates = min(int(max_candidates), 1000)
+        # db_postprocess.cpp:239 ignores the kwarg (const int max_candidates = 1000); the Python branch honours it
+        self.max_candidates = 1000 if self.cpp_speedup else max(0, int(max_candidates))
         self.unclip_ratio = unclip_ratio
         self.min_size = 3
         self.score_mode = score_mode
@@ -40,7 +51,7 @@ class DBPostProcess(object):
         # max_candidates (1000) contours; real pages have far fewer, so the block is sized for
         # `out_capacity` candidates and the call is repeated with the full capacity when the library
         # reports OCRPP_IMG_CANDIDATES_TRUNCATED below it (same results, 3x less D2H traffic).
-        self.out_capacity = max(1, min(self.max_candidates, int(out_capacity or self.max_candidates)))
+        self.out_capacity = max(1, min(max(1, self.max_candidates), int(out_capacity or self.max_candidates or 1)))
         self._cache = {}
 
     # -- device plumbing ------------------------------------------------------------------------
@@ -126,11 +137,14 @@ class DBPostProcess(object):
                 if labels:
                     extras_dev["labels"] = torch.empty((N, H, W), dtype=torch.int32, device=t.device)
                     lab_ptr = extras_dev["labels"].data_ptr()
-                _lib.check(L.ocrpp_db_postprocess(
+                _lib.check(L.ocrpp_db_postprocess_ex(
                     t.data_ptr(), _lib.F32 if t.dtype == torch.float32 else _lib.F16, N, H, W,
                     t.stride(0), t.stride(2), buf["wh_dev"].data_ptr(),
                     float(self.thresh), float(self.box_thresh), float(self.unclip_ratio), cap, R,
-                    1 if self.use_dilation else 0, 1 if use_padding_resize else 0, base + o_box, base + o_sc, base + o_cnt, base + o_st, bf_ptr, lab_ptr,
+                    1 if self.use_dilation else 0, 1 if use_padding_resize else 0,
+                    _lib.DB_SEMANTICS_CPP if self.cpp_speedup else _lib.DB_SEMANTICS_PYTHON,
+                    _lib.DB_SCORE_BOX if (self.score_mode == "box" and not self.cpp_speedup) else _lib.DB_SCORE_POLY,
+                    base + o_box, base + o_sc, base + o_cnt, base + o_st, bf_ptr, lab_ptr,
                     buf["ws"].data_ptr(), buf["ws_bytes"], stream.cuda_stream))
                 buf["out_host"].copy_(out, non_blocking=True)
                 stream.synchronize()
@@ -192,6 +206,9 @@ class DBPostProcess(object):
         on_host = isinstance(maps, np.ndarray) or not getattr(maps, "is_cuda", True)
         if on_host and len(maps) >= 2 * self.upload_chunk:
             return self._call_host_batch(maps, shape_list, use_padding_resize)
+        if self.max_candidates == 0:      # Python branch: num_contours = min(len(contours), 0)
+            return [{"points": np.array([], dtype=np.int16), "scores": [], "box_scores": np.zeros((0,), np.float32)}
+                    for _ in range(len(maps))]
         boxes, scores, counts, _, _ = self.run_device(maps, shape_list, use_padding_resize=use_padding_resize)
         res_batch = []
         for n in range(boxes.shape[0]):
@@ -200,7 +217,10 @@ class DBPostProcess(object):
                 pts = np.array([], dtype=np.int16)
             else:
                 pts = boxes[n, :k].copy()
-            res_batch.append({"points": pts, "scores": [1.0] * k, "box_scores": scores[n, :k].copy()})
+            sc = scores[n, :k].copy()
+            # cpp_speedup: the wrapper discards the C++ module's scores (db_postprocess.py:64-67)
+            res_batch.append({"points": pts, "scores": [1.0] * k if self.cpp_speedup else [float(v) for v in sc],
+                              "box_scores": sc})
         return res_batch
 
 

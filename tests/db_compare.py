@@ -92,9 +92,10 @@ def tie_alternatives(d):
 
     # rel = 2e-6: cv2's float32 rotating calipers cannot tell rectangles whose areas differ by less than that
     firsts = G.tied_min_area_rects(d["contour"], rel=2e-6, corners=True)
+    py = d.get("semantics") == "python"
     for c1 in firsts:
         mini = mini_box(c1)
-        rect2, _, _, soln = O.unclip(mini, d["unclip_ratio"])
+        soln = (O.unclip_py(mini, d["unclip_ratio"]) if py else O.unclip(mini, d["unclip_ratio"]))[3]
         pts = [p for path in soln for p in path]
         seconds = G.tied_min_area_rects(pts, rel=2e-6, corners=True) if len(pts) >= 3 else []
         for c2 in seconds:
@@ -161,6 +162,7 @@ def compare_image(boxes, boxes_f, scores, details, tol_px=1e-3, tol_score=1e-5):
     # corner-order independent distance between boxes, for the MATCHING in map pixels (a box that moved by one
     # map pixel on one of the reference's discontinuities moves by src/map pixels in the output)
     norm = np.ones(2)
+    width = height = 1 << 30
     if "scale" in ok[0]:
         width, height, src_w, src_h = ok[0]["scale"]
         norm = np.array([min(1.0, width / float(src_w)), min(1.0, height / float(src_h))])
@@ -176,7 +178,17 @@ def compare_image(boxes, boxes_f, scores, details, tol_px=1e-3, tol_score=1e-5):
         used.add(j)
         done.add(int(i))
         d = ok[i]
-        assert abs(scores[j] - d["score"]) <= tol_score * abs(d["score"]) + 1e-7, (scores[j], d["score"])
+        if abs(scores[j] - d["score"]) > tol_score * abs(d["score"]) + 1e-7:
+            # score_mode "box" (Python branch) truncates the float32 mini-box corners to int before cv2.fillPoly: a
+            # corner within 2e-3 of an integer (cv2's float32 calipers against exact arithmetic) moves one edge of the
+            # mask by a pixel, and a mini box that leaves the map meets OpenCV-version-dependent clipping. Anything
+            # else is a failure.
+            mini = np.asarray(d["mini"], np.float64)
+            leaves = mini.min() < 0 or mini[:, 0].max() > width - 1 or mini[:, 1].max() > height - 1
+            assert d.get("score_mode") == "box" and ("truncation" in classify(d) or leaves or on_discontinuity(d)), \
+                (scores[j], d["score"])
+            assert abs(scores[j] - d["score"]) <= 0.2 * abs(d["score"]), (scores[j], d["score"])
+            stats["box_score_discontinuity"] = stats.get("box_score_discontinuity", 0) + 1
         ordered = np.abs(of[i] - gf[j]).max()
         if ordered < tol_px:
             stable = np.abs(of[i] - np.floor(of[i]) - 0.5) > 2e-3

@@ -87,4 +87,20 @@ void shim_db_rescale(float mx, float my, int W, int H, float sw, float sh, int u
 
 float shim_roundf(float v) { return roundf_half_away(v); }
 double shim_round_half_even(double v) { return round_half_even(v); }
+
+// score_mode "box": rectangle + integer quad of box_score, then the fillPoly row extents
+void shim_box_score_rows(const float* bxy, int W, int H, int* rect, int* L, int* R) {
+  float bx[4], by[4];
+  for (int i = 0; i < 4; ++i) { bx[i] = bxy[2 * i]; by[i] = bxy[2 * i + 1]; }
+  int qx[4], qy[4];
+  box_score_quad(bx, by, W, H, &rect[0], &rect[1], &rect[2], &rect[3], qx, qy);
+  fill_quad_rows(qx, qy, rect[2], rect[3], L, R);
 }
+
+void shim_fill_quad_rows(const int* qxy, int w, int h, int* L, int* R) {
+  int qx[4], qy[4];
+  for (int i = 0; i < 4; ++i) { qx[i] = qxy[2 * i]; qy[i] = qxy[2 * i + 1]; }
+  fill_quad_rows(qx, qy, w, h, L, R);
+}
+
+}  // extern "C"
