@@ -244,6 +244,22 @@ OCRPP_API int ocrpp_crop_boxes(const uint8_t* img_dev, int N, int H, int W, int 
                      int64_t* offsets_out_dev, int32_t* dims_out_dev, int32_t* order_out_dev,
                      int32_t* status_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Recogniser pre-processing of the crop arena ocrpp_crop_boxes wrote: one float32 batch [K, Cout, img_h, img_w] for
+ * ONE recogniser forward. Replaces, per crop, cv2.cvtColor + RecResizeImg (resize_norm_img: cv2.resize to
+ * (min(img_w, ceil(img_h * w / h)), img_h), / 255, (x - 0.5) / 0.5, zero padding to img_w) + the upload of
+ * R/deploy/pytorch/run_ocr.py:212-220 and R/pytocr/data/imaug/rec_img_aug.py:108-134, with cv2's 8-bit arithmetic
+ * reproduced bit for bit.
+ *   crops_dev / offsets_dev / dims_dev: the arena, byte offsets and (rows, cols) of K crops with `channels` (1 or 3,
+ *   BGR) interleaved channels; a crop with rows == 0 gives an all-zero image.
+ *   img_mode: OCRPP_IMG_MODE_GRAY (Cout = 1; BGR2GRAY for 3-channel crops), _RGB (channel order reversed), _BGR.
+ * ------------------------------------------------------------------------------------------- */
+#define OCRPP_IMG_MODE_GRAY 0
+#define OCRPP_IMG_MODE_RGB 1
+#define OCRPP_IMG_MODE_BGR 2
+OCRPP_API int ocrpp_rec_preprocess(const uint8_t* crops_dev, const int64_t* offsets_dev, const int32_t* dims_dev, int K,
+                         int channels, int img_mode, int img_h, int img_w, float* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, "libocrpp.so")
-SOURCES = ["api.cu", "ctc.cu", "db.cu", "expand.cu", "crop.cu"]
+SOURCES = ["api.cu", "ctc.cu", "db.cu", "expand.cu", "crop.cu", "prep.cu"]
 EXTRA = os.environ.get("OCRPP_NVCC_EXTRA", "").split()
 NVCC_FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

@@ -48,15 +48,18 @@ class PartImageCropper(object):
             assert counts.is_cuda and counts.dtype == torch.int32 and counts.numel() == N and counts.is_contiguous()
         dev = imgs.device
         K = N * cap
-        key = (N, cap, dev)
-        buf = self._bufs.get(key)
+        # ONE grow-only set of buffers per device (workspace, device meta block, pinned meta block, crop arena): a page
+        # loop calls this with a different (N, cap) for nearly every page, so buffers keyed by the shape would pile up
+        ws_bytes = L.ocrpp_crop_workspace_bytes(N, cap)
+        meta_elems = 2 * (K + 1) + 2 * K + K + N          # int64 offsets (as 2 x int32), dims, order, status
+        buf = self._bufs.get(dev)
         if buf is None:
-            ws_bytes = L.ocrpp_crop_workspace_bytes(N, cap)
-            meta_elems = 2 * (K + 1) + 2 * K + K + N          # int64 offsets (as 2 x int32), dims, order, status
-            buf = dict(ws=torch.empty(ws_bytes, dtype=torch.uint8, device=dev),
-                       meta=torch.empty(meta_elems, dtype=torch.int32, device=dev),
-                       host=torch.empty(meta_elems, dtype=torch.int32, pin_memory=True), arena=None)
-            self._bufs[key] = buf
+            buf = self._bufs[dev] = dict(ws=None, meta=None, host=None, arena=None)
+        if buf["ws"] is None or buf["ws"].numel() < ws_bytes:
+            buf["ws"] = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        if buf["meta"] is None or buf["meta"].numel() < meta_elems:
+            buf["meta"] = torch.empty(meta_elems, dtype=torch.int32, device=dev)
+            buf["host"] = torch.empty(meta_elems, dtype=torch.int32, pin_memory=True)
         if capacity is None:
             capacity = N * H * W * C if buf["arena"] is None else buf["arena"].numel()
         stream = torch.cuda.current_stream(dev)
@@ -73,9 +76,11 @@ class PartImageCropper(object):
                                           cap, 1 if self.sort else 0, 1 if self.rotate_tall else 0,
                                           arena.data_ptr(), arena.numel(), base, o_dims, o_order, o_status,
                                           buf["ws"].data_ptr(), buf["ws"].numel(), stream.cuda_stream))
-            buf["host"].copy_(meta, non_blocking=True)
+            buf["host"][:meta_elems].copy_(meta[:meta_elems], non_blocking=True)
             stream.synchronize()
-            h = buf["host"].numpy()
+            h = buf["host"].numpy()[:meta_elems]
+            # device views of the same block for callers that stay on the device (deploy/run_ocr.py); valid until the next call
+            self.last_device_meta = dict(offsets=meta[:2 * (K + 1)].view(torch.int64), dims=meta[2 * (K + 1):2 * (K + 1) + 2 * K])
             offsets = h[:2 * (K + 1)].view(np.int64).copy()
             dims = h[2 * (K + 1):2 * (K + 1) + 2 * K].reshape(K, 2).copy()
             order = h[2 * (K + 1) + 2 * K:2 * (K + 1) + 3 * K].reshape(N, cap).copy()

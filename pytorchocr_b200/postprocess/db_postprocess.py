@@ -165,6 +165,10 @@ class DBPostProcess(object):
         scores = host[o_sc:o_sc + N * cap * 4].view(np.float32).reshape(N, cap)
         counts = host[o_cnt:o_cnt + 4 * N].view(np.int32)
         extras = {k: v.cpu().numpy() for k, v in extras_dev.items()}
+        # device views of the same results for callers that stay on the device (deploy/run_ocr.py: crops are cut from
+        # these without a host round trip); valid until the next call of this operator
+        extras["boxes_dev"] = out[o_box:o_box + N * cap * 16].view(torch.int16).view(N, cap, 4, 2)
+        extras["counts_dev"] = out[o_cnt:o_cnt + 4 * N].view(torch.int32)
         return boxes, scores, counts, status, extras
 
     upload_chunk = 64   # images per H2D chunk of the host-input path

@@ -3,6 +3,7 @@
 #include <vector>
 
 #include "../../pytorchocr_b200/csrc/geometry.cuh"
+#include "../../pytorchocr_b200/csrc/prep.cuh"
 
 using namespace ocrpp::geom;
 
@@ -101,6 +102,18 @@ void shim_fill_quad_rows(const int* qxy, int w, int h, int* L, int* R) {
   int qx[4], qy[4];
   for (int i = 0; i < 4; ++i) { qx[i] = qxy[2 * i]; qy[i] = qxy[2 * i + 1]; }
   fill_quad_rows(qx, qy, w, h, L, R);
+}
+
+// recogniser pre-processing of one crop [h,w,cin] -> float32 [cout, img_h, img_w] (zero padded), returns resized_w
+int shim_rec_preprocess(const uint8_t* crop, int h, int w, int cin, int mode, int img_h, int img_w, float* out) {
+  using namespace ocrpp::prep;
+  const int cout = mode == 0 ? 1 : cin;
+  const int rw = resized_width(h, w, img_h, img_w);
+  for (int c = 0; c < cout; ++c)
+    for (int y = 0; y < img_h; ++y)
+      for (int x = 0; x < img_w; ++x)
+        out[((size_t)c * img_h + y) * img_w + x] = x < rw ? normalise(resized_value(crop, h, w, cin, mode, rw, img_h, x, y, c)) : 0.f;
+  return rw;
 }
 
 }  // extern "C"

@@ -391,3 +391,33 @@ def test_fill_quad_rows_equals_cv2_fillpoly(shim):
     print(stats)
     assert stats["in"][0] > 2000 and stats["in"][1] == 0, stats
     assert stats["out"][0] > 1500 and stats["out"][1] <= 0.01 * stats["out"][0], stats
+
+
+def _ref_rec_preprocess(part_img, mode, image_shape):
+    from oracle.rec_prep_oracle import rec_preprocess
+    return rec_preprocess(part_img, mode, image_shape)
+
+
+def test_rec_preprocess_equals_cv2(shim):
+    """pytorchocr_b200/csrc/prep.cuh (the code the rec_preprocess kernel runs per output pixel) against the
+    reference's cvtColor + cv2.resize + normalise + pad on random crops: float32 tensors bit for bit."""
+    rng = np.random.default_rng(4)
+    shim.shim_rec_preprocess.restype = C.c_int
+    n = 0
+    for t in range(400):
+        if t % 10 == 0:
+            h, w = 64, 2 * int(rng.integers(3, 150))          # exact 2x2 decimation
+        elif t % 10 == 1:
+            h, w = 32, int(rng.integers(2, 400))               # no vertical resize
+        else:
+            h, w = int(rng.integers(2, 90)), int(rng.integers(2, 500))
+        crop = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        if t % 7 == 0:
+            crop = cv2.GaussianBlur(crop, (0, 0), 2.0)
+        for mode, name, shape in ((0, "GRAY", (1, 32, 320)), (1, "RGB", (3, 32, 320)), (2, "BGR", (3, 32, 100))):
+            want = _ref_rec_preprocess(crop, name, shape)
+            got = np.empty(shape, np.float32)
+            shim.shim_rec_preprocess(crop.ctypes.data_as(C.c_void_p), h, w, 3, mode, shape[1], shape[2], got.ctypes.data_as(C.c_void_p))
+            assert np.array_equal(got, want), (t, h, w, name, np.abs(got - want).max(), int((got != want).sum()))
+            n += 1
+    assert n == 1200
