@@ -1779,7 +1779,7 @@ extern "C" int ocrpp_db_postprocess_ex(const void* maps_dev, int dtype, int N, i
   // Large batches run as independent sub-batch pipelines on separate streams: the issue-bound map scan of one
   // sub-batch overlaps the latency-bound stage 2 and the ALU-bound geometry of another. (Not while per-phase
   // profiling is on: the event marks describe one whole-batch chain.)
-  int nsplit = N >= 192 ? 4 : (N >= 64 ? 2 : 1);
+  int nsplit = N >= 64 ? 2 : 1;
   const int forced = tuning(OCRPP_TUNE_DB_SPLIT);
   if (forced > 0) nsplit = forced > kDbMaxSplit ? kDbMaxSplit : forced;
   DbAux* aux = (nsplit > 1 && nsplit <= N && !profile_on()) ? db_aux() : nullptr;

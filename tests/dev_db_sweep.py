@@ -25,9 +25,9 @@ def timeit(k=20):
     e0.record(); [step() for _ in range(k)]; e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / k
 _lib.check(L.ocrpp_set_tuning(2, 1))
-for scan in (0, 1):
+for scan in (0,):
     _lib.check(L.ocrpp_set_tuning(3, scan))
-    for split in (1, 2, 4):
+    for split in (1, 2, 4, 8):
         _lib.check(L.ocrpp_set_tuning(1, split))
         ms = timeit()
         print("scan%d split %d: %.4f ms  %.0f img/s  whole-step %.3f" % (2 - scan, split, ms, N / ms * 1e3, N * 736 * 1280 * 4 / (ms * 1e-3) / 6546.2e9))

@@ -26,6 +26,22 @@ import test_pse_gpu as tpse  # noqa: E402
 from pytorchocr_b200 import synth  # noqa: E402
 
 
+def _db_variant(rng, kw):
+    """random stage-2 code path (include/ocrpp.h OCRPP_TUNE_DB_PATH / _SCAN) and reference branch (cpp_speedup)"""
+    from pytorchocr_b200 import _lib
+    L = _lib.lib()
+    path = int(rng.choice([0, 1, 2, 3]))
+    scan = int(rng.choice([0, 2]))
+    _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_PATH, path))
+    _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_SCAN, scan))
+    tag = "path%d scan%d" % (path, scan)
+    if rng.random() < 0.4:
+        kw["cpp_speedup"] = False
+        kw["score_mode"] = str(rng.choice(["poly", "box"]))
+        tag += " python/" + kw["score_mode"]
+    return tag
+
+
 def case_db(rng):
     H, W = int(rng.integers(24, 260)), int(rng.integers(24, 400))
     sig = float(rng.choice([0.45, 0.6, 1.0, 1.5, 2.5, 4.0]))
@@ -36,16 +52,19 @@ def case_db(rng):
     kw = dict(thresh=q, box_thresh=q + 0.02, max_unmatched=0)
     if rng.random() < 0.3:
         kw["use_dilation"] = True
+    tag = _db_variant(rng, kw)
     sl = np.array([[H, W, 1.0, 1.0], [int(H * 1.7), int(W * 0.8), 1.7, 0.8]])
     tdb._check(p[:, None], sl, **kw)
-    return "db %dx%d sig=%.2f %s" % (H, W, sig, "dil" if "use_dilation" in kw else "")
+    return "db %dx%d sig=%.2f %s %s" % (H, W, sig, "dil" if "use_dilation" in kw else "", tag)
 
 
 def case_db_synth(rng):
     H, W = int(rng.integers(64, 400)), int(rng.integers(64, 700))
     maps = synth.db_batch(2, seed=int(rng.integers(1 << 30)), H=H, W=W)
-    tdb._check(maps, np.array([[H, W, 1.0, 1.0]] * 2), max_unmatched=0)
-    return "db_synth %dx%d" % (H, W)
+    kw = dict(max_unmatched=0)
+    tag = _db_variant(rng, kw)
+    tdb._check(maps, np.array([[H, W, 1.0, 1.0]] * 2), **kw)
+    return "db_synth %dx%d %s" % (H, W, tag)
 
 
 def case_pse(rng):
