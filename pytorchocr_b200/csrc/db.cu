@@ -906,7 +906,7 @@ __global__ void __launch_bounds__(kRunBlk) db_extents_kernel(DbParams p) {
     }
     // ---- background run ----
     // (a) stair pixel of the OUTER contour of the component to the left: e = (a, y)
-    if (a > 0) {
+    if (a > 0 && p.stairs) {
       const int C = par[r - 1];
       const bool updn = (y > 0 && bv.at(a, y - 1)) || (y < H - 1 && bv.at(a, y + 1));
       if (updn) {
@@ -951,7 +951,7 @@ __global__ void __launch_bounds__(kRunBlk) db_extents_kernel(DbParams p) {
     // (c) o = (b, y) is the last pixel of a hole run, q = (b+1, y) is foreground; for dy in {-1,+1}:
     //     p = (b, y+dy) in C => the hole contour steps diagonally p <-> q and the 4-connected
     //     boundary also paints e = (b+1, y+dy)
-    for (int dy = -1; dy <= 1; dy += 2) {
+    for (int dy = -1; dy <= 1 && p.stairs; dy += 2) {
       if (!in_C(b, y + dy)) continue;
       const int ex = b + 1, ey = y + dy;
       if (dy == -1) {

@@ -221,7 +221,10 @@ def compare_image(boxes, boxes_f, scores, details, tol_px=1e-3, tol_score=1e-5):
                     used.add(hit[0])
                     stats["tie"] += 1
                     stats["unmatched_oracle"] -= 1
-                    assert abs(scores[hit[0]] - ok[i]["score"]) <= tol_score * abs(ok[i]["score"]) + 1e-7
+                    # score_mode "box" scores the mini box, which is a different one on the other side of the tie
+                    assert (ok[i].get("score_mode") == "box" or
+                            abs(scores[hit[0]] - ok[i]["score"]) <= tol_score * abs(ok[i]["score"]) + 1e-7), \
+                        (scores[hit[0]], ok[i]["score"])
                     break
     # what is still unmatched: "explained" when it sits on a discontinuity the oracle's data proves
     stats["explained"] = 0

@@ -26,6 +26,9 @@ import test_pse_gpu as tpse  # noqa: E402
 from pytorchocr_b200 import synth  # noqa: E402
 
 
+LAST_TAG = ""
+
+
 def _db_variant(rng, kw):
     """random stage-2 code path (include/ocrpp.h OCRPP_TUNE_DB_PATH / _SCAN) and reference branch (cpp_speedup)"""
     from pytorchocr_b200 import _lib
@@ -35,10 +38,13 @@ def _db_variant(rng, kw):
     _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_PATH, path))
     _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_SCAN, scan))
     tag = "path%d scan%d" % (path, scan)
+    global LAST_TAG
+    LAST_TAG = tag
     if rng.random() < 0.4:
         kw["cpp_speedup"] = False
         kw["score_mode"] = str(rng.choice(["poly", "box"]))
         tag += " python/" + kw["score_mode"]
+    LAST_TAG = tag
     return tag
 
 
@@ -197,7 +203,7 @@ def main():
             n[case.__name__] = n.get(case.__name__, 0) + 1
         except (AssertionError, pytest.fail.Exception, Exception) as e:  # noqa: B014
             fails.append((case.__name__, seed, repr(e)[:300]))
-            print("FAIL", case.__name__, "seed", seed, repr(e)[:300], flush=True)
+            print("FAIL", case.__name__, "seed", seed, LAST_TAG if "db" in case.__name__ else "", repr(e)[:300], flush=True)
             if not isinstance(e, (AssertionError, pytest.fail.Exception)):
                 traceback.print_exc()
     print("passed:", n, "failed:", len(fails))

@@ -24,7 +24,8 @@ def test_db_batch_256_full_size():
     rng.shuffle(idx)
     maps = torch.from_numpy(uniq).cuda()[torch.from_numpy(idx).cuda()]            # [256,1,736,1280] on the device
     sl = np.array([[H, W, 1.0, 1.0]] * N)
-    cfg = dict(name="DBPostProcess", thresh=0.3, box_thresh=0.5, max_candidates=1000, unclip_ratio=1.7, cuda_speedup=True)
+    cfg = dict(name="DBPostProcess", thresh=0.3, box_thresh=0.5, max_candidates=1000, unclip_ratio=1.7, cpp_speedup=True,
+               cuda_speedup=True)
     op = build_post_process(cfg)
     res = op({"maps": maps}, sl)
     res2 = op({"maps": maps}, sl)
@@ -37,8 +38,8 @@ def test_db_batch_256_full_size():
         pts = np.asarray(res[n]["points"])
         assert 150 <= len(pts) <= 260
         assert pts[..., 0].min() >= 0 and pts[..., 0].max() <= W and pts[..., 1].min() >= 0 and pts[..., 1].max() <= H
-    want = DBPostProcessOracle(thresh=0.3, box_thresh=0.5, unclip_ratio=1.7)({"maps": uniq[:2]}, sl[:2])
-    for u in range(2):
+    want = DBPostProcessOracle(thresh=0.3, box_thresh=0.5, unclip_ratio=1.7, cpp_speedup=True)({"maps": uniq}, sl[:U])
+    for u in range(U):                                        # all 8 distinct maps of the batch against the oracle
         a, b = np.array(first[u]), np.array(_rows(want[u]))
         assert a.shape == b.shape
         diff = np.abs(a - b).max(1)
@@ -93,7 +94,8 @@ def test_ctc_8192_lines():
     # decoding a shard gives the same lines as decoding everything (no cross-line state)
     part = op(probs[:, 4096:4096 + 512].contiguous())
     assert [t for t, _ in part] == [t for t, _ in full[4096:4096 + 512]]
-    sample = probs[:, :256].cpu()
+    sel = np.r_[0:512, 8192 - 512:8192]                        # 1024 lines: both ends of the batch
+    sample = probs[:, torch.from_numpy(sel).cuda()].cpu()
     want = CTCLabelDecodeOracle(d)(sample)
-    assert [t for t, _ in want] == [t for t, _ in full[:256]]
-    assert np.allclose([c for _, c in want], [c for _, c in full[:256]], rtol=1e-6, equal_nan=True)
+    assert [t for t, _ in want] == [full[i][0] for i in sel]
+    assert np.allclose([c for _, c in want], [full[i][1] for i in sel], rtol=1e-6, equal_nan=True)
