@@ -187,7 +187,9 @@ def compare_image(boxes, boxes_f, scores, details, tol_px=1e-3, tol_score=1e-5):
             leaves = mini.min() < 0 or mini[:, 0].max() > width - 1 or mini[:, 1].max() > height - 1
             assert d.get("score_mode") == "box" and ("truncation" in classify(d) or leaves or on_discontinuity(d)), \
                 (scores[j], d["score"])
-            assert abs(scores[j] - d["score"]) <= 0.2 * abs(d["score"]), (scores[j], d["score"])
+            # one column / row of the mask moved: bounded by its share of the mask (tiny boxes: a few dozen pixels)
+            bound = 0.2 if d.get("fill_count", 0) > 60 else 0.6
+            assert abs(scores[j] - d["score"]) <= bound * abs(d["score"]), (scores[j], d["score"], d.get("fill_count"))
             stats["box_score_discontinuity"] = stats.get("box_score_discontinuity", 0) + 1
         ordered = np.abs(of[i] - gf[j]).max()
         if ordered < tol_px:

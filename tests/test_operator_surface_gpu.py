@@ -99,7 +99,8 @@ def _quad_iou(a, b):
 
     def clip(subject, cp):
         out = [tuple(map(float, q)) for q in subject]
-        if np.cross(np.subtract(cp[1], cp[0]), np.subtract(cp[2], cp[1])) < 0:
+        e0, e1 = np.subtract(cp[1], cp[0]), np.subtract(cp[2], cp[1])
+        if e0[0] * e1[1] - e0[1] * e1[0] < 0:
             cp = cp[::-1]
         for i in range(len(cp)):
             a0, a1 = cp[i], cp[(i + 1) % len(cp)]
