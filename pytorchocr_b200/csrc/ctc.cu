@@ -24,7 +24,8 @@ struct Best {
   int i;
 };
 
-__device__ __forceinline__ void upd(Best& b, float v, int i) {
+__device__ __forceinline__ void upd(Best& b, float& acc, float v, int i) {
+  acc += v;   // NaN canary
   if (v > b.v) {
     b.v = v;
     b.i = i;
@@ -37,9 +38,10 @@ struct VecOps;
 template <>
 struct VecOps<float> {
   static constexpr int kElems = 4;
-  __device__ static __forceinline__ void consume(Best& b, const uint4& u, int base) {
+  __device__ static __forceinline__ void consume(Best& b, float& acc, const uint4& u, int base) {
     const float x = __uint_as_float(u.x), y = __uint_as_float(u.y), z = __uint_as_float(u.z),
                 w = __uint_as_float(u.w);
+    acc += (x + y) + (z + w);   // NaN canary (fmaxf drops NaNs); see the end of ctc_argmax_kernel
     const float m = fmaxf(fmaxf(x, y), fmaxf(z, w));
     if (m > b.v) {  // rare after the first few vectors
       b.v = m;
@@ -51,10 +53,11 @@ struct VecOps<float> {
 template <>
 struct VecOps<__half> {
   static constexpr int kElems = 8;
-  __device__ static __forceinline__ void consume(Best& b, const uint4& u, int base) {
+  __device__ static __forceinline__ void consume(Best& b, float& acc, const uint4& u, int base) {
     float f[8] = {h2f_lo(u.x), h2f_hi(u.x), h2f_lo(u.y), h2f_hi(u.y),
                   h2f_lo(u.z), h2f_hi(u.z), h2f_lo(u.w), h2f_hi(u.w)};
     float m = f[0];
+    acc += ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));   // NaN canary
 #pragma unroll
     for (int k = 1; k < 8; ++k) m = fmaxf(m, f[k]);
     if (m > b.v) {
@@ -83,7 +86,8 @@ ctc_argmax_kernel(const T* __restrict__ probs, int Tn, int B, int C, long long s
   int head = (int)(((16u - (unsigned)((uintptr_t)row & 15u)) & 15u) / sizeof(T));
   if (head > C) head = C;
   Best best{-INFINITY, 0x7fffffff};
-  if (lane < head) upd(best, load_scalar<T>(row + lane), lane);
+  float acc = 0.f;   // becomes NaN when the lane has seen a NaN (or +inf and -inf): the row is then re-read below
+  if (lane < head) upd(best, acc, load_scalar<T>(row + lane), lane);
 
   const uint4* vp = reinterpret_cast<const uint4*>(row + head);
   const int nvec = (C - head) / EPV;
@@ -96,7 +100,7 @@ ctc_argmax_kernel(const T* __restrict__ probs, int Tn, int B, int C, long long s
     for (int u = 0; u < kCtcUnroll; ++u) v[u] = ldg_stream_u4(vp + j0 + u * 32 + lane);
 #pragma unroll
     for (int u = 0; u < kCtcUnroll; ++u)
-      VecOps<T>::consume(best, v[u], head + (j0 + u * 32 + lane) * EPV);
+      VecOps<T>::consume(best, acc, v[u], head + (j0 + u * 32 + lane) * EPV);
   }
   {  // ragged last batch
     uint4 v[kCtcUnroll];
@@ -107,9 +111,9 @@ ctc_argmax_kernel(const T* __restrict__ probs, int Tn, int B, int C, long long s
     }
 #pragma unroll
     for (int u = 0; u < kCtcUnroll; ++u)
-      VecOps<T>::consume(best, v[u], head + (j0 + u * 32 + lane) * EPV);
+      VecOps<T>::consume(best, acc, v[u], head + (j0 + u * 32 + lane) * EPV);
   }
-  for (int i = head + nvec * EPV + lane; i < C; i += 32) upd(best, load_scalar<T>(row + i), i);
+  for (int i = head + nvec * EPV + lane; i < C; i += 32) upd(best, acc, load_scalar<T>(row + i), i);
 
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -120,8 +124,22 @@ ctc_argmax_kernel(const T* __restrict__ probs, int Tn, int B, int C, long long s
       best.i = oi;
     }
   }
+  // numpy's argmax / max (rec_postprocess.py:83-84) treat NaN as the maximum: the FIRST NaN wins and the
+  // probability is NaN. Rare: only rows whose canary tripped are read again.
+  if (__any_sync(0xffffffffu, acc != acc)) {
+    int first_nan = 0x7fffffff;
+    for (int i = lane; i < C; i += 32) {
+      const float v = load_scalar<T>(row + i);
+      if (v != v && i < first_nan) first_nan = i;
+    }
+    first_nan = __reduce_min_sync(0xffffffffu, first_nan);
+    if (first_nan != 0x7fffffff) {
+      best.i = first_nan;
+      best.v = __int_as_float(0x7fc00000);
+    }
+  }
   if (lane == 0) {
-    const int bi = best.i == 0x7fffffff ? 0 : best.i;  // all -inf / NaN row: numpy would say 0
+    const int bi = best.i == 0x7fffffff ? 0 : best.i;  // all -inf row: numpy says 0
     const long long o = (long long)b * Tn + t;
     idx_out[o] = bi;
     prob_out[o] = best.v;

@@ -1284,6 +1284,10 @@ void ex_fill(ExParams& p, int mode, int N, int C, int K, int h, int w, int fin, 
 }
 
 // auxiliary streams / events of the current device (created once, never destroyed)
+// The auxiliary streams / events below are shared per device by every instantiation (float, __half) of the pipeline:
+// one fork/join section at a time, guarded by ONE mutex per set.
+std::mutex g_ex_enqueue_mu, g_ex_split_enqueue_mu;
+
 struct ExAux {
   cudaStream_t st[3];
   cudaEvent_t fork, join[3];
@@ -1355,8 +1359,7 @@ int ex_pipeline(ExParams p, int N, cudaStream_t s, bool vec, ProfileScope* prof,
     ExAux* aux = fork ? ex_aux() : nullptr;
     OCRPP_CHECK_ARG(!fork || aux != nullptr, "expand: cannot create auxiliary streams");
     cudaStream_t s1 = s, s2 = s, s3 = s;
-    static std::mutex enqueue_mu;   // the auxiliary streams/events are shared: one fork/join section at a time
-    std::unique_lock<std::mutex> lock(enqueue_mu, std::defer_lock);
+    std::unique_lock<std::mutex> lock(g_ex_enqueue_mu, std::defer_lock);
     if (aux) {
       lock.lock();
       OCRPP_CUDA(cudaEventRecord(aux->fork, s));
@@ -1365,19 +1368,27 @@ int ex_pipeline(ExParams p, int N, cudaStream_t s, bool vec, ProfileScope* prof,
       s2 = aux->st[1];
       s3 = aux->st[2];
     }
+    int frc = OCRPP_OK;   // inside the fork/join section errors are collected: the join must always be enqueued
+    auto launched = [&frc](const char* what) {
+      g_launch_count.fetch_add(1, std::memory_order_relaxed);
+      const cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess && frc == OCRPP_OK) frc = set_error(OCRPP_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+    };
     huge_k<<<kNumSMs, kHugeThreads, ex_smem_bytes(kHugeCap, kListCap), s>>>(p);   // long items first
-    OCRPP_LAUNCHED();
+    launched("ex_expand (huge tiles)");
     big_k<<<kNumSMs * 2, kBigThreads, ex_smem_bytes(kBigCap, kListCap), s1>>>(p);
-    OCRPP_LAUNCHED();
+    launched("ex_expand (big tiles)");
     small_k<<<kNumSMs * 4, kSmallThreads, ex_smem_bytes(kSmallCap, kListCap), s2>>>(p);
-    OCRPP_LAUNCHED();
+    launched("ex_expand (small tiles)");
     tiny_k<<<kNumSMs * 9, kTinyThreads, ex_smem_bytes(kTinyCap, kTinyList), s3>>>(p);
-    OCRPP_LAUNCHED();
+    launched("ex_expand (tiny tiles)");
     if (aux)
       for (int i = 0; i < 3; ++i) {
-        OCRPP_CUDA(cudaEventRecord(aux->join[i], aux->st[i]));
-        OCRPP_CUDA(cudaStreamWaitEvent(s, aux->join[i], 0));
+        cudaEventRecord(aux->join[i], aux->st[i]);
+        cudaStreamWaitEvent(s, aux->join[i], 0);
       }
+    if (frc != OCRPP_OK) return frc;
+    if (debug_sync()) OCRPP_CUDA(cudaDeviceSynchronize());
   }
   if (prof) prof->mark("ex_expand");
   ex_stats_kernel<T, 1><<<rgrid, kRunBlk, 0, s>>>(p);
@@ -1457,20 +1468,20 @@ int ex_launch(ExParams& p, cudaStream_t s, bool vec) {
     ProfileScope prof(s);
     return ex_pipeline<T>(ex_sub_params(p, 0, 1, 0), N, s, vec, &prof, true);
   }
-  static std::mutex enqueue_mu;   // the auxiliary streams/events are shared: one fork/join section at a time
-  std::lock_guard<std::mutex> lock(enqueue_mu);
+  std::lock_guard<std::mutex> lock(g_ex_split_enqueue_mu);
   OCRPP_CUDA(cudaEventRecord(aux->fork, s));
+  int rc = OCRPP_OK;
   for (int i = 0; i < nsplit; ++i) {
     cudaStream_t si = i == 0 ? s : aux->st[i - 1];
-    if (i > 0) OCRPP_CUDA(cudaStreamWaitEvent(si, aux->fork, 0));
+    if (i > 0 && cudaStreamWaitEvent(si, aux->fork, 0) != cudaSuccess) rc = set_error(OCRPP_ERR_CUDA, "expand: cudaStreamWaitEvent failed");
     const int lo = (int)((long long)N * i / nsplit), hi = (int)((long long)N * (i + 1) / nsplit);
-    const int rc = ex_pipeline<T>(ex_sub_params(p, i, nsplit, lo), hi - lo, si, vec, nullptr, false);
-    if (rc != OCRPP_OK) return rc;
-    if (i > 0) {
-      OCRPP_CUDA(cudaEventRecord(aux->join[i - 1], si));
-      OCRPP_CUDA(cudaStreamWaitEvent(s, aux->join[i - 1], 0));
+    if (rc == OCRPP_OK) rc = ex_pipeline<T>(ex_sub_params(p, i, nsplit, lo), hi - lo, si, vec, nullptr, false);
+    if (i > 0) {   // always join, also after a failed launch: the auxiliary stream may still touch the caller's buffers
+      cudaEventRecord(aux->join[i - 1], si);
+      cudaStreamWaitEvent(s, aux->join[i - 1], 0);
     }
   }
+  if (rc != OCRPP_OK) return rc;
   return OCRPP_OK;
 }
 

@@ -140,7 +140,9 @@ class DBPostProcess(object):
                 _lib.check(L.ocrpp_db_postprocess_ex(
                     t.data_ptr(), _lib.F32 if t.dtype == torch.float32 else _lib.F16, N, H, W,
                     t.stride(0), t.stride(2), buf["wh_dev"].data_ptr(),
-                    float(self.thresh), float(self.box_thresh), float(self.unclip_ratio), cap, R,
+                    # numpy evaluates `pred > self.thresh` in the dtype of the map (db_postprocess.py:46)
+                    float(np.float16(self.thresh)) if t.dtype == torch.float16 else float(self.thresh),
+                    float(self.box_thresh), float(self.unclip_ratio), cap, R,
                     1 if self.use_dilation else 0, 1 if use_padding_resize else 0,
                     _lib.DB_SEMANTICS_CPP if self.cpp_speedup else _lib.DB_SEMANTICS_PYTHON,
                     _lib.DB_SCORE_BOX if (self.score_mode == "box" and not self.cpp_speedup) else _lib.DB_SCORE_POLY,

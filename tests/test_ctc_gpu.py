@@ -133,3 +133,25 @@ def test_cls_postprocess_matches_reference_semantics(B, C, dtype):
     assert np.array_equal(np.array([g[1] for g in got], np.float32), np.array([w[1] for w in want], np.float32))
     out, lab = op(x, label=[1, 0])
     assert lab == [(labels[1], 1.0), (labels[0], 1.0)] and len(out) == B
+
+
+def test_ctc_nan_rows_follow_numpy(dict_path):
+    """numpy's argmax / max (rec_postprocess.py:83-84) treat NaN as the maximum: the FIRST NaN of a row wins and the
+    probability (and with it the line's confidence) is NaN; +inf and -inf in one row are not NaN."""
+    import torch
+    op, oracle, _ = _ops(dict_path)
+    T, B, C = 12, 5, 6623
+    rng = np.random.default_rng(8)
+    p = rng.random((T, B, C)).astype(np.float32)
+    p[3, 0, 4000] = np.nan; p[3, 0, 17] = np.nan        # two NaNs: index 17
+    p[5, 1, 0] = np.nan                                 # NaN on the blank class
+    p[:, 2, 123] = 5.0; p[7, 2, 6622] = np.nan          # NaN in the scalar tail of the row
+    p[2, 3, 9] = np.inf; p[2, 3, 10] = -np.inf          # inf - inf trips the canary, but there is no NaN
+    p[:, 4, 1] = 2.0; p[0, 4, 2] = np.nan               # NaN among the head elements
+    for dt in (np.float32, np.float16):
+        x = p.astype(dt)
+        got = op(torch.from_numpy(x).cuda())
+        want = oracle(torch.from_numpy(x))
+        assert [g[0] for g in got] == [w[0] for w in want], dt
+        assert np.allclose([g[1] for g in got], [w[1] for w in want], rtol=2e-3 if dt == np.float16 else 1e-6, equal_nan=True)
+    assert math.isnan(got[0][1]) and not math.isnan(got[3][1])
