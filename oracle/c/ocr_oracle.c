@@ -199,8 +199,9 @@ void oracle_ctc_greedy(const float* probs, int T, int B, int C, int64_t stride_t
       const float* row = probs + t * stride_t + b * stride_b;
       int32_t best = 0;
       float bv = row[0];
-      for (int c = 1; c < C; ++c)
-        if (row[c] > bv) { bv = row[c]; best = c; }
+      /* numpy's argmax / max (rec_postprocess.py:83-84): NaN is the maximum and the FIRST NaN wins */
+      for (int c = 1; c < C && bv == bv; ++c)
+        if (row[c] > bv || row[c] != row[c]) { bv = row[c]; best = c; }
       if (raw_idx_out) raw_idx_out[(int64_t)b * T + t] = best;
       if (best != 0 && !(t > 0 && prev == best)) {
         idx_out[(int64_t)b * T + n] = best;
