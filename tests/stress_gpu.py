@@ -173,7 +173,9 @@ def case_db_fp16(rng):
     big = torch.zeros((2, 1, H + 2, W + 8), dtype=torch.float16, device="cuda")     # strided half view
     big[:, :, 1:H + 1, 8:W + 8] = torch.from_numpy(maps).cuda().half()
     dev = big[:, :, 1:H + 1, 8:W + 8]
-    tdb._check(dev, np.array([[H, W, 1.0, 1.0]] * 2), oracle_maps=dev.float().cpu().numpy(), max_unmatched=0)
+    # the oracle gets the float16 array itself, as the reference does (`pred.detach().cpu().numpy()`): numpy then
+    # evaluates `pred > thresh` in float16
+    tdb._check(dev, np.array([[H, W, 1.0, 1.0]] * 2), oracle_maps=dev.cpu().numpy(), max_unmatched=0)
     return "db_fp16 %dx%d" % (H, W)
 
 
