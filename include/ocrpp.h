@@ -77,7 +77,8 @@ OCRPP_API void ocrpp_reset_launch_count(void);
                                 * 3 run-parallel multi-kernel chain (what large images take) */
 #define OCRPP_TUNE_DB_SPLIT 1  /* sub-batch pipelines of one DB call (0 = chosen from the batch size) */
 #define OCRPP_TUNE_DB_PRIO 2   /* 1: sub-batch pipelines without stream priorities */
-#define OCRPP_TUNE_DB_SCAN 3   /* 2: the two-phase map scan (db_scan2_kernel) in front of the one-kernel stage 2 */
+#define OCRPP_TUNE_DB_SCAN 3   /* 2: the two-phase map scan in front of the one-kernel stage 2 (db_scan3_kernel where the
+                                * width has a compile-time specialisation, else db_scan2_kernel); 3: db_scan2_kernel only */
 #define OCRPP_TUNE_COUNT 8
 OCRPP_API int ocrpp_set_tuning(int key, int value);
 

@@ -108,6 +108,10 @@ __device__ __forceinline__ float load_px(const void* maps, long long off) {
 // into a per-row segment (one 64-bit entry per run: x << 48 | cumulative sum) of fixed capacity (row_cap runs; overflow is flagged and the caller retries).
 // ------------------------------------------------------------------------------------------------
 constexpr int kBinWarps = 8;
+#ifndef OCRPP_SCAN_MIN_CTAS
+#define OCRPP_SCAN_MIN_CTAS 4
+#endif
+constexpr int kScanMinCtas = OCRPP_SCAN_MIN_CTAS;   // resident CTAs per SM the scan kernel is compiled for (register cap)
 
 template <typename T, int kEpl>
 struct RowLoader;
@@ -266,7 +270,7 @@ __device__ __forceinline__ void db_scan_group(const DbParams& p, const float* v,
 }
 
 template <typename T, int kEpl, int kU = 4, bool kDilate = false>
-__global__ void __launch_bounds__(kBinWarps * 32) db_scan_kernel(DbParams p) {
+__global__ void __launch_bounds__(kBinWarps * 32, kScanMinCtas) db_scan_kernel(DbParams p) {
   const int n = blockIdx.y + p.n0;
   const int y = blockIdx.x * kBinWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -487,6 +491,156 @@ __global__ void __launch_bounds__(kScan2Warps * 32) db_scan2_kernel(DbParams p, 
     if (total_cnt <= p.cap) sc[total_cnt] = total_sum;
   }
   if (__any_sync(0xffffffffu, worst > 0x800000u) && lane == 0) atomicOr(&p.imgflags[n], OCRPP_IMG_VALUE_OUT_OF_RANGE);
+}
+
+// K1'': db_scan2_kernel specialised at compile time for rows of exactly kC full groups (W == 32 * kEpl * kC, e.g. 1280
+// float32 pixels: kC = 10): no bounds predicates, constant shared-memory offsets, unrolled chunk sums.
+template <typename T, int kEpl, int kC>
+__global__ void __launch_bounds__(kScan2Warps * 32) db_scan3_kernel(DbParams p) {
+  extern __shared__ __align__(16) uint32_t s_scan[];
+  constexpr int kRowWords = (32 * kC * kEpl + 32 * kC + (kC + 1) * kEpl + 3) & ~3;
+  const int n = blockIdx.y + p.n0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int y = blockIdx.x * kScan2Warps + warp;
+  if (y >= p.H) return;
+  uint32_t* uval = s_scan + (size_t)warp * kRowWords;   // [32*kC*kEpl] pixel values, 2^-23 units
+  uint32_t* csum = uval + 32 * kC * kEpl;                // [32*kC] cell sums
+  uint32_t* bits = csum + 32 * kC;                       // [(kC+1)*kEpl] ballot words, g-major
+  const T* row = reinterpret_cast<const T*>(p.maps) + n * p.stride_n + y * p.stride_h;
+  const size_t rowid = (size_t)n * p.H + y;
+  unsigned long long* sc = p.scum + rowid * (p.cap + 1);
+  const uint4* vp = reinterpret_cast<const uint4*>(row) + lane;
+  const float thresh = p.thresh;
+  unsigned worst = 0;
+
+  // ---- phase 1: stream the row ----
+  if (lane < kEpl) bits[kC * kEpl + lane] = 0u;
+  constexpr int U = kC <= 10 ? kC : (kC % 5 == 0 ? 5 : (kC % 4 == 0 ? 4 : 1));   // loads in flight per lane: the whole row when it fits
+#pragma unroll
+  for (int g0 = 0; g0 < kC; g0 += U) {
+    uint4 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) raw[u] = ldg_stream_u4(vp + (g0 + u) * 32);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int g = g0 + u;
+      float f[kEpl];
+      if (kEpl == 4) {
+        f[0] = __uint_as_float(raw[u].x); f[1 % kEpl] = __uint_as_float(raw[u].y);
+        f[2 % kEpl] = __uint_as_float(raw[u].z); f[3 % kEpl] = __uint_as_float(raw[u].w);
+      } else {
+        f[0] = h2f_lo(raw[u].x); f[1 % kEpl] = h2f_hi(raw[u].x); f[2 % kEpl] = h2f_lo(raw[u].y); f[3 % kEpl] = h2f_hi(raw[u].y);
+        f[4 % kEpl] = h2f_lo(raw[u].z); f[5 % kEpl] = h2f_hi(raw[u].z); f[6 % kEpl] = h2f_lo(raw[u].w); f[7 % kEpl] = h2f_hi(raw[u].w);
+      }
+      unsigned q[kEpl], m[kEpl], run = 0;
+#pragma unroll
+      for (int k = 0; k < kEpl; ++k) {
+        m[k] = __ballot_sync(0xffffffffu, f[k] > thresh);
+        q[k] = __float_as_uint(f[k] + 1.0f) - 0x3f800000u;   // round(f * 2^23) for f in [0,1], > 2^23 otherwise
+        worst = max(worst, q[k]);
+        run += q[k];
+      }
+      uint4* uv = reinterpret_cast<uint4*>(uval + (g * 32 + lane) * kEpl);
+      uv[0] = make_uint4(q[0], q[1 % kEpl], q[2 % kEpl], q[3 % kEpl]);
+      if (kEpl == 8) uv[1] = make_uint4(q[4 % kEpl], q[5 % kEpl], q[6 % kEpl], q[7 % kEpl]);
+      csum[g * 32 + lane] = run;
+      if (lane == 0) {
+        uint4* bw = reinterpret_cast<uint4*>(bits + g * kEpl);
+        bw[0] = make_uint4(m[0], m[1 % kEpl], m[2 % kEpl], m[3 % kEpl]);
+        if (kEpl == 8) bw[1] = make_uint4(m[4 % kEpl], m[5 % kEpl], m[6 % kEpl], m[7 % kEpl]);
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- phase 2: lane owns cells [c0, c0 + kC), pixels [c0 * kEpl, ...) ----
+  const int c0 = kC * lane;
+  constexpr unsigned vmask = kC >= 32 ? 0xffffffffu : ((1u << kC) - 1u);
+  unsigned F[kEpl], Tm[kEpl];
+  {
+    const int w0 = c0 >> 5, sh = c0 & 31;
+#pragma unroll
+    for (int k = 0; k < kEpl; ++k)
+      F[k] = __funnelshift_r(bits[w0 * kEpl + k], bits[(w0 + 1) * kEpl + k], sh) & vmask;
+  }
+  unsigned prevbit = __shfl_up_sync(0xffffffffu, (F[kEpl - 1] >> (kC - 1)) & 1u, 1);
+  if (lane == 0) prevbit = F[0] & 1u;
+  int cnt_l = 0;
+  unsigned cellmask = 0;
+#pragma unroll
+  for (int k = 0; k < kEpl; ++k) {
+    const unsigned prev = k == 0 ? ((F[kEpl - 1] << 1) | prevbit) : F[k - 1];
+    Tm[k] = (F[k] ^ prev) & vmask;
+    cnt_l += __popc(Tm[k]);
+    cellmask |= Tm[k];
+  }
+  unsigned acc = 0;
+#pragma unroll
+  for (int i = 0; i < kC; ++i) acc += csum[c0 + i];
+  int pos = cnt_l;
+  unsigned long long base = acc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int tp = __shfl_up_sync(0xffffffffu, pos, o);
+    const unsigned long long tb = __shfl_up_sync(0xffffffffu, base, o);
+    if (lane >= o) {
+      pos += tp;
+      base += tb;
+    }
+  }
+  const int total_cnt = __shfl_sync(0xffffffffu, pos, 31) + 1;          // run 0 starts at x = 0
+  const unsigned long long total_sum = __shfl_sync(0xffffffffu, base, 31);
+  pos -= cnt_l;     // exclusive
+  base -= acc;
+  for (unsigned rest = cellmask; rest; rest &= rest - 1) {
+    const int i = __ffs(rest) - 1;
+    const unsigned below = (1u << i) - 1u;
+    int j = 1 + pos;
+#pragma unroll
+    for (int k = 0; k < kEpl; ++k) j += __popc(Tm[k] & below);
+    unsigned long long cb = base;
+    for (int q = 0; q < i; ++q) cb += csum[c0 + q];
+    const uint32_t* uv = uval + (size_t)(c0 + i) * kEpl;
+    unsigned within = 0;
+#pragma unroll
+    for (int k = 0; k < kEpl; ++k) {
+      if ((Tm[k] >> i) & 1u) {
+        if (j < p.cap) sc[j] = ((unsigned long long)((c0 + i) * kEpl + k) << 48) | (cb + within);
+        ++j;
+      }
+      within += uv[k];
+    }
+  }
+  if (lane == 0) {
+    sc[0] = 0ull;
+    p.srow_cnt[rowid] = total_cnt | ((F[0] & 1u) << 31);
+    if (total_cnt <= p.cap) sc[total_cnt] = total_sum;
+  }
+  if (__any_sync(0xffffffffu, worst > 0x800000u) && lane == 0) atomicOr(&p.imgflags[n], OCRPP_IMG_VALUE_OUT_OF_RANGE);
+}
+
+template <typename T, int kEpl, int kC>
+int launch_scan3(const DbParams& p, dim3 grid, cudaStream_t s) {
+  constexpr int kRowWords = (32 * kC * kEpl + 32 * kC + (kC + 1) * kEpl + 3) & ~3;
+  constexpr int smem = kScan2Warps * kRowWords * (int)sizeof(uint32_t);
+  OCRPP_CUDA(cudaFuncSetAttribute(db_scan3_kernel<T, kEpl, kC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  db_scan3_kernel<T, kEpl, kC><<<grid, kScan2Warps * 32, smem, s>>>(p);
+  return OCRPP_OK;
+}
+
+// rows of exactly C full groups for which a specialisation exists (640 / 1024 / 1280 / 1920 / 2560 float32 pixels)
+template <typename T, int kEpl>
+int launch_scan3_any(const DbParams& p, int C, dim3 grid, cudaStream_t s, bool* done) {
+  *done = true;
+  switch (C) {
+    case 4: return launch_scan3<T, kEpl, 4>(p, grid, s);
+    case 5: return launch_scan3<T, kEpl, 5>(p, grid, s);
+    case 8: return launch_scan3<T, kEpl, 8>(p, grid, s);
+    case 10: return launch_scan3<T, kEpl, 10>(p, grid, s);
+    case 15: return launch_scan3<T, kEpl, 15>(p, grid, s);
+    case 20: return launch_scan3<T, kEpl, 20>(p, grid, s);
+    default: *done = false; return OCRPP_OK;
+  }
 }
 
 // pixel (x,y) of the lane-major bit mask written by db_scan_kernel
@@ -1572,7 +1726,7 @@ int db_pipeline(DbParams p, int N, int dtype, cudaStream_t s_scan, cudaStream_t 
   // DESIGN.md): needs the vector layout, no dilation, a consumer that does not read the global bit mask (the
   // one-kernel stage 2) and a row that fits the warp's shared-memory slice
   const int scan2_C = (p.W / epl + 31) / 32;
-  const bool scan2 = fused && vec && !p.dilate && scan2_C <= 32 && tuning(OCRPP_TUNE_DB_SCAN) == 2 &&
+  const bool scan2 = fused && vec && !p.dilate && scan2_C <= 32 && tuning(OCRPP_TUNE_DB_SCAN) >= 2 &&
                      kScan2Warps * scan2_row_words(scan2_C, epl) * sizeof(uint32_t) <= 100 * 1024;
   {
     dim3 grid((p.H + kBinWarps - 1) / kBinWarps, N);
@@ -1596,6 +1750,14 @@ int db_pipeline(DbParams p, int N, int dtype, cudaStream_t s_scan, cudaStream_t 
     } else if (scan2) {
       const int smem = kScan2Warps * scan2_row_words(scan2_C, epl) * (int)sizeof(uint32_t);
       dim3 grid2((p.H + kScan2Warps - 1) / kScan2Warps, N);
+      bool done = false;
+      if (p.W == 32 * epl * scan2_C && tuning(OCRPP_TUNE_DB_SCAN) != 3) {   // compile-time specialisation for this width
+        const int rc = dtype == OCRPP_F32 ? launch_scan3_any<float, 4>(p, scan2_C, grid2, s_scan, &done)
+                                          : launch_scan3_any<__half, 8>(p, scan2_C, grid2, s_scan, &done);
+        if (rc != OCRPP_OK) return rc;
+      }
+      if (done) {
+      } else
       if (dtype == OCRPP_F32) {
         OCRPP_CUDA(cudaFuncSetAttribute(db_scan2_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         db_scan2_kernel<float, 4><<<grid2, kScan2Warps * 32, smem, s_scan>>>(p, scan2_C);
