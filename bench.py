@@ -923,6 +923,15 @@ def run_ours(args):
         results.append(measure(wl, args, steps, L, torch, dist, dev, local_rank, world, sampler))
         wl.release()
     h2d = h2d_probe(torch, dist, dev, local_rank, world)
+    # every rank's own clock summary (a rank that is slower than the others at identical kernels is usually a GPU
+    # that sat at a lower SM clock under its power cap): median SM MHz and a bit mask of the reasons seen
+    mine = sampler.summary()
+    bits = sum(b for nm, b in (("hw_slowdown", 1), ("hw_thermal_slowdown", 2), ("sw_thermal_slowdown", 4), ("sw_power_cap", 8))
+               if nm in mine.get("reasons", []))
+    ck = torch.tensor([mine.get("sm_mhz") or 0.0, float(bits)], dtype=torch.float64, device=dev)
+    cks = [ck.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(cks, ck)
 
     if rank == 0:
         head = results[0]
@@ -935,6 +944,8 @@ def run_ours(args):
             "gpu_launches": head["gpu_launches"], "ms_per_step_by_rank": head["ms_per_step_by_rank"],
             "h2d_gbs_by_rank": h2d, "host_cores_per_rank": pinned,
             "clocks": sampler.summary(),
+            "sm_mhz_by_rank": [float(x[0]) for x in cks],
+            "clock_reason_bits_by_rank": [int(x[1]) for x in cks],   # 1 hw_slowdown 2 hw_thermal 4 sw_thermal 8 sw_power_cap
         }
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
