@@ -19,7 +19,7 @@ q = float(np.quantile(maps.cpu().numpy(), 0.5))
 import os
 for path in ([int(os.environ["ONLY_PATH"])] if "ONLY_PATH" in os.environ else (1, 2, 3)):
     _lib.check(L.ocrpp_set_tuning(0, path))
-    op = build_post_process({"name": "DBPostProcess", "thresh": q, "box_thresh": q + 0.02, "unclip_ratio": 1.7, "cuda_speedup": True})
+    op = build_post_process({"name": "DBPostProcess", "thresh": q, "box_thresh": q + 0.02, "unclip_ratio": 1.7, "cpp_speedup": True, "cuda_speedup": True})
     ref = None
     bad = 0
     for it in range(int(sys.argv[1]) if len(sys.argv) > 1 else 300):

@@ -4,7 +4,7 @@ from pytorchocr_b200 import synth
 from pytorchocr_b200.postprocess import build_post_process
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 maps = torch.from_numpy(synth.db_batch(8)).cuda().repeat((N + 7) // 8, 1, 1, 1)[:N].contiguous()
-op = build_post_process({"name": "DBPostProcess", "thresh": 0.3, "box_thresh": 0.5, "unclip_ratio": 1.7, "cuda_speedup": True})
+op = build_post_process({"name": "DBPostProcess", "thresh": 0.3, "box_thresh": 0.5, "unclip_ratio": 1.7, "cpp_speedup": True, "cuda_speedup": True})
 sl = np.array([[736, 1280, 1.0, 1.0]] * N)
 for it in range(3):
     boxes, scores, counts, status, ex = op.run_device(maps, sl, boxes_f=True)

@@ -7,7 +7,7 @@ L = _lib.lib()
 N = 256
 base = torch.from_numpy(synth.db_batch(16)).cuda()
 maps = base.repeat(N // 16, 1, 1, 1).contiguous()
-op = build_post_process({"name": "DBPostProcess", "thresh": 0.3, "box_thresh": 0.5, "unclip_ratio": 1.7, "cuda_speedup": True})
+op = build_post_process({"name": "DBPostProcess", "thresh": 0.3, "box_thresh": 0.5, "unclip_ratio": 1.7, "cpp_speedup": True, "cuda_speedup": True})
 sl = np.array([[736, 1280, 1.0, 1.0]] * N)
 op.run_device(maps, sl)
 buf = next(iter(op._cache.values())); key = next(iter(op._cache))
