@@ -53,6 +53,15 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
   return r;
 }
 
+// the same, pinned in program order (the compiler may otherwise sink a batch of prefetching loads to their uses)
+__device__ __forceinline__ uint4 ldg_stream_u4_ordered(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
 __device__ __forceinline__ float h2f_lo(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u & 0xffffu))); }
 __device__ __forceinline__ float h2f_hi(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u >> 16))); }
 

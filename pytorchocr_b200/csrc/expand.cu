@@ -115,7 +115,10 @@ constexpr int kTinyCap = 4096;    // expansion, tiny tiles: pixels of the padded
 constexpr int kSmallCap = 7936;   // small tiles (4 CTAs of 47 KB per SM)
 constexpr int kBigCap = 18432;    // big tiles (merged text regions): 2 CTAs of 88 KB per SM
 
-template <typename T, bool kVec>
+// kPre: 128-pixel groups whose loads are issued before the first of them is processed. With K channels a lane has
+// K 128-bit loads in flight per group: 7 for PSE, but only 2 for PAN (3.5 KB vs 1 KB per warp) - too little
+// memory-level parallelism to stream at the HBM rate, so few-channel inputs prefetch four groups (kKmax = 2).
+template <typename T, bool kVec, int kPre, int kKmax>
 __global__ void __launch_bounds__(kBinWarps * 32) ex_binarize_kernel(ExParams p) {
   const int n = blockIdx.y + p.n0;
   const int y = blockIdx.x * kBinWarps + (threadIdx.x >> 5);
@@ -127,23 +130,33 @@ __global__ void __launch_bounds__(kBinWarps * 32) ex_binarize_kernel(ExParams p)
   const int K = p.K;
   unsigned tprev = 0, sprev = 0;   // last word of the previous 128-pixel group (run starts need its top bit)
   int tcnt = 0, scnt = 0;          // run starts of this row, counted by the lanes that own a word
-  for (int x0 = 0; x0 < p.W; x0 += 128) {
+  for (int xb = 0; xb < p.W; xb += 128 * kPre) {
+    uint4 v[kPre][kKmax];
+    if (kVec) {  // fin == 1, float rows 16-byte aligned, W % 4 == 0
+#pragma unroll
+      for (int u = 0; u < kPre; ++u) {
+        const int x = xb + u * 128 + lane * 4;
+        const float* base = reinterpret_cast<const float*>(p.maps) + n * p.stride_n + (long long)y * p.stride_h + x;
+#pragma unroll
+        for (int k = 0; k < kKmax; ++k)
+          if (k < K && x < p.W) v[u][k] = kPre > 1 ? ldg_stream_u4_ordered(base + k * p.stride_c) : ldg_stream_u4(base + k * p.stride_c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) {
+    const int x0 = xb + u * 128;
+    if (x0 >= p.W) break;
     const int x = x0 + lane * 4;
     unsigned b[4] = {0u, 0u, 0u, 0u};
     if (x < p.W) {
-      if (kVec) {  // fin == 1, float rows 16-byte aligned, W % 4 == 0
-        const float* base = reinterpret_cast<const float*>(p.maps) + n * p.stride_n + (long long)y * p.stride_h + x;
-        uint4 v[kMaxK];
+      if (kVec) {
 #pragma unroll
-        for (int k = 0; k < kMaxK; ++k)
-          if (k < K) v[k] = ldg_stream_u4(base + k * p.stride_c);
-#pragma unroll
-        for (int k = 0; k < kMaxK; ++k)
+        for (int k = 0; k < kKmax; ++k)
           if (k < K) {
-            b[0] |= (__uint_as_float(v[k].x) > p.thresh ? 1u : 0u) << k;
-            b[1] |= (__uint_as_float(v[k].y) > p.thresh ? 1u : 0u) << k;
-            b[2] |= (__uint_as_float(v[k].z) > p.thresh ? 1u : 0u) << k;
-            b[3] |= (__uint_as_float(v[k].w) > p.thresh ? 1u : 0u) << k;
+            b[0] |= (__uint_as_float(v[u][k].x) > p.thresh ? 1u : 0u) << k;
+            b[1] |= (__uint_as_float(v[u][k].y) > p.thresh ? 1u : 0u) << k;
+            b[2] |= (__uint_as_float(v[u][k].z) > p.thresh ? 1u : 0u) << k;
+            b[3] |= (__uint_as_float(v[u][k].w) > p.thresh ? 1u : 0u) << k;
           }
       } else {
 #pragma unroll
@@ -189,6 +202,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) ex_binarize_kernel(ExParams p)
     }
     tprev = __shfl_sync(0xffffffffu, tw, 24);
     sprev = __shfl_sync(0xffffffffu, sw, 24);
+    }
   }
   tcnt = __reduce_add_sync(0xffffffffu, tcnt);
   scnt = __reduce_add_sync(0xffffffffu, scnt);
@@ -1317,8 +1331,9 @@ template <typename T>
 int ex_pipeline(ExParams p, int N, cudaStream_t s, bool vec, ProfileScope* prof, bool fork) {
   {
     dim3 grid((p.H + kBinWarps - 1) / kBinWarps, N);
-    if (vec) ex_binarize_kernel<T, true><<<grid, kBinWarps * 32, 0, s>>>(p);
-    else ex_binarize_kernel<T, false><<<grid, kBinWarps * 32, 0, s>>>(p);
+    if (vec && p.K <= 2) ex_binarize_kernel<T, true, 4, 2><<<grid, kBinWarps * 32, 0, s>>>(p);
+    else if (vec) ex_binarize_kernel<T, true, 1, kMaxK><<<grid, kBinWarps * 32, 0, s>>>(p);
+    else ex_binarize_kernel<T, false, 1, kMaxK><<<grid, kBinWarps * 32, 0, s>>>(p);
     OCRPP_LAUNCHED();
     if (prof) prof->mark("ex_binarize");
   }
