@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(kScan2Warps * 32) db_scan3_kernel(DbParams p) 
   for (int g0 = 0; g0 < kC; g0 += U) {
     uint4 raw[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) raw[u] = ldg_stream_u4(vp + (g0 + u) * 32);
+    for (int u = 0; u < U; ++u) raw[u] = ldg_stream_u4_ordered(vp + (g0 + u) * 32);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int g = g0 + u;

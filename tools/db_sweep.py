@@ -25,7 +25,7 @@ def timeit(k=20):
     e0.record(); [step() for _ in range(k)]; e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / k
 _lib.check(L.ocrpp_set_tuning(2, 1))
-for scan in (0,):
+for scan in (0, 2):
     _lib.check(L.ocrpp_set_tuning(3, scan))
     for split in (1, 2):
         _lib.check(L.ocrpp_set_tuning(1, split))
