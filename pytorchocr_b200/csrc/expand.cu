@@ -606,19 +606,36 @@ __device__ bool ex_expand_tile(const ExParams& p, const ExItem& it, unsigned cha
   const uint8_t* kb = p.kb + (size_t)it.n * H * W;
   uint32_t* st = p.st + (size_t)it.n * H * W;
   // load the tile (rows are contiguous in global memory; both loads are issued unconditionally)
+  // (four 32-pixel chunks per step, all eight loads in flight before the first cell is written: a big tile is
+  // hundreds of steps per warp and each used to wait for its own two loads)
+  constexpr int kLoadU = 4;
   for (int ty = warp; ty < th; ty += nwarps) {
     const int gy = it.y0 - 1 + ty;
-    for (int tx = lane; tx < tw; tx += 32) {
-      uint32_t c = 0;
-      if (ty > 0 && ty < th - 1 && tx > 0 && tx < tw - 1) {   // interior = inside the image
-        const size_t g = (size_t)gy * W + (it.x0 - 1 + tx);
-        const unsigned kv = kb[g];
-        const uint32_t sv = __ldcg(st + g);                    // garbage where kv has no text bit
-        if (kv & 1u)
-          c = (kv << 24) | (is_labelled(sv) ? (kCellLabel | ((sv & kGateBit) ? kCellGated : 0u) | (sv & kCellLabMask))
-                                            : kCellUnset);
+    const bool row_in = ty > 0 && ty < th - 1;
+    for (int tx0 = lane; tx0 < tw; tx0 += 32 * kLoadU) {
+      unsigned kv[kLoadU];
+      uint32_t sv[kLoadU];
+#pragma unroll
+      for (int u = 0; u < kLoadU; ++u) {
+        const int tx = tx0 + 32 * u;
+        kv[u] = 0u;
+        sv[u] = 0u;
+        if (row_in && tx > 0 && tx < tw - 1) {   // interior = inside the image
+          const size_t g = (size_t)gy * W + (it.x0 - 1 + tx);
+          kv[u] = kb[g];
+          sv[u] = __ldcg(st + g);                // garbage where kv has no text bit
+        }
       }
-      cell[ty * tw + tx] = c;
+#pragma unroll
+      for (int u = 0; u < kLoadU; ++u) {
+        const int tx = tx0 + 32 * u;
+        if (tx >= tw) break;
+        uint32_t c = 0;
+        if (kv[u] & 1u)
+          c = (kv[u] << 24) | (is_labelled(sv[u]) ? (kCellLabel | ((sv[u] & kGateBit) ? kCellGated : 0u) | (sv[u] & kCellLabMask))
+                                                  : kCellUnset);
+        cell[ty * tw + tx] = c;
+      }
     }
   }
   __syncthreads();
@@ -671,6 +688,102 @@ __device__ bool ex_expand_tile(const ExParams& p, const ExItem& it, unsigned cha
     uint16_t* nxt = X;
     const uint32_t lvl_bit = 0x01000000u << level;
     while (nw > 0) {
+      if (nw <= 32) {
+        // Small frontier (the long tail of thin / merged components, where a wave is a handful of pixels): warp 0
+        // runs the waves alone, with warp-level synchronisation and a shuffle prefix, for as long as they fit a
+        // warp - a wave then costs a few hundred cycles instead of three block barriers. Same claims, same order.
+        __shared__ int s_small[5];
+        if (warp == 0) {
+          const uint16_t* w_ = wave;
+          uint16_t* n_ = nxt;
+          int nw_ = nw, nqn_ = nqn;
+          bool over = false;
+          while (nw_ > 0 && nw_ <= 32) {
+            const int r = lane;
+            const bool active = r < nw_;
+            int q = 0;
+            uint32_t lab = 0;
+            if (active) {
+              q = w_[r];
+              lab = cell[q] & (kCellLabMask | kCellGated);
+              const bool gated = (lab & kCellGated) != 0;
+              ExMean mean{};
+              if (gated) mean = ex_mean_emb(p, so + (lab & kCellLabMask) - 1);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int t = q + nb4[j];
+                const uint32_t c = reinterpret_cast<volatile uint32_t*>(cell)[t];
+                if (!(c & lvl_bit) || cell_labelled(c)) continue;
+                if (gated) {
+                  const int ty = t / tw, tx = t - ty * tw;
+                  if (ex_gate_blocks<T>(p, it.n, mean, it.y0 - 1 + ty, it.x0 - 1 + tx)) continue;
+                }
+                atomicMin(cell + t, (c & 0xff000000u) | (uint32_t)(r * 4 + j));
+              }
+            }
+            __syncwarp();
+            unsigned win = 0;
+            bool alive = false;
+            if (active) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t c = reinterpret_cast<volatile uint32_t*>(cell)[q + nb4[j]];
+                if (!(c & 0x01000000u)) continue;
+                const uint32_t pay = c & 0x00ffffffu;
+                if (pay == kCellUnset) alive = true;
+                else if (pay == (uint32_t)(r * 4 + j)) win |= 1u << j;
+              }
+            }
+            const bool requeue = active && win == 0 && alive;
+            const int mine = __popc(win);
+            int inc = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int t = __shfl_up_sync(0xffffffffu, inc, o);
+              if (lane >= o) inc += t;
+            }
+            const int totw = __shfl_sync(0xffffffffu, inc, 31);
+            const unsigned rq = __ballot_sync(0xffffffffu, requeue);
+            if (totw > kListCap || nqn_ + __popc(rq) > kListCap) {
+              over = true;
+              break;
+            }
+            if (active) {
+              int pos = inc - mine;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (win & (1u << j)) {
+                  const int t = q + nb4[j];
+                  n_[pos++] = (uint16_t)t;
+                  cell[t] = (cell[t] & 0xff000000u) | kCellLabel | kCellClaimed | lab;
+                }
+              if (requeue) Qn[nqn_ + __popc(rq & ((1u << lane) - 1u))] = (uint16_t)q;
+            }
+            nqn_ += __popc(rq);
+            __syncwarp();
+            w_ = n_;
+            nw_ = totw;
+            n_ = (n_ == X) ? Y : X;
+          }
+          if (lane == 0) {
+            s_small[0] = nw_;
+            s_small[1] = nqn_;
+            s_small[2] = w_ == X ? 1 : (w_ == Y ? 2 : 0);
+            s_small[3] = n_ == X ? 1 : 2;
+            s_small[4] = over ? 1 : 0;
+          }
+        }
+        __syncthreads();
+        const int sw = s_small[2];
+        nw = s_small[0];
+        nqn = s_small[1];
+        if (sw) wave = sw == 1 ? X : Y;
+        nxt = s_small[3] == 1 ? X : Y;
+        const bool over = s_small[4] != 0;
+        __syncthreads();   // s_small may be rewritten by the next small phase
+        if (over) return false;
+        continue;
+      }
       int nn = 0;
       for (int c0 = 0; c0 < nw; c0 += kExThreads) {
         const int r = c0 + tid;
