@@ -294,9 +294,12 @@ class DetWorkload(Workload):
     def d2h_bytes(self):
         return int(self.buf["out_host"].numel())
 
-    def config(self):
-        return {"batch_per_gpu": self.batch, "H": H, "W": W, "input": list(self.dev_maps.shape[1:]) + [str(self.dev_maps.dtype)],
-                "boxes_per_step_rank0": self.n_boxes, "l2": self.l2_note(),
+    def public_config(self):
+        """The workload as both arms name it (identical dicts in `config` of our line and of --impl reference)."""
+        return {"batch_per_gpu": self.batch, "H": H, "W": W, "l2": self.l2_note()}
+
+    def detail(self):
+        return {"input": list(self.dev_maps.shape[1:]) + [str(self.dev_maps.dtype)], "boxes_per_step_rank0": self.n_boxes,
                 "timed_region": "device maps -> boxes/scores/counts in pinned host memory"}
 
     def l2_note(self):
@@ -563,11 +566,13 @@ class CtcWorkload(Workload):
         e = self.host_chunk.shape[1]
         return int((e * CTC_T + e) * 4 + e * 4)
 
-    def config(self):
+    def public_config(self):
         return {"batch_per_gpu": self.batch, "T": CTC_T, "C": CTC_C,
                 "l2": "inputs (%.1f GB per GPU) larger than the 126 MB L2; no flush needed"
-                      % (self.batch * self.alg_bytes_per_unit() / 1e9),
-                "timed_region": "device probabilities -> kept class ids / lengths / confidences in pinned host memory",
+                      % (self.batch * self.alg_bytes_per_unit() / 1e9)}
+
+    def detail(self):
+        return {"timed_region": "device probabilities -> kept class ids / lengths / confidences in pinned host memory",
                 "e2e_region": "%d-line chunks: pinned host probabilities -> python strings" % self.host_chunk.shape[1]}
 
 
@@ -645,10 +650,12 @@ class CropWorkload(Workload):
     def d2h_bytes(self):
         return int(self.crop_bytes + self.meta_host.numel() * 4)
 
-    def config(self):
+    def public_config(self):
         return {"batch_per_gpu": self.batch, "H": H, "W": W, "boxes_per_page": CROP_BOXES,
-                "crop_bytes_per_step": self.crop_bytes,
-                "l2": "pages (%.0f MB per GPU) larger than the 126 MB L2; no flush needed" % (self.batch * H * W * 3 / 1e6),
+                "l2": "pages (%.0f MB per GPU) larger than the 126 MB L2; no flush needed" % (self.batch * H * W * 3 / 1e6)}
+
+    def detail(self):
+        return {"crop_bytes_per_step": self.crop_bytes,
                 "timed_region": "device pages + device boxes -> crops in a device arena (where the recogniser reads "
                                 "them), offsets/dims/order in pinned host memory",
                 "e2e_region": "pinned host pages + boxes -> crops in pinned host memory"}
@@ -712,7 +719,7 @@ def run_reference(args):
         "impl": "reference", "metric": wl.metric, "value": rate, "unit": wl.unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-        "config": {"workload": wl.workload, "batch_per_gpu": wl.batch, "H": H, "W": W},
+        "config": dict({"workload": wl.workload}, **wl.public_config()),
         "cpu_baseline": {"value": rate, "unit": wl.unit, "cores": cores, "kind": "port",
                          "sample": "%s x %d steps, fork pool of %d workers, cv2.setNumThreads(1); %s"
                                    % (what, args.steps, cores, note)},
@@ -844,10 +851,10 @@ def measure(wl, args, steps, L, torch, dist, dev, local_rank, world, sampler):
     k1_ms = phases[sp][1] / max(1, calls) if len(phases) > sp else None
     achieved = kernel_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms else None
     cfg = {"workload": wl.workload}
-    cfg.update(wl.config())
+    cfg.update(wl.public_config())
     return {
         "metric": wl.metric, "value": world * wl.batch * steps / (ms_dev_max * 1e-3), "unit": wl.unit,
-        "steps": steps, "ms_per_step": ms_dev_max / steps, "dtype": wl.dtype, "config": cfg,
+        "steps": steps, "ms_per_step": ms_dev_max / steps, "dtype": wl.dtype, "config": cfg, "detail": wl.detail(),
         "roofline": {"bound": "hbm", "kernel": wl.stream_kernel, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": _traffic(wl),
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
@@ -940,6 +947,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic", "config": head["config"],
+            "detail": head["detail"],
             "roofline": head["roofline"], "phases_ms": head["phases_ms"], "e2e": head["e2e"],
             "gpu_launches": head["gpu_launches"], "ms_per_step_by_rank": head["ms_per_step_by_rank"],
             "h2d_gbs_by_rank": h2d, "host_cores_per_rank": pinned,
@@ -951,7 +959,7 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_base
         if len(results) > 1:
             line["other_workloads"] = {
-                wl.name: {k: r[k] for k in ("metric", "value", "unit", "steps", "ms_per_step", "dtype", "config", "roofline",
+                wl.name: {k: r[k] for k in ("metric", "value", "unit", "steps", "ms_per_step", "dtype", "config", "detail", "roofline",
                                             "phases_ms", "e2e", "gpu_launches", "ms_per_step_by_rank")}
                 for wl, r in zip(wls[1:], results[1:])}
         print(json.dumps(line), flush=True)
