@@ -77,8 +77,12 @@ OCRPP_API void ocrpp_reset_launch_count(void);
                                 * 3 run-parallel multi-kernel chain (what large images take) */
 #define OCRPP_TUNE_DB_SPLIT 1  /* sub-batch pipelines of one DB call (0 = chosen from the batch size) */
 #define OCRPP_TUNE_DB_PRIO 2   /* 1: sub-batch pipelines without stream priorities */
-#define OCRPP_TUNE_DB_SCAN 3   /* 2: the two-phase map scan in front of the one-kernel stage 2 (db_scan3_kernel where the
-                                * width has a compile-time specialisation, else db_scan2_kernel); 3: db_scan2_kernel only */
+#define OCRPP_TUNE_DB_SCAN 3   /* map scan in front of the one-kernel stage 2. 0 auto: db_scan4_kernel (bulk-copy fed ring,
+                                * lane-contiguous chunks) when the row layout allows it, else db_scan_kernel |
+                                * 1: db_scan_kernel (warp per row, ballots) | 2: the two-phase scan (db_scan3_kernel where the
+                                * width has a compile-time specialisation, else db_scan2_kernel) | 3: db_scan2_kernel only */
+#define OCRPP_TUNE_DB_SCAN4_STAGES 4  /* ring slots per CTA of db_scan4_kernel (0 = fill 100 KB) */
+#define OCRPP_TUNE_DB_SCAN4_CTAS 5    /* CTAs per SM of db_scan4_kernel's persistent grid (0 = 2) */
 #define OCRPP_TUNE_COUNT 8
 OCRPP_API int ocrpp_set_tuning(int key, int value);
 

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libocrpp.so")
 OK = 0
 F32, F16 = 0, 1
 IMG_RUN_OVERFLOW, IMG_CANDIDATES_TRUNCATED, IMG_VALUE_OUT_OF_RANGE = 1, 2, 4
-TUNE_DB_PATH, TUNE_DB_SPLIT, TUNE_DB_PRIO, TUNE_DB_SCAN = 0, 1, 2, 3
+TUNE_DB_PATH, TUNE_DB_SPLIT, TUNE_DB_PRIO, TUNE_DB_SCAN, TUNE_DB_SCAN4_STAGES, TUNE_DB_SCAN4_CTAS = 0, 1, 2, 3, 4, 5
 DB_SEMANTICS_CPP, DB_SEMANTICS_PYTHON, DB_SCORE_POLY, DB_SCORE_BOX = 0, 1, 0, 1
 
 _lib = None

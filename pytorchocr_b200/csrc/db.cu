@@ -28,6 +28,7 @@
 #include "dev_common.cuh"
 #include "dev_geom.cuh"
 #include "geometry.cuh"
+#include "db_scan4.cuh"
 
 namespace ocrpp {
 namespace {
@@ -1728,6 +1729,20 @@ int db_pipeline(DbParams p, int N, int dtype, cudaStream_t s_scan, cudaStream_t 
   const int scan2_C = (p.W / epl + 31) / 32;
   const bool scan2 = fused && vec && !p.dilate && scan2_C <= 32 && tuning(OCRPP_TUNE_DB_SCAN) >= 2 &&
                      kScan2Warps * scan2_row_words(scan2_C, epl) * sizeof(uint32_t) <= 100 * 1024;
+  // the bulk-copy fed scan (default): same consumer and layout requirements as the two-phase scan; rows are copied as
+  // whole 16-byte cells (vec: base, strides and width are multiples of 16 bytes)
+  bool scan4_done = false;
+  if (fused && vec && !p.dilate && tuning(OCRPP_TUNE_DB_SCAN) == 0) {
+    Scan4Params q{};
+    q.maps = p.maps; q.stride_n = p.stride_n; q.stride_h = p.stride_h;
+    q.H = p.H; q.n0 = p.n0; q.nimg = N; q.cap = p.cap;
+    q.ncells = p.W / epl;
+    q.thresh = p.thresh;
+    q.scum = p.scum; q.srow_cnt = p.srow_cnt; q.imgflags = p.imgflags;
+    const int rc = dtype == OCRPP_F32 ? scan4_any<float>(q, s_scan) : scan4_any<__half>(q, s_scan);
+    if (rc > 0) return rc;
+    scan4_done = rc == OCRPP_OK;
+  }
   {
     dim3 grid((p.H + kBinWarps - 1) / kBinWarps, N);
     p.epl = vec ? epl : 1;
@@ -1747,6 +1762,7 @@ int db_pipeline(DbParams p, int N, int dtype, cudaStream_t s_scan, cudaStream_t 
         if (vec) db_scan_kernel<__half, 8, 4, true><<<grid, kBinWarps * 32, 0, s_scan>>>(p);
         else db_scan_kernel<__half, 1, 4, true><<<grid, kBinWarps * 32, 0, s_scan>>>(p);
       }
+    } else if (scan4_done) {
     } else if (scan2) {
       const int smem = kScan2Warps * scan2_row_words(scan2_C, epl) * (int)sizeof(uint32_t);
       dim3 grid2((p.H + kScan2Warps - 1) / kScan2Warps, N);

@@ -34,7 +34,7 @@ def _db_variant(rng, kw):
     from pytorchocr_b200 import _lib
     L = _lib.lib()
     path = int(rng.choice([0, 1, 2, 3]))
-    scan = int(rng.choice([0, 2]))
+    scan = int(rng.choice([0, 0, 1, 2]))
     _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_PATH, path))
     _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_SCAN, scan))
     tag = "path%d scan%d" % (path, scan)

@@ -15,17 +15,18 @@ pytestmark = pytest.mark.gpu
 CFG = dict(thresh=0.3, box_thresh=0.5, max_candidates=1000, unclip_ratio=1.7, score_mode="poly", cpp_speedup=True)
 
 
-@pytest.fixture(autouse=True, params=["image_smem", "image_global", "chain", "image_scan2"])
+@pytest.fixture(autouse=True, params=["image_smem", "image_global", "chain", "image_scan1", "image_scan2"])
 def db_path(request):
     """Every test of this module runs on each of the library's three equivalent stage-2 code paths (include/ocrpp.h
     OCRPP_TUNE_DB_PATH): one CTA per image with the tables in shared memory (the default for maps up to 4 Mpx), the
     same kernel with the tables in the global workspace (what an image takes whose tables do not fit), and the
-    run-parallel multi-kernel chain (what larger maps take). "image_scan2" runs the first behind the
-    opt-in two-phase map scan (db_scan2_kernel) instead of the single-phase db_scan_kernel."""
+    run-parallel multi-kernel chain (what larger maps take). The default map scan in front of the one-kernel stage is
+    db_scan4_kernel (bulk-copy fed); "image_scan1" runs it behind the warp-per-row db_scan_kernel (what dilation,
+    unaligned maps and the chain take), "image_scan2" behind the opt-in two-phase scan (db_scan2/3_kernel)."""
     from pytorchocr_b200 import _lib
     L = _lib.lib()
-    _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_PATH, {"image_smem": 1, "image_global": 2, "chain": 3, "image_scan2": 1}[request.param]))
-    _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_SCAN, 2 if request.param == "image_scan2" else 0))
+    _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_PATH, {"image_smem": 1, "image_global": 2, "chain": 3, "image_scan1": 1, "image_scan2": 1}[request.param]))
+    _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_SCAN, {"image_scan1": 1, "image_scan2": 2}.get(request.param, 0)))
     yield request.param
     _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_PATH, 0))
     _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_SCAN, 0))

@@ -24,16 +24,29 @@ def timeit(k=20):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); [step() for _ in range(k)]; e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / k
+def phases():
+    L.ocrpp_profile_enable(1); step(); torch.cuda.synchronize(); L.ocrpp_profile_reset()
+    for _ in range(5): step()
+    torch.cuda.synchronize(); L.ocrpp_profile_enable(0)
+    calls, ph = _lib.profile_read()
+    return {k: round(v / calls, 4) for k, v in ph}
 _lib.check(L.ocrpp_set_tuning(2, 1))
-for scan in (0, 2):
+for scan in (0, 1, 2):
     _lib.check(L.ocrpp_set_tuning(3, scan))
     for split in (1, 2):
         _lib.check(L.ocrpp_set_tuning(1, split))
         ms = timeit()
         print("scan-tuning %d split %d: %.4f ms  %.0f img/s  whole-step %.3f" % (scan, split, ms, N / ms * 1e3, N * 736 * 1280 * 4 / (ms * 1e-3) / 6546.2e9))
-_lib.check(L.ocrpp_set_tuning(1, 1)); _lib.check(L.ocrpp_set_tuning(3, 0))
-L.ocrpp_profile_enable(1); step(); torch.cuda.synchronize(); L.ocrpp_profile_reset()
-for _ in range(5): step()
-torch.cuda.synchronize(); L.ocrpp_profile_enable(0)
-calls, phases = _lib.profile_read()
-print({k: round(v / calls, 4) for k, v in phases})
+    _lib.check(L.ocrpp_set_tuning(1, 1))
+    print("   phases", phases())
+_lib.check(L.ocrpp_set_tuning(3, 0))
+# db_scan4_kernel: ring slots x CTAs per SM
+for stages in (8, 16, 24, 32):
+    for ctas in (1, 2, 3, 4):
+        if stages * 5120 * ctas > 200 * 1024: continue
+        _lib.check(L.ocrpp_set_tuning(4, stages)); _lib.check(L.ocrpp_set_tuning(5, ctas))
+        _lib.check(L.ocrpp_set_tuning(1, 1))
+        ph = phases()
+        _lib.check(L.ocrpp_set_tuning(1, 2))
+        ms = timeit()
+        print("scan4 stages %d ctas/SM %d: scan %.4f ms | step(split 2) %.4f ms %.0f img/s" % (stages, ctas, ph["db_scan"], ms, N / ms * 1e3))
