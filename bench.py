@@ -317,7 +317,7 @@ class DbWorkload(DetWorkload):
     default_batch = 256
     op_name = "DBPostProcess"
     cfg = DB_CFG
-    stream_kernel = "db_scan_kernel"
+    stream_kernel = "db_scan4_kernel"
     workload = ("DB++ r18 post-process, batch 256 synthetic 736x1280 maps with ~200 text regions each per GPU "
                 "(BASELINE.json configs[1])")
     cpu_note = ("oracle/db_oracle_fast.py = the oracle's db_postprocess.cpp semantics (cv2-python 4.13 + the reference's "
@@ -364,7 +364,7 @@ class DbFp16Workload(DbWorkload):
     dtype = "f16"
     map_dtype = "float16"
     elem_bytes = 2
-    stream_kernel = "db_scan_kernel<__half>"
+    stream_kernel = "db_scan4_kernel<__half>"
     workload = ("DB++ r18 post-process on fp16 probability maps (SURVEY 8(d) variant), batch 256 synthetic 736x1280 maps "
                 "per GPU")
 

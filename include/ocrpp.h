@@ -83,6 +83,7 @@ OCRPP_API void ocrpp_reset_launch_count(void);
                                 * width has a compile-time specialisation, else db_scan2_kernel) | 3: db_scan2_kernel only */
 #define OCRPP_TUNE_DB_SCAN4_STAGES 4  /* ring slots per CTA of db_scan4_kernel (0 = fill 100 KB) */
 #define OCRPP_TUNE_DB_SCAN4_CTAS 5    /* CTAs per SM of db_scan4_kernel's persistent grid (0 = 2) */
+#define OCRPP_TUNE_DB_IMG_SMEM_KB 6    /* dynamic shared memory of db_image_kernel in KB (0 = default) */
 #define OCRPP_TUNE_COUNT 8
 OCRPP_API int ocrpp_set_tuning(int key, int value);
 

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libocrpp.so")
+LIB_PATH = os.environ.get("OCRPP_LIB_PATH") or os.path.join(_HERE, "csrc", "libocrpp.so")   # the override is a development aid
 
 OK = 0
 F32, F16 = 0, 1

@@ -26,7 +26,10 @@
 //   cand_off[ko] slice of the hull scratch / global row extents, cand_y0[ko], cand_nrows[ko], hull_n[ko]
 #pragma once
 
-constexpr int kImgThreads = 1024;
+#ifndef OCRPP_IMG_THREADS
+#define OCRPP_IMG_THREADS 1024
+#endif
+constexpr int kImgThreads = OCRPP_IMG_THREADS;   // a multiple of 64
 
 struct ImgTables {
   int* rowptr;            // [H+1]
@@ -673,7 +676,7 @@ __device__ bool db_image_run(const DbParams& p, const int n, char* smem, const s
   // points), top-of-stack points in registers. Chains run for every candidate the non-score rules keep.
   constexpr int kHalf = kImgThreads / 2;
   for (int kb = 0; kb < ncand; kb += kHalf) {
-    const int k = kb + (tid & (kHalf - 1)), side = tid / kHalf;
+    const int side = tid / kHalf, k = kb + (tid - side * kHalf);
     int c = 0, off = 0, nrows = 0, y0 = 0, verdict = 0;   // verdict 0 dropped | 2 big | 3 hull
     int first_pt = 0, turn_pt = 0;
     if (k < ncand) {
