@@ -260,3 +260,51 @@ def test_db_host_batch_is_uploaded_in_chunks():
         assert len(got) == len(want)
         for g, w in zip(got, want):
             assert np.array_equal(g["points"], w["points"]) and np.array_equal(g["box_scores"], w["box_scores"])
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float16"])
+def test_db_scan_variants_agree_over_widths(dtype, db_path):
+    """The bulk-copy fed map scan (db_scan4_kernel: lane-contiguous chunks of 2..16 sixteen-byte cells, rows that do
+    not fill the last lanes, the widest row a 64-pixel chunk allows and the first one past it) against the
+    warp-per-row db_scan_kernel on the same maps: identical boxes, scores and counts, bit for bit. The maps hold the
+    values the fixed-point trick treats specially (0, -0, 1, the threshold itself, its two neighbours)."""
+    import torch
+    from pytorchocr_b200 import _lib
+    if db_path != "image_smem":
+        pytest.skip("compares the two scans itself")
+    L = _lib.lib()
+    H = 40
+    rng = np.random.default_rng(11)
+    th = np.float32(0.3)
+    special = np.array([0.0, -0.0, 1.0, th, np.nextafter(th, np.float32(1)), np.nextafter(th, np.float32(0))], np.float32)
+    op = _op()
+    for W in (8, 40, 120, 128, 136, 640, 1288, 2040, 2048, 2056):
+        base = cv2.GaussianBlur(rng.random((H, W)).astype(np.float32), (0, 0), 2.0)
+        base = (base - base.min()) / (base.max() - base.min())
+        pick = rng.random((H, W)) < 0.05
+        base[pick] = rng.choice(special, size=int(pick.sum()))
+        maps = torch.from_numpy(base[None, None]).cuda()
+        if dtype == "float16":
+            maps = maps.half()
+        sl = np.array([[H, W, 1.0, 1.0]])
+        out = []
+        for scan in (0, 1):
+            _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_SCAN, scan))
+            boxes, scores, counts, status, _ = op.run_device(maps, sl)
+            out.append((boxes.copy(), scores.copy(), counts.copy(), status.copy()))
+        _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_SCAN, 0))
+        for a, b in zip(*out):
+            assert np.array_equal(a, b), "scan variants differ at W=%d" % W
+        assert not (int(out[0][3][0]) & _lib.IMG_VALUE_OUT_OF_RANGE)
+    # a value above 1 and a negative value are reported by both scans; a negative value that rounds away in `f + 1.0f` is not
+    for bad, ok in ((np.float32(1.001), False), (np.float32(-1e-3), False), (np.float32(-1e-12), True)):
+        m = np.full((1, 1, H, 128), 0.6, np.float32)
+        m[0, 0, 7, 77] = bad
+        for scan in (0, 1):
+            _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_SCAN, scan))
+            if ok:
+                op({"maps": torch.from_numpy(m).cuda()}, np.array([[H, 128, 1.0, 1.0]]))
+            else:
+                with pytest.raises(_lib.OcrppError):
+                    op({"maps": torch.from_numpy(m).cuda()}, np.array([[H, 128, 1.0, 1.0]]))
+        _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_SCAN, 0))
