@@ -153,6 +153,14 @@ __global__ void __launch_bounds__(kS4Threads) db_scan4_kernel(Scan4Params p) {
     const int r = r0 + i;
     s4_mbar_wait(full0 + 8u * slot, par);
     const uint4* rowp = reinterpret_cast<const uint4*>(ring + (size_t)slot * row_bytes) + lane * kCells;
+#ifdef OCRPP_S4_DRAIN_ONLY   // tools/micro/scan4_bench.cu: the consumers only drain the ring (its own streaming rate)
+    if (rowp[0].x == 0x7fc00001u) p.srow_cnt[r] = 1;
+    __syncwarp();
+    if (lane == 0) s4_mbar_arrive(empty0 + 8u * slot);
+    slot += kS4Warps;
+    if (slot >= stages) { slot -= stages; par ^= 1u; }
+    continue;
+#endif
     uint4 raw[kCells];
 #pragma unroll
     for (int c = 0; c < kCells; ++c) {
