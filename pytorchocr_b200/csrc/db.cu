@@ -1323,7 +1323,7 @@ __global__ void __launch_bounds__(kGeoWarps * 32) db_geometry_big_kernel(DbParam
 // projections, points packed as short2 in shared memory. Candidates that do not fit its fixed
 // buffers are appended to the per-image `big` list and handled by db_geometry_big_kernel.
 // ------------------------------------------------------------------------------------------------
-constexpr int kGeoThreads = 128;              // 16 candidates per CTA
+constexpr int kGeoThreads = 16 * kGrp;              // 16 candidates per CTA
 constexpr int kFastRows = 64;                 // max rows of a candidate's point set
 constexpr int kFastOff = 96;                  // max points of its unclip polygon
 

@@ -1161,7 +1161,7 @@ __global__ void __launch_bounds__(kRunThreads) ex_cand_kernel(ExParams p) {
 // then hull -> min-area rectangle -> corner order -> rescale for labels of up to kFastRows rows, FOUR
 // labels per warp (groups of 8 lanes, 32-bit integer projections, points packed in shared memory).
 constexpr int kFastRows = 128;
-constexpr int kGeoThreads = 128;
+constexpr int kGeoThreads = 16 * kGrp;
 
 __device__ __forceinline__ void ex_emit_box(const ExParams& p, int n, size_t ko, const geom::Rect& rect, float score) {
   double bx[4], by[4];
