@@ -1218,15 +1218,17 @@ constexpr int kSmallRows = 64;              // candidates up to this many rows b
 constexpr int kOffCap = 320;                // capacity of the unclip polygon (points)
 
 
-__global__ void __launch_bounds__(kGeoWarps * 32) db_geometry_big_kernel(DbParams p) {
+// The candidates db_geometry_kernel deferred (point sets or unclip polygons that do not fit its fixed buffers; rare):
+// one warp per candidate, generic buffers. Runs on the first kGeoWarps warps of db_compact_kernel's CTA, before the
+// compaction (a launch of its own cost 6 us per step for a list that is almost always empty).
+__device__ __forceinline__ void db_geometry_big_run(const DbParams& p, const int n) {
   __shared__ P2i s_pts[kGeoWarps][2 * kSmallRows];
   __shared__ P2i s_hull[kGeoWarps][2 * kSmallRows + 2];
   __shared__ P2i s_off[kGeoWarps][kOffCap];
   __shared__ P2i s_offh[kGeoWarps][kOffCap + 2];
-  const int n = blockIdx.y + p.n0;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nbig = min(p.nbig[n], p.maxc);
-  for (int bi = blockIdx.x * kGeoWarps + wib; bi < nbig; bi += gridDim.x * kGeoWarps) {
+  for (int bi = wib; bi < nbig; bi += kGeoWarps) {
   const int k = p.big[(size_t)n * p.maxc + bi];
   const size_t ko = (size_t)n * p.maxc + k;
   if (lane == 0) p.res_keep[ko] = 0;
@@ -1321,17 +1323,21 @@ __global__ void __launch_bounds__(kGeoWarps * 32) db_geometry_big_kernel(DbParam
 // ------------------------------------------------------------------------------------------------
 // K9: per-candidate geometry, FOUR candidates per warp (groups of 8 lanes), 32-bit integer
 // projections, points packed as short2 in shared memory. Candidates that do not fit its fixed
-// buffers are appended to the per-image `big` list and handled by db_geometry_big_kernel.
+// buffers are appended to the per-image `big` list and handled by db_geometry_big_run.
 // ------------------------------------------------------------------------------------------------
 constexpr int kGeoThreads = 16 * kGrp;              // 16 candidates per CTA
 constexpr int kFastRows = 64;                 // max rows of a candidate's point set
-constexpr int kFastOff = 96;                  // max points of its unclip polygon
+constexpr int kFastOff = 64;                  // max points of its unclip polygon. A candidate of this path is at most kFastRows
+                                              // rows high, so its unclip distance (area * ratio / perimeter < 0.85 * height at
+                                              // ratio 1.7) stays below ~55 px and the four round joins make <= 40 points;
+                                              // anything longer is deferred. Each point is 8 bytes of the group's shared memory:
+                                              // 96 -> 64 points = 7 -> 8 CTAs per SM (0.118 -> 0.101 ms)
 
 
 // K9a: candidate triage + convex hull of the row extents, ONE THREAD per candidate (the monotone chain is
 // sequential: with a thread per candidate a warp advances 32 hulls at once instead of 4). The hull is
 // written, packed, to the candidate's slice of the hull scratch; res_keep carries the verdict:
-// 0 dropped, 2 deferred to db_geometry_big_kernel, 3 hull ready (hull_n vertices).
+// 0 dropped, 2 deferred to db_geometry_big_run, 3 hull ready (hull_n vertices).
 constexpr int kHullThreads = 64;
 
 __global__ void __launch_bounds__(kHullThreads) db_hull_kernel(DbParams p) {
@@ -1561,6 +1567,10 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
 // K10: ordered compaction of the kept boxes, one CTA per image.
 __global__ void __launch_bounds__(kRunThreads) db_compact_kernel(DbParams p) {
   const int n = blockIdx.x + p.n0;
+  if (p.nbig[n] > 0) {   // uniform over the CTA
+    if ((threadIdx.x >> 5) < kGeoWarps) db_geometry_big_run(p, n);
+    __syncthreads();
+  }
   const int nc = p.ncand[n];
   const size_t ko = (size_t)n * p.maxc;
   const int chunk = (nc + kRunThreads - 1) / kRunThreads;
@@ -1870,9 +1880,6 @@ int db_pipeline(DbParams p, int N, int dtype, cudaStream_t s_scan, cudaStream_t 
     db_geometry_kernel<<<grid, kGeoThreads, 0, s>>>(p);
     OCRPP_LAUNCHED();
     if (prof) prof->mark("db_geometry");
-    db_geometry_big_kernel<<<dim3(2, N), kGeoWarps * 32, 0, s>>>(p);
-    OCRPP_LAUNCHED();
-    if (prof) prof->mark("db_geometry_big");
   }
   db_compact_kernel<<<N, kRunThreads, 0, s>>>(p);
   OCRPP_LAUNCHED();

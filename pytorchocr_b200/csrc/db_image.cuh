@@ -22,7 +22,7 @@
 //   * the two monotone chains of a candidate's hull run in place in its row-extent arrays, one thread each.
 //
 // Results handed to db_geometry_kernel, per candidate k (cv2 order) of image n, ko = n * maxc + k:
-//   res_keep[ko] 0 dropped | 2 deferred to db_geometry_big_kernel | 3 hull ready,  res_score[ko] BoxScore,
+//   res_keep[ko] 0 dropped | 2 deferred to db_geometry_big_run | 3 hull ready,  res_score[ko] BoxScore,
 //   cand_off[ko] slice of the hull scratch / global row extents, cand_y0[ko], cand_nrows[ko], hull_n[ko]
 #pragma once
 
@@ -744,7 +744,7 @@ __device__ bool db_image_run(const DbParams& p, const int n, char* smem, const s
         }
         cntk = kk;
       }
-    } else if (verdict == 2 && kSmem) {   // db_geometry_big_kernel reads the row extents from the global workspace
+    } else if (verdict == 2 && kSmem) {   // db_geometry_big_run reads the row extents from the global workspace
       int* g = (side ? p.ext_r : p.ext_l) + (size_t)n * p.E + off;
       const int* e = (side ? t.ext_r : t.ext_l) + off;
       for (int j = 0; j < nrows; ++j) g[j] = e[j];
