@@ -1327,11 +1327,11 @@ __device__ __forceinline__ void db_geometry_big_run(const DbParams& p, const int
 // ------------------------------------------------------------------------------------------------
 constexpr int kGeoThreads = 16 * kGrp;              // 16 candidates per CTA
 constexpr int kFastRows = 64;                 // max rows of a candidate's point set
-constexpr int kFastOff = 64;                  // max points of its unclip polygon. A candidate of this path is at most kFastRows
+constexpr int kFastOff = 48;                  // max points of its unclip polygon. A candidate of this path is at most kFastRows
                                               // rows high, so its unclip distance (area * ratio / perimeter < 0.85 * height at
                                               // ratio 1.7) stays below ~55 px and the four round joins make <= 40 points;
-                                              // anything longer is deferred. Each point is 8 bytes of the group's shared memory:
-                                              // 96 -> 64 points = 7 -> 8 CTAs per SM (0.118 -> 0.101 ms)
+                                              // anything longer is deferred. The group's shared memory decides how many CTAs an
+                                              // SM holds: 96 points of 8 bytes -> 64 -> 48 packed points of 4 bytes = 7 -> 8 -> 11
 
 
 // K9a: candidate triage + convex hull of the row extents, ONE THREAD per candidate (the monotone chain is
@@ -1439,7 +1439,7 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
   constexpr int kGroups = kGeoThreads / kGrp;
   __shared__ int s_a[kGroups][2 * kFastRows];        // sorted unclip polygon
   __shared__ int s_b[kGroups][2 * kFastRows + 2];    // hull
-  __shared__ P2i s_off[kGroups][kFastOff];           // raw unclip polygon
+  __shared__ int s_off[kGroups][kFastOff];           // raw unclip polygon, points packed x | y << 16
   const int n = blockIdx.y + p.n0;
   const int g = threadIdx.x / kGrp, gl = threadIdx.x % kGrp;
   const unsigned gmask = ((1u << kGrp) - 1u) << ((threadIdx.x & 31) / kGrp * kGrp);
@@ -1503,15 +1503,14 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
   // rank sort by (y, x, index) into A: every lane ranks its own points against all of them (one packed key per point:
   // coordinates are within +-16384 on this path)
   for (int i = gl; i < m; i += kGrp) {
-    const P2i q = s_off[g][i];
-    const unsigned kq = ((unsigned)(q.y + 16384) << 16) | (unsigned)(q.x + 16384);
+    const int q = s_off[g][i];
+    const unsigned kq = (unsigned)q ^ 0x80008000u;   // both signed halves biased: unsigned order = (y, x) order
     int rank = 0;
     for (int j = 0; j < m; ++j) {
-      const P2i o = s_off[g][j];
-      const unsigned ko = ((unsigned)(o.y + 16384) << 16) | (unsigned)(o.x + 16384);
+      const unsigned ko = (unsigned)s_off[g][j] ^ 0x80008000u;
       rank += (ko < kq || (ko == kq && j < i)) ? 1 : 0;
     }
-    A[rank] = pk(q.x, q.y);
+    A[rank] = q;
   }
   __syncwarp(gmask);
   // monotone chain (same result as hull_sorted32): its two passes are independent - the second starts from the last
@@ -1520,7 +1519,7 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
   // turn is not strictly left. Lane 0's stack is B[1..], lane 1's goes to the (dead) raw polygon buffer.
   int hm = 0;
   {
-    int* S = gl == 0 ? B + 1 : reinterpret_cast<int*>(s_off[g]);
+    int* S = gl == 0 ? B + 1 : s_off[g];
     int cnt = 0;
     if (gl < 2) {
       const int dir = gl;
@@ -1540,7 +1539,7 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
     const int k1 = 1 + c1;
     hm = k1 > 1 ? k1 + c2 - 1 : 1;
     __syncwarp(gmask);
-    const int* S2 = reinterpret_cast<const int*>(s_off[g]);
+    const int* S2 = s_off[g];
     for (int j = gl; j < c2 - 1; j += kGrp) B[k1 + j] = S2[j];
   }
   __syncwarp(gmask);

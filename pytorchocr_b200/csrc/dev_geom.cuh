@@ -220,7 +220,8 @@ __device__ void group_min_area_rect(const int* h, int n, geom::Rect* r, int gl, 
 // Anything off the common path (fewer than 4 distinct points, a near-straight corner that Clipper skips
 // without advancing k, near-zero delta) takes the sequential routine on lane 0. Returns the point count
 // on every lane (-1: cap too small).
-__device__ int group_do_offset_quad(const P2i* quad, double delta, P2i* out, int cap, int gl, unsigned gmask) {
+// `out` receives the points packed as x | y << 16 (coordinates of this path are within +-16384 plus the distance).
+__device__ int group_do_offset_quad(const P2i* quad, double delta, int* out, int cap, int gl, unsigned gmask) {
   const double kPi = 3.141592653589793238, kTwoPi = kPi * 2;
   bool serial = false;
   // AddPath duplicate stripping (clipper.cpp:3845-3864): the parallel path needs 4 distinct points
@@ -289,7 +290,7 @@ __device__ int group_do_offset_quad(const P2i* quad, double delta, P2i* out, int
   serial |= (__ballot_sync(gmask, gl < 4 && kind == 0) & gmask) != 0;
   if (serial) {
     int m = 0;
-    if (gl == 0) m = geom::do_offset_quad(quad, delta, out, cap);
+    if (gl == 0) m = geom::do_offset_quad_t(quad, delta, geom::PackedOut{out}, cap);
     return __shfl_sync(gmask, m, (threadIdx.x & 31) & ~(kGrp - 1));
   }
   const int cnt = gl < 4 ? (kind == 2 ? 3 : ns + 1) : 0;
@@ -304,20 +305,20 @@ __device__ int group_do_offset_quad(const P2i* quad, double delta, P2i* out, int
   if (total > cap) return -1;
   auto ofs = [delta](int cc, double nn) { return (int)geom::clipper_round(geom::dadd((double)cc, geom::dmul(nn, delta))); };
   if (gl < 4) {
-    P2i* o = out + off;
+    int* o = out + off;
     if (kind == 2) {
-      o[0] = P2i{ofs(c[j].x, nkx), ofs(c[j].y, nky)};
-      o[1] = c[j];
-      o[2] = P2i{ofs(c[j].x, njx), ofs(c[j].y, njy)};
+      o[0] = pk(ofs(c[j].x, nkx), ofs(c[j].y, nky));
+      o[1] = pk(c[j].x, c[j].y);
+      o[2] = pk(ofs(c[j].x, njx), ofs(c[j].y, njy));
     } else {
       double X = nkx, Y = nky;
       for (int i = 0; i < ns; ++i) {
-        o[i] = P2i{ofs(c[j].x, X), ofs(c[j].y, Y)};
+        o[i] = pk(ofs(c[j].x, X), ofs(c[j].y, Y));
         const double X2 = X;
         X = geom::dsub(geom::dmul(X, m_cos), geom::dmul(m_sin, Y));
         Y = geom::dadd(geom::dmul(X2, m_sin), geom::dmul(Y, m_cos));
       }
-      o[ns] = P2i{ofs(c[j].x, njx), ofs(c[j].y, njy)};
+      o[ns] = pk(ofs(c[j].x, njx), ofs(c[j].y, njy));
     }
   }
   return total;

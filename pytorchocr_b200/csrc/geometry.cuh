@@ -337,7 +337,17 @@ OCRPP_HD long long clipper_round(double v) { return v < 0 ? (long long)(v - 0.5)
 // ClipperOffset for ONE closed polygon of 4 integer points, jtRound, ArcTolerance 0.25.
 // Writes the raw m_destPoly into out[0..cap) and returns the number of points, 0 when AddPath
 // rejects the path (< 3 distinct points), or -1 when cap is too small.
-OCRPP_HD int do_offset_quad(const P2i* quad, double delta, P2i* out, int cap) {
+// (`Out` stores point i: P2iOut into a P2i array; PackedOut as x | y << 16 for coordinates within +-32767)
+struct P2iOut {
+  P2i* p;
+  OCRPP_HD void set(int i, int x, int y) const { p[i].x = x; p[i].y = y; }
+};
+struct PackedOut {
+  int* p;
+  OCRPP_HD void set(int i, int x, int y) const { p[i] = (x & 0xffff) | (int)((unsigned)y << 16); }
+};
+template <typename Out>
+OCRPP_HD int do_offset_quad_t(const P2i* quad, double delta, Out out, int cap) {
   const double kPi = 3.141592653589793238, kTwoPi = kPi * 2;
   P2i c[4];
   int high = 3;
@@ -363,7 +373,7 @@ OCRPP_HD int do_offset_quad(const P2i* quad, double delta, P2i* out, int cap) {
   }
   if (delta > -1e-20 && delta < 1e-20) {  // NEAR_ZERO :3993-4003
     if (n > cap) return -1;
-    for (int i = 0; i < n; ++i) out[i] = c[i];
+    for (int i = 0; i < n; ++i) out.set(i, c[i].x, c[i].y);
     return n;
   }
   const double ad = fabs(delta);
@@ -392,8 +402,7 @@ OCRPP_HD int do_offset_quad(const P2i* quad, double delta, P2i* out, int cap) {
 #define OCRPP_EMIT(X, Y)                                  \
   do {                                                    \
     if (m >= cap) return -1;                              \
-    out[m].x = (int)(X);                                  \
-    out[m].y = (int)(Y);                                  \
+    out.set(m, (int)(X), (int)(Y));                       \
     ++m;                                                  \
   } while (0)
   for (int j = 0; j < n; ++j) {  // OffsetPoint :4160-4201
@@ -428,6 +437,9 @@ OCRPP_HD int do_offset_quad(const P2i* quad, double delta, P2i* out, int cap) {
 #undef OCRPP_EMIT
 #undef OCRPP_OFS
   return m;
+}
+OCRPP_HD int do_offset_quad(const P2i* quad, double delta, P2i* out, int cap) {
+  return do_offset_quad_t(quad, delta, P2iOut{out}, cap);
 }
 
 // In-place lexicographic (y, x) insertion sort; offset polygons have a few dozen points.
