@@ -557,6 +557,7 @@ __device__ bool db_image_run(const DbParams& p, const int n, char* smem, const s
         if (twice) bg_run(2 * i + 1);
       }
     }
+    IMG_CLK(15);
     // (b) hole runs (background, not the outside region; few): ring pixels - each counted once, owner = the first of
     //     its up / left / right / down neighbours that lies in the hole - with their row extents, and (c) the stair
     //     pixels of the hole contour. One WARP per hole run: lanes take the pixels of the run (one thread walking a
@@ -575,6 +576,7 @@ __device__ bool db_image_run(const DbParams& p, const int n, char* smem, const s
     __syncthreads();
     const int nhole = s_etot;
     const bool listed = nhole <= hcap;
+    IMG_CLK(16);
     for (int w = warp; w < (listed ? nhole : nwords); w += nw) {
       const int rr = w * 32 + lane;
       const bool hole = !listed && rr < nr && !(t.yf[rr] >> 15) && ~t.par[rr] != cout;
@@ -750,6 +752,7 @@ __device__ bool db_image_run(const DbParams& p, const int n, char* smem, const s
       for (int j = 0; j < nrows; ++j) g[j] = e[j];
     }
     if (k < ncand) t.hcnt[side * p.maxc + k] = cntk;
+    if (kb == 0) IMG_CLK(17);
     if (kb == 0) {
       // the pixels requested above have arrived by now; further ones (more than kU per thread) in the plain way
 #pragma unroll
@@ -767,6 +770,7 @@ __device__ bool db_image_run(const DbParams& p, const int n, char* smem, const s
       }
     }
     __syncthreads();   // chain lengths, chains in place, fill sums complete
+    if (kb == 0) IMG_CLK(18);
     if (k < ncand) {
       const size_t ko = (size_t)n * p.maxc + k;
       // BoxScore: a low score drops the candidate whatever its rectangle is
