@@ -1231,29 +1231,41 @@ __device__ __forceinline__ void db_geometry_big_run(const DbParams& p, const int
   for (int bi = wib; bi < nbig; bi += kGeoWarps) {
   const int k = p.big[(size_t)n * p.maxc + bi];
   const size_t ko = (size_t)n * p.maxc + k;
+  // 2: deferred by the triage (db_image_kernel / db_hull_kernel; its row extents are in the global workspace),
+  // 4: deferred by db_geometry_kernel (its hull is ready in p.hull, packed points, at most 2 * kFastRows + 2 of them)
+  const int how = p.res_keep[ko];
+  __syncwarp();
   if (lane == 0) p.res_keep[ko] = 0;
   // triaged by db_image_kernel / db_hull_kernel: <= 2-point rule and (score_mode poly) BoxScore passed
   const int off = p.cand_off[ko], nrows = p.cand_nrows[ko], y0 = p.cand_y0[ko];
-  const int32_t* ext_l = p.ext_l + (size_t)n * p.E + off;
-  const int32_t* ext_r = p.ext_r + (size_t)n * p.E + off;
-  P2i* pts;
   P2i* hull;
-  if (nrows <= kSmallRows) {
-    pts = s_pts[wib];
-    hull = s_hull[wib];
-  } else {
-    pts = p.hull + ((size_t)n * p.E + off) * 4;
-    hull = pts + 2 * nrows;
-  }
-  for (int i = lane; i < nrows; i += 32) {
-    pts[2 * i] = P2i{ext_l[i], y0 + i};
-    pts[2 * i + 1] = P2i{ext_r[i], y0 + i};
-  }
-  __syncwarp();
   int hn = 0;
-  if (lane == 0) hn = geom::hull_sorted(pts, 2 * nrows, hull);
-  hn = __shfl_sync(0xffffffffu, hn, 0);
-  __syncwarp();
+  if (how == 4) {
+    hull = s_hull[wib];
+    hn = min(p.hull_n[ko], 2 * kSmallRows + 2);
+    const int* gh = reinterpret_cast<const int*>(p.hull + ((size_t)n * p.E + off) * 4);
+    for (int i = lane; i < hn; i += 32) hull[i] = P2i{pkx(gh[i]), pky(gh[i])};
+    __syncwarp();
+  } else {
+    const int32_t* ext_l = p.ext_l + (size_t)n * p.E + off;
+    const int32_t* ext_r = p.ext_r + (size_t)n * p.E + off;
+    P2i* pts;
+    if (nrows <= kSmallRows) {
+      pts = s_pts[wib];
+      hull = s_hull[wib];
+    } else {
+      pts = p.hull + ((size_t)n * p.E + off) * 4;
+      hull = pts + 2 * nrows;
+    }
+    for (int i = lane; i < nrows; i += 32) {
+      pts[2 * i] = P2i{ext_l[i], y0 + i};
+      pts[2 * i + 1] = P2i{ext_r[i], y0 + i};
+    }
+    __syncwarp();
+    if (lane == 0) hn = geom::hull_sorted(pts, 2 * nrows, hull);
+    hn = __shfl_sync(0xffffffffu, hn, 0);
+    __syncwarp();
+  }
 
   geom::Rect rect;
   warp_min_area_rect(hull, hn, &rect, lane);
@@ -1327,6 +1339,7 @@ __device__ __forceinline__ void db_geometry_big_run(const DbParams& p, const int
 // ------------------------------------------------------------------------------------------------
 constexpr int kGeoThreads = 16 * kGrp;              // 16 candidates per CTA
 constexpr int kFastRows = 64;                 // max rows of a candidate's point set
+constexpr int kFastPts = 64;                  // max vertices of its hull, and max rows of its mini box in score_mode box
 constexpr int kFastOff = 48;                  // max points of its unclip polygon. A candidate of this path is at most kFastRows
                                               // rows high, so its unclip distance (area * ratio / perimeter < 0.85 * height at
                                               // ratio 1.7) stays below ~55 px and the four round joins make <= 40 points;
@@ -1437,8 +1450,8 @@ __global__ void __launch_bounds__(kHullThreads) db_hull_kernel(DbParams p) {
 
 __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
   constexpr int kGroups = kGeoThreads / kGrp;
-  __shared__ int s_a[kGroups][2 * kFastRows];        // sorted unclip polygon
-  __shared__ int s_b[kGroups][2 * kFastRows + 2];    // hull
+  __shared__ int s_a[kGroups][kFastPts];             // sorted unclip polygon | fill rows of score_mode box
+  __shared__ int s_b[kGroups][kFastPts + 2];         // hull
   __shared__ int s_off[kGroups][kFastOff];           // raw unclip polygon, points packed x | y << 16
   const int n = blockIdx.y + p.n0;
   const int g = threadIdx.x / kGrp, gl = threadIdx.x % kGrp;
@@ -1451,8 +1464,11 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
   if (gl == 0) p.res_keep[ko] = 0;
   float score = p.res_score[ko];
   const int off = p.cand_off[ko];
+  // hand the candidate to db_geometry_big_run (generic buffers). Mark 4 = "its hull is ready in p.hull": the row
+  // extents it was built from may live only in db_image_kernel's shared memory, so they cannot be read again
   auto defer = [&]() {
     if (gl == 0) {
+      p.res_keep[ko] = 4;
       const int slot = atomicAdd(&p.nbig[n], 1);
       if (slot < p.maxc) p.big[(size_t)n * p.maxc + slot] = k;
     }
@@ -1460,6 +1476,10 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
   int* A = s_a[g];
   int* B = s_b[g];
   const int hn = p.hull_n[ko];
+  if (hn > kFastPts) {   // a hull of more points than the group's buffer (a near-ellipse 33+ rows high)
+    defer();
+    return;
+  }
   {
     const int* hull = reinterpret_cast<const int*>(p.hull + ((size_t)n * p.E + off) * 4);
     for (int i = gl; i < hn; i += kGrp) B[i] = hull[i];
@@ -1478,7 +1498,7 @@ __global__ void __launch_bounds__(kGeoThreads) db_geometry_kernel(DbParams p) {
   if (p.score_box) {
     int bxmin, bymin, bw, bh, qx[4], qy[4];
     geom::box_score_quad(mx, my, p.W, p.H, &bxmin, &bymin, &bw, &bh, qx, qy);
-    if (bh > 2 * kFastRows) {
+    if (bh > kFastPts) {
       defer();
       return;
     }

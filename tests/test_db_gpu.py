@@ -308,3 +308,22 @@ def test_db_scan_variants_agree_over_widths(dtype, db_path):
                 with pytest.raises(_lib.OcrppError):
                     op({"maps": torch.from_numpy(m).cuda()}, np.array([[H, 128, 1.0, 1.0]]))
         _lib.check(L.ocrpp_set_tuning(_lib.TUNE_DB_SCAN, 0))
+
+
+@pytest.mark.parametrize("ratio", [3.0, 5.0, 8.0])
+def test_db_large_unclip_ratio_defers_to_the_generic_path(ratio):
+    """Unclip polygons with more points than the per-candidate buffer of db_geometry_kernel (tall regions offset by a
+    large distance: Clipper's round joins grow with the distance) are handed to the generic routine AFTER their hull was
+    built - from that hull, not from row extents that only ever lived in the stage-2 kernel's shared memory."""
+    H, W = 256, 512
+    m = np.full((2, 1, H, W), 0.05, np.float32)
+    rng = np.random.default_rng(3)
+    for n in range(2):
+        for i in range(4):
+            x0, y0 = 40 + 110 * i, 40 + 30 * n
+            h, w = 44 + 5 * i, 70 + 6 * i
+            m[n, 0, y0:y0 + h, x0:x0 + w] = 0.9
+            m[n, 0, y0 + 3:y0 + 6, x0 + w:x0 + w + 9] = 0.85          # a bump: not a plain rectangle
+        m[n, 0, 180:190, 30:480] = 0.8                                  # a long thin line
+    m += rng.random(m.shape).astype(np.float32) * 0.04
+    _check(m, np.array([[H, W, 1.0, 1.0]] * 2), unclip_ratio=ratio, loose=0.3)
