@@ -1214,7 +1214,9 @@ __device__ __forceinline__ void db_store_corner(const DbParams& p, size_t ko, in
 }
 
 constexpr int kGeoWarps = 4;
-constexpr int kSmallRows = 64;              // candidates up to this many rows build their hull in smem
+constexpr int kSmallRows = 128;             // candidates up to this many rows build their hull in smem (taller ones: in the global
+                                            // workspace, one lane walking it - ~100 us for a single candidate, which then is the
+                                            // whole step's tail: the slow rank of the 4- and 8-GPU runs had one such page)
 constexpr int kOffCap = 320;                // capacity of the unclip polygon (points)
 
 

@@ -30,6 +30,7 @@
 #define OCRPP_IMG_THREADS 1024
 #endif
 constexpr int kImgThreads = OCRPP_IMG_THREADS;   // a multiple of 64
+constexpr int kImgChainRows = 512;               // tallest candidate whose hull is built here (in place, two threads)
 
 struct ImgTables {
   int* rowptr;            // [H+1]
@@ -696,7 +697,11 @@ __device__ bool db_image_run(const DbParams& p, const int n, char* smem, const s
       }
       nrows = fg ? (ymax - y_first + 1) : (ymax - y_first + 3);
       y0 = fg ? y_first : y_first - 1;
-      if (verdict && (nrows > kFastRows || W >= 16384 || H >= 16384)) verdict = 2;
+      // The chains run in place in the extent arrays, whatever the candidate's height; db_geometry_kernel takes any
+      // hull of up to kFastPts vertices. Only very tall candidates go to the generic routine (one warp, mostly one
+      // lane: ~100 us for a single candidate, which is then the tail of the whole step - with the limit at 64 rows
+      // one 65-row blob on one page of a 256-page batch cost that rank 20 % of its step).
+      if (verdict && (nrows > kImgChainRows || W >= 16384 || H >= 16384)) verdict = 2;
       if (verdict == 3) {
         IMG_CHK(off >= 0 && off + nrows < etot + 1 && nrows >= 1);
         first_pt = pk(t.ext_l[off], y0);                            // out[0] of the chain
