@@ -327,3 +327,53 @@ def test_db_large_unclip_ratio_defers_to_the_generic_path(ratio):
         m[n, 0, 180:190, 30:480] = 0.8                                  # a long thin line
     m += rng.random(m.shape).astype(np.float32) * 0.04
     _check(m, np.array([[H, W, 1.0, 1.0]] * 2), unclip_ratio=ratio, loose=0.3)
+
+
+def test_db_call_is_cuda_graph_capturable(db_path):
+    """One ocrpp_db_postprocess call (memset, fork / join onto the library's auxiliary streams, all kernels) can be
+    captured into a CUDA graph and replayed - what bench.py does for the batch-256 step, and what a serving loop
+    would do. Replays on new map contents give the same outputs as direct calls."""
+    import torch
+    from pytorchocr_b200 import _lib
+    L = _lib.lib()
+    N, H, W = 64, 96, 160            # >= 64 images: the call forks into two sub-batch pipelines
+    op = _op()
+    sl = np.array([[H, W, 1.0, 1.0]] * N)
+    a = torch.from_numpy(synth.db_batch(N, seed=71, H=H, W=W)).cuda()
+    b = torch.from_numpy(synth.db_batch(N, seed=72, H=H, W=W)).cuda()
+    maps = a.clone()
+    op.run_device(maps, sl)                      # allocates and caches the buffers for this shape
+    buf = next(iter(op._cache.values())); key = next(iter(op._cache))
+    o_box, o_sc, o_cnt, o_st = buf["offs"]
+    base = buf["out_dev"].data_ptr()
+
+    def call(stream):
+        _lib.check(L.ocrpp_db_postprocess(maps.data_ptr(), _lib.F32, N, H, W, maps.stride(0), maps.stride(2),
+                                          buf["wh_dev"].data_ptr(), CFG["thresh"], CFG["box_thresh"], CFG["unclip_ratio"],
+                                          key[5], key[4], 0, 0, base + o_box, base + o_sc, base + o_cnt, base + o_st,
+                                          None, None, buf["ws"].data_ptr(), buf["ws_bytes"], stream.cuda_stream))
+
+    def direct(src):
+        maps.copy_(src)
+        call(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        return buf["out_dev"].cpu().numpy().copy()
+
+    want_a, want_b = direct(a), direct(b)
+    assert not np.array_equal(want_a, want_b)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        call(torch.cuda.current_stream())
+    for src, want in ((a, want_a), (b, want_b), (a, want_a)):
+        maps.copy_(src)
+        buf["out_dev"].zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        got = buf["out_dev"].cpu().numpy()
+        nb = o_sc   # boxes region; scores / counts / status follow
+        cnt = got[o_cnt:o_cnt + 4 * N].view(np.int32)
+        assert np.array_equal(cnt, want[o_cnt:o_cnt + 4 * N].view(np.int32))
+        cap = key[5]
+        gb, wb = got[:nb].view(np.int16).reshape(N, cap, 8), want[:nb].view(np.int16).reshape(N, cap, 8)
+        for n in range(N):
+            assert np.array_equal(gb[n, :cnt[n]], wb[n, :cnt[n]])
